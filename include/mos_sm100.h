@@ -41,7 +41,7 @@ typedef struct mos_gemm_args {
   const void* A;          /* bf16 [M, lda]; conv: NHWC activation [B, H, Wd, C] */
   const void* W;          /* bf16 [N, Kw], K contiguous; conv: [N, 9*C] with k = (kh*3+kw)*C + c */
   int64_t M, N, K;        /* K = C for conv (reduction per tap) */
-  int64_t lda;            /* row pitch of A in elements (plain mode) */
+  int64_t lda;            /* row pitch of A in elements (conv: pixel pitch, >= C) */
   int32_t conv;           /* 0 = plain GEMM, 1 = 3x3 / stride 1 / pad 1 convolution */
   int32_t B, H, Wd, C;    /* conv geometry */
   int32_t splits;         /* split-K factor, >= 1; > 1 requires `partial` and forbids lora / geglu / heads */
@@ -50,6 +50,7 @@ typedef struct mos_gemm_args {
   const float* bias;      /* [N] or NULL */
   const float* bias_batch;/* [nbatch, N] or NULL; row m uses batch m / rows_per_batch (resnet temb add) */
   int64_t rows_per_batch;
+  int64_t bias_batch_ld;  /* row pitch of bias_batch in elements (0 = N) */
   const void* residual;   /* bf16 [M, ldr] or NULL, added last */
   int64_t ldr;
   int32_t geglu;          /* 1: tile columns are [80 x a | 80 x gate]; writes a*gelu(gate), N_out = N/2 */

@@ -25,6 +25,7 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;               // 16384
 constexpr int B_STAGE_BYTES = BN * BK * 2;               // 20480
 constexpr int L_STAGE_BYTES = LORA_N * BK * 2;           // 2048
 constexpr int TMEM_COLS = 256;
+constexpr int MAX_DYN_SMEM = 227 * 1024 - 2048;  // leave room for the static barriers
 
 struct GemmDev {
   int M, N;
@@ -40,6 +41,7 @@ struct GemmDev {
   const float* bias;
   const float* bias_batch;
   long long rows_per_batch;
+  long long bias_batch_ld;
   const __nv_bfloat16* residual;
   long long ldr;
   const float* lora_up;
@@ -65,7 +67,7 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v)
 __global__ void __launch_bounds__(192, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmL, const GemmDev p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by SWIZZLE_128B; dynamic smem base is only guaranteed 16 B aligned.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_bytes = B_STAGE_BYTES + (p.lora ? L_STAGE_BYTES : 0);
@@ -209,7 +211,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int j = 0; j < 16; ++j) t[j] = __uint_as_float(tv[j]);
       }
       const float* bb = nullptr;
-      if (p.bias_batch) bb = p.bias_batch + (valid ? (m / p.rows_per_batch) : 0) * p.N;
+      if (p.bias_batch) bb = p.bias_batch + (valid ? (m / p.rows_per_batch) : 0) * p.bias_batch_ld;
 
       if (p.geglu) {
         // tile columns [0,80) = a, [80,160) = gate for the same 80 outputs
@@ -436,7 +438,10 @@ extern "C" int mos_gemm_bf16(const mos_gemm_args* a, void* stream_) {
     p.kc_per_tap = (int)(a->K / BK);
     p.kb_total = 9 * p.kc_per_tap;
     uint64_t dims[4] = {(uint64_t)a->C, (uint64_t)a->Wd, (uint64_t)a->H, (uint64_t)a->B};
-    uint64_t str[3] = {(uint64_t)a->C * 2, (uint64_t)a->Wd * a->C * 2, (uint64_t)a->H * a->Wd * a->C * 2};
+    const uint64_t pitch = (uint64_t)(a->lda > 0 ? a->lda : a->C);
+    MOS_CHECK_ARG(pitch >= (uint64_t)a->C && pitch % 8 == 0, "mos_gemm_bf16: conv pixel pitch %llu invalid",
+                  (unsigned long long)pitch);
+    uint64_t str[3] = {pitch * 2, (uint64_t)a->Wd * pitch * 2, (uint64_t)a->H * a->Wd * pitch * 2};
     uint32_t box[4] = {BK, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TB};
     int rc = encode_tmap(&tmA, a->A, 2, 4, dims, str, box, 3);
     if (rc) return rc;
@@ -478,6 +483,7 @@ extern "C" int mos_gemm_bf16(const mos_gemm_args* a, void* stream_) {
   p.bias = a->bias;
   p.bias_batch = a->bias_batch;
   p.rows_per_batch = a->rows_per_batch > 0 ? a->rows_per_batch : 1;
+  p.bias_batch_ld = a->bias_batch_ld > 0 ? a->bias_batch_ld : a->N;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
   p.ldr = a->ldr;
   p.lora_up = a->lora_up;
@@ -498,15 +504,15 @@ extern "C" int mos_gemm_bf16(const mos_gemm_args* a, void* stream_) {
   const int stage_bytes = A_STAGE_BYTES + B_STAGE_BYTES + (lora ? L_STAGE_BYTES : 0);
   int stages = a->stages > 0 ? a->stages : 5;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
-  while (stages * stage_bytes + 1024 > 226 * 1024) --stages;
+  while (stages * stage_bytes + 1024 > MAX_DYN_SMEM) --stages;
   if (stages > p.kb_per_split) stages = p.kb_per_split < 2 ? 2 : p.kb_per_split;
   p.stages = stages;
   const int smem_bytes = stages * stage_bytes + 1024;
 
-  static int configured_smem = 0;
-  if (smem_bytes > configured_smem) {
-    MOS_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured_smem = 227 * 1024;
+  static bool configured = false;
+  if (!configured) {
+    MOS_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM));
+    configured = true;
   }
   dim3 grid((unsigned)(a->N / BN), (unsigned)m_tiles, (unsigned)splits);
   gemm_kernel<<<grid, 192, smem_bytes, stream>>>(tmA, tmB, tmL, p);

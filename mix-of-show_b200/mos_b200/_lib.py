@@ -20,7 +20,7 @@ class GemmArgs(ctypes.Structure):
         ('M', c_i64), ('N', c_i64), ('K', c_i64), ('lda', c_i64),
         ('conv', c_i32), ('B', c_i32), ('H', c_i32), ('Wd', c_i32), ('C', c_i32),
         ('splits', c_i32), ('stages', c_i32),
-        ('partial', c_vp), ('bias', c_vp), ('bias_batch', c_vp), ('rows_per_batch', c_i64),
+        ('partial', c_vp), ('bias', c_vp), ('bias_batch', c_vp), ('rows_per_batch', c_i64), ('bias_batch_ld', c_i64),
         ('residual', c_vp), ('ldr', c_i64),
         ('geglu', c_i32),
         ('lora_down', c_vp), ('lora_up', c_vp), ('lora_seg', c_i64),

@@ -20,7 +20,7 @@ def _is_bf16(t):
 
 def gemm(A, W, out=None, *, bias=None, bias_batch=None, rows_per_batch=0, residual=None, geglu=False,
          lora_down=None, lora_up=None, lora_seg=0, conv=None, splits=1, partial=None, stages=0,
-         out_f32=False, heads=None, M=None, lda=None, ldc=None, ldr=None):
+         out_f32=False, heads=None, M=None, lda=None, ldc=None, ldr=None, bias_batch_ld=0):
     """out = epilogue(A @ W^T [+ LoRA]).
 
     A: bf16 [M, K] (row pitch lda) or, with conv=(B, H, Wd, C), the NHWC activation [B, H, Wd, C].
@@ -35,7 +35,7 @@ def gemm(A, W, out=None, *, bias=None, bias_batch=None, rows_per_batch=0, residu
         B, H, Wd, C = conv
         a.conv, a.B, a.H, a.Wd, a.C = 1, B, H, Wd, C
         a.M, a.K = B * H * Wd, C
-        a.lda = C
+        a.lda = C if lda is None else lda
         assert W.shape[1] == 9 * C
     else:
         a.M = A.shape[0] if M is None else M
@@ -49,6 +49,7 @@ def gemm(A, W, out=None, *, bias=None, bias_batch=None, rows_per_batch=0, residu
     a.bias = ptr(bias)
     a.bias_batch = ptr(bias_batch)
     a.rows_per_batch = rows_per_batch
+    a.bias_batch_ld = bias_batch_ld
     assert _is_bf16(residual)
     a.residual = ptr(residual)
     if residual is not None:

@@ -122,7 +122,9 @@ def test_gemm_heads(cuda, d, heads):
     assert rel_l2(Kt[:, :, :T, :d], k_ref) < 4e-3
     assert rel_l2(Vt[:, :, :d, :T], v_ref) < 4e-3
     assert Q[:, :, T:].abs().max().item() == 0 and Q[..., d:].abs().max().item() == 0
-    assert Vt[:, :, d:].abs().max().item() == 0 and Vt[..., T:].abs().max().item() == 0
+    assert Vt[..., T:].abs().max().item() == 0
+    if dv > d:
+        assert Vt[:, :, d:].abs().max().item() == 0
 
 
 @pytest.mark.parametrize('B,H,Wd,Cin,Cout', [(2, 64, 64, 320, 320), (2, 32, 32, 640, 640), (2, 8, 8, 1280, 1280),
