@@ -75,6 +75,68 @@ int mos_splitk_finalize(const float* partial, int32_t splits, int64_t M, int64_t
                         const float* bias_batch, int64_t rows_per_batch, const void* residual, int64_t ldr,
                         void* out, int64_t ldc, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Flash attention (tcgen05 S = QK^T and PV in TMEM, online softmax in registers), head_dim in {40, 80, 160}.
+ *   Q, K : bf16 [batch*heads, nq|nk, DP]   DP = head_dim rounded up to 64, pad columns zero
+ *   Vt   : bf16 [batch*heads, DV, nk8]     DV = head_dim rounded up to 16, nk8 = nk rounded up to 8, pads zero
+ *   out  : bf16 [batch, nq, ldo], head h at columns [h*head_dim, (h+1)*head_dim)
+ *   probs: optional fp32 [batch*heads, nq, nk] (cross-attention maps for the controller; single kv tile only)
+ * Replaces xformers.ops.memory_efficient_attention and attn.get_attention_scores + torch.bmm at
+ *   mixofshow/models/edlora.py:77-83,151-156; mixofshow/pipelines/pipeline_regionally_t2iadapter.py:111-116
+ * and the per-region einsum/softmax/einsum at pipeline_regionally_t2iadapter.py:71-78 (one call per region).
+ * ---------------------------------------------------------------------------------------------------------- */
+int mos_attention_fwd(const void* Q, const void* K, const void* Vt, void* out, int64_t ldo, float* probs,
+                      int32_t batch, int32_t heads, int32_t head_dim, int32_t nq, int32_t nk, int32_t nk8,
+                      float scale, void* stream);
+
+/* GroupNorm(32)(+SiLU) over NHWC bf16 rows: x [B, HW, ldx] -> y [B, HW, ldy]; partial = fp32 workspace of
+ * partial_capacity_floats floats (>= B * 592 * 64 is always enough). diffusers ResnetBlock2D.norm1/norm2,
+ * Transformer2DModel.norm, conv_norm_out (reached from mixofshow/pipelines/pipeline_edlora.py:277). */
+int mos_groupnorm_fwd(const void* x, int64_t ldx, int32_t B, int32_t HW, int32_t C, const float* gamma,
+                      const float* beta, float eps, int32_t silu_act, float* partial,
+                      int32_t partial_capacity_floats, void* y, int64_t ldy, void* stream);
+
+/* LayerNorm over rows of bf16 [M, ldx] -> [M, ldy], C <= 1280 (BasicTransformerBlock.norm1/2/3). */
+int mos_layernorm_fwd(const void* x, int64_t ldx, int64_t M, int32_t C, const float* gamma, const float* beta,
+                      float eps, void* y, int64_t ldy, void* stream);
+
+/* Sinusoidal timestep embedding [B, dim] fp32 = [cos | sin] (diffusers Timesteps, flip_sin_to_cos, shift 0). */
+int mos_timestep_embedding(const float* t, int32_t B, int32_t dim, float* out, void* stream);
+
+/* Small-batch GEMV: out[b, n] = act_out(bias[n] + sum_k act_in(x[b,k]) W[n,k]); x fp32 [nb<=8, K], W bf16 [N, K];
+ * act: 0 = identity, 1 = SiLU. Time-embedding MLP and all ResnetBlock2D.time_emb_proj in one launch. */
+int mos_gemv_bf16(const float* x, int32_t nb, int32_t K, const void* W, const float* bias, int32_t N,
+                  int32_t act_in, int32_t act_out, float* out, int64_t ldo, void* stream);
+
+/* conv_in: NCHW fp32 latents [B, Cin, H, W] -> NHWC bf16 [B, H, W, ldy]; w fp32 [9*Cin, Cout] tap-major. */
+int mos_conv_in(const float* x, int32_t B, int32_t Cin, int32_t H, int32_t W, const float* w, const float* bias,
+                int32_t Cout, void* y, int64_t ldy, void* stream);
+/* conv_out: NHWC bf16 [B, H, W, C] -> NCHW fp32 [B, Cout<=4, H, W]; w fp32 [Cout, 9, C]. */
+int mos_conv_out(const void* x, int32_t B, int32_t H, int32_t W, int32_t C, const float* w, const float* bias,
+                 int32_t Cout, float* y, void* stream);
+
+/* Upsample2D nearest x2: NHWC bf16 [B, H, W, ldx] -> contiguous [B, 2H, 2W, C]. */
+int mos_upsample2x(const void* x, int64_t ldx, int32_t B, int32_t H, int32_t W, int32_t C, void* y, void* stream);
+/* Downsample2D (3x3, stride 2, pad 1) im2col: NHWC bf16 -> [B*H/2*W/2, 9*C] for mos_gemm_bf16. */
+int mos_im2col_s2(const void* x, int64_t ldx, int32_t B, int32_t H, int32_t W, int32_t C, void* col, void* stream);
+/* x[m, :C] += r[m, :C] (T2I-Adapter residuals, pipeline_regionally_t2iadapter.py:565). */
+int mos_add_rows(void* x, int64_t ldx, const void* r, int64_t ldr, int64_t M, int32_t C, void* stream);
+
+/* One fused kernel for mixofshow/pipelines/pipeline_edlora.py:273-290: classifier-free-guidance combine,
+ * DPM-Solver++(2M) data-prediction update and re-duplication of the latents for the next UNet call.
+ * noise_pred fp32 [2n] (uncond | cond) when cfg else [n]; coefficients from the host-side schedule. */
+int mos_cfg_dpmpp_step(const float* noise_pred, float* latents, float* x0_prev, float* unet_in, int64_t n,
+                       int32_t cfg, float guidance, float c_x, float c_m0, float c_m1, float alpha_s, float sigma_s,
+                       void* stream);
+
+/* Region combine (pipeline_regionally_t2iadapter.py:54-83, replace_ratio = 1): out = global where no region
+ * covers the feature pixel, else the mean of the covering regions' attention outputs. boxes_host: int32
+ * [nregions, 4] = (start_h, start_w, end_h, end_w) feature-pixel indices computed by the host in float64 exactly
+ * as the reference does (ceil / floor); region_ptrs_dev: device array of nregions bf16 pointers. */
+int mos_region_combine(const void* glob, const void* const* region_ptrs_dev, int32_t nregions,
+                       const int32_t* boxes_host, int32_t B, int32_t FH, int32_t FW, int32_t C, int64_t ld, void* out,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,240 @@
+// norm.cu — K5: GroupNorm(32) statistics / apply(+SiLU) over NHWC bf16 and LayerNorm over token rows.
+// HBM-bound glue: 128-bit loads, fp32 statistics, warp-shuffle / shared-memory reductions, deterministic
+// (no floating-point atomics to global memory: per-chunk partials are summed in a fixed order).
+// Replaces diffusers GroupNorm / LayerNorm call sites inside ResnetBlock2D, Transformer2DModel and
+// BasicTransformerBlock (reached from mixofshow/pipelines/pipeline_edlora.py:277).
+#include "common.h"
+#include "tc.cuh"
+
+namespace mos {
+
+constexpr int GN_GROUPS = 32;
+
+// partial[b][chunk][g][2] = (sum, sumsq) over rows [chunk*rows_per_chunk, ...) of batch b
+__global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int HW, int C,
+                                int rows_per_chunk, float* __restrict__ partial) {
+  extern __shared__ float red[];  // [blockDim][16]: per-thread channel sums / sums of squares
+  const int oct = C / 8;
+  const int b = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+  const int lanes = blockDim.x / oct;  // row lanes; blockDim is a multiple of oct
+  const int o = threadIdx.x % oct, rl = threadIdx.x / oct;
+  const int r0 = chunk * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  const __nv_bfloat16* base = x + ((long long)b * HW) * ldx + o * 8;
+  for (int r = r0 + rl; r < r1; r += lanes) {
+    uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (long long)r * ldx));
+    uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = unpack_bf16x2(w[i]);
+      s[2 * i] += f.x;
+      q[2 * i] += f.x * f.x;
+      s[2 * i + 1] += f.y;
+      q[2 * i + 1] += f.y * f.y;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    red[threadIdx.x * 16 + i] = s[i];
+    red[threadIdx.x * 16 + 8 + i] = q[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < GN_GROUPS) {  // fixed summation order -> bitwise reproducible statistics
+    const int g = threadIdx.x, cpg = C / GN_GROUPS;
+    float gs = 0.f, gq = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      for (int l = 0; l < lanes; ++l) {
+        const float* t = red + (l * oct + (c >> 3)) * 16 + (c & 7);
+        gs += t[0];
+        gq += t[8];
+      }
+    }
+    float* dst = partial + (((long long)b * nchunks + chunk) * GN_GROUPS + g) * 2;
+    dst[0] = gs;
+    dst[1] = gq;
+  }
+}
+
+__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int HW, int C,
+                                const float* __restrict__ partial, int nchunks, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, float eps, int silu_act, int rows_per_block,
+                                __nv_bfloat16* __restrict__ y, long long ldy) {
+  __shared__ float mean[GN_GROUPS], rstd[GN_GROUPS];
+  const int b = blockIdx.y;
+  const int cpg = C / GN_GROUPS;
+  if (threadIdx.x < GN_GROUPS) {
+    float s = 0.f, q = 0.f;
+    for (int c = 0; c < nchunks; ++c) {
+      const float* src = partial + (((long long)b * nchunks + c) * GN_GROUPS + threadIdx.x) * 2;
+      s += src[0];
+      q += src[1];
+    }
+    const float n = (float)HW * (float)cpg;
+    const float m = s / n;
+    const float var = fmaxf(q / n - m * m, 0.f);
+    mean[threadIdx.x] = m;
+    rstd[threadIdx.x] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  const int oct = C / 8;
+  const int lanes = blockDim.x / oct;
+  const int o = threadIdx.x % oct, rl = threadIdx.x / oct;
+  if (rl >= lanes) return;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int c = o * 8 + i, g = c / cpg;
+    float ga = __ldg(gamma + c) * rstd[g];
+    sc[i] = ga;
+    sh[i] = __ldg(beta + c) - mean[g] * ga;
+  }
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(HW, r0 + rows_per_block);
+  const __nv_bfloat16* xb = x + ((long long)b * HW) * ldx + o * 8;
+  __nv_bfloat16* yb = y + ((long long)b * HW) * ldy + o * 8;
+  for (int r = r0 + rl; r < r1; r += lanes) {
+    uint4 u = __ldg(reinterpret_cast<const uint4*>(xb + (long long)r * ldx));
+    uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = unpack_bf16x2(w[i]);
+      v[2 * i] = f.x * sc[2 * i] + sh[2 * i];
+      v[2 * i + 1] = f.y * sc[2 * i + 1] + sh[2 * i + 1];
+    }
+    if (silu_act) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = silu(v[i]);
+    }
+    uint4 out;
+    out.x = pack_bf16x2(v[0], v[1]);
+    out.y = pack_bf16x2(v[2], v[3]);
+    out.z = pack_bf16x2(v[4], v[5]);
+    out.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(yb + (long long)r * ldy) = out;
+  }
+}
+
+// One warp per row; C <= 1280 (5 octets per lane), two-pass statistics in registers.
+__global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, long long M, int C,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                 __nv_bfloat16* __restrict__ y, long long ldy) {
+  const long long row = (long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const int oct = C / 8;
+  float v[5][8];
+  float s = 0.f;
+  const __nv_bfloat16* xr = x + row * ldx;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    int o = lane + k * 32;
+    if (o < oct) {
+      uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + o * 8));
+      uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float2 f = unpack_bf16x2(w[i]);
+        v[k][2 * i] = f.x;
+        v[k][2 * i + 1] = f.y;
+        s += f.x + f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  const float mean = s / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    int o = lane + k * 32;
+    if (o < oct) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float d = v[k][i] - mean;
+        q += d * d;
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) q += __shfl_xor_sync(0xffffffffu, q, d);
+  const float rstd = rsqrtf(q / (float)C + eps);
+  __nv_bfloat16* yr = y + row * ldy;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    int o = lane + k * 32;
+    if (o < oct) {
+      float r[8];
+      float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + o * 8));
+      float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + o * 8 + 4));
+      float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + o * 8));
+      float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + o * 8 + 4));
+      float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[i] = (v[k][i] - mean) * rstd * gg[i] + bb[i];
+      uint4 out;
+      out.x = pack_bf16x2(r[0], r[1]);
+      out.y = pack_bf16x2(r[2], r[3]);
+      out.z = pack_bf16x2(r[4], r[5]);
+      out.w = pack_bf16x2(r[6], r[7]);
+      *reinterpret_cast<uint4*>(yr + o * 8) = out;
+    }
+  }
+}
+
+static int gn_block_threads(int C) {
+  int oct = C / 8;
+  int k = 320 / oct;
+  if (k < 1) k = 1;
+  return oct * k;
+}
+
+}  // namespace mos
+
+using namespace mos;
+
+// GroupNorm(32) + optional SiLU:  y[b, r, c] = act((x - mean_bg) * rstd_bg * gamma_c + beta_c)
+// x: bf16 [B, HW, ldx] (first C channels), y: bf16 [B, HW, ldy]; partial: fp32 workspace [B, nchunks, 32, 2],
+// nchunks = *nchunks_io (0 = choose; the chosen value is returned through the pointer).
+extern "C" int mos_groupnorm_fwd(const void* x, int64_t ldx, int32_t B, int32_t HW, int32_t C, const float* gamma,
+                                 const float* beta, float eps, int32_t silu_act, float* partial,
+                                 int32_t partial_capacity_floats, void* y, int64_t ldy, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MOS_CHECK_ARG(x && y && gamma && beta && partial, "mos_groupnorm_fwd: NULL pointer");
+  MOS_CHECK_ARG(C % 32 == 0 && C % 8 == 0 && C <= 2560 && ldx % 8 == 0 && ldy % 8 == 0 && ldx >= C && ldy >= C,
+                "mos_groupnorm_fwd: bad C=%d ldx=%lld ldy=%lld", C, (long long)ldx, (long long)ldy);
+  const int threads = gn_block_threads(C);
+  // aim for ~4 blocks per SM overall
+  int nchunks = (int)ceil_div(592, B);
+  int min_rows = 4 * (threads / (C / 8));
+  if (nchunks > (int)ceil_div(HW, min_rows)) nchunks = (int)ceil_div(HW, min_rows);
+  if (nchunks < 1) nchunks = 1;
+  int rows_per_chunk = (int)ceil_div(HW, nchunks);
+  nchunks = (int)ceil_div(HW, rows_per_chunk);
+  MOS_CHECK_ARG((long long)B * nchunks * GN_GROUPS * 2 <= partial_capacity_floats,
+                "mos_groupnorm_fwd: partial workspace too small (need %lld floats)",
+                (long long)B * nchunks * GN_GROUPS * 2);
+  gn_stats_kernel<<<dim3(nchunks, B), threads, threads * 16 * sizeof(float), stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, HW, C,
+                                                            rows_per_chunk, partial);
+  MOS_CHECK_LAUNCH();
+  gn_apply_kernel<<<dim3(nchunks, B), threads, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), ldx, HW, C, partial, nchunks, gamma, beta, eps, silu_act,
+      rows_per_chunk, reinterpret_cast<__nv_bfloat16*>(y), ldy);
+  MOS_CHECK_LAUNCH();
+  return MOS_OK;
+}
+
+extern "C" int mos_layernorm_fwd(const void* x, int64_t ldx, int64_t M, int32_t C, const float* gamma,
+                                 const float* beta, float eps, void* y, int64_t ldy, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MOS_CHECK_ARG(x && y && gamma && beta, "mos_layernorm_fwd: NULL pointer");
+  MOS_CHECK_ARG(C % 8 == 0 && C <= 1280 && ldx % 8 == 0 && ldy % 8 == 0, "mos_layernorm_fwd: bad C=%d", C);
+  const int warps = 8;
+  layernorm_kernel<<<(unsigned)ceil_div(M, warps), warps * 32, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), ldx, M, C, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y),
+      ldy);
+  MOS_CHECK_LAUNCH();
+  return MOS_OK;
+}

@@ -85,3 +85,105 @@ def splitk_finalize(partial, splits, M, N, out, *, bias=None, bias_batch=None, r
         ctypes.c_int64((residual.stride(0) if ldr is None else ldr) if residual is not None else 0), ptr(out),
         ctypes.c_int64(out.stride(0) if ldc is None else ldc), current_stream()), 'mos_splitk_finalize')
     return out
+
+
+def _s():
+    return current_stream()
+
+
+def attention(Q, K, Vt, out, *, batch, heads, head_dim, nq, nk, scale=None, probs=None, ldo=None):
+    """Flash attention over head-split Q/K [B*H, n, DP] and V^T [B*H, DV, nk8]; out bf16 [B, nq, ldo]."""
+    scale = head_dim ** -0.5 if scale is None else scale
+    check(_lib.lib().mos_attention_fwd(
+        ptr(Q), ptr(K), ptr(Vt), ptr(out), ctypes.c_int64(out.stride(-2) if ldo is None else ldo), ptr(probs),
+        ctypes.c_int32(batch), ctypes.c_int32(heads), ctypes.c_int32(head_dim), ctypes.c_int32(nq),
+        ctypes.c_int32(nk), ctypes.c_int32(Vt.shape[-1]), ctypes.c_float(scale), _s()), 'mos_attention_fwd')
+    return out
+
+
+def groupnorm(x, gamma, beta, y, partial, *, B, HW, C, eps, silu, ldx=None, ldy=None):
+    check(_lib.lib().mos_groupnorm_fwd(
+        ptr(x), ctypes.c_int64(x.stride(-2) if ldx is None else ldx), ctypes.c_int32(B), ctypes.c_int32(HW),
+        ctypes.c_int32(C), ptr(gamma), ptr(beta), ctypes.c_float(eps), ctypes.c_int32(1 if silu else 0),
+        ptr(partial), ctypes.c_int32(partial.numel()), ptr(y),
+        ctypes.c_int64(y.stride(-2) if ldy is None else ldy), _s()), 'mos_groupnorm_fwd')
+    return y
+
+
+def layernorm(x, gamma, beta, y, *, M, C, eps=1e-5, ldx=None, ldy=None):
+    check(_lib.lib().mos_layernorm_fwd(
+        ptr(x), ctypes.c_int64(x.stride(-2) if ldx is None else ldx), ctypes.c_int64(M), ctypes.c_int32(C),
+        ptr(gamma), ptr(beta), ctypes.c_float(eps), ptr(y), ctypes.c_int64(y.stride(-2) if ldy is None else ldy),
+        _s()), 'mos_layernorm_fwd')
+    return y
+
+
+def timestep_embedding(t, out):
+    check(_lib.lib().mos_timestep_embedding(ptr(t), ctypes.c_int32(out.shape[0]), ctypes.c_int32(out.shape[1]),
+                                            ptr(out), _s()), 'mos_timestep_embedding')
+    return out
+
+
+def gemv(x, W, bias, out, *, act_in=False, act_out=False):
+    nb, K = x.shape
+    check(_lib.lib().mos_gemv_bf16(ptr(x), ctypes.c_int32(nb), ctypes.c_int32(K), ptr(W), ptr(bias),
+                                   ctypes.c_int32(W.shape[0]), ctypes.c_int32(int(act_in)),
+                                   ctypes.c_int32(int(act_out)), ptr(out), ctypes.c_int64(out.stride(0)), _s()),
+          'mos_gemv_bf16')
+    return out
+
+
+def conv_in(x, w, bias, y, *, ldy=None):
+    B, Cin, H, W = x.shape
+    check(_lib.lib().mos_conv_in(ptr(x), ctypes.c_int32(B), ctypes.c_int32(Cin), ctypes.c_int32(H), ctypes.c_int32(W),
+                                 ptr(w), ptr(bias), ctypes.c_int32(w.shape[1]), ptr(y),
+                                 ctypes.c_int64(w.shape[1] if ldy is None else ldy), _s()), 'mos_conv_in')
+    return y
+
+
+def conv_out(x, w, bias, y, *, B, H, W, C):
+    check(_lib.lib().mos_conv_out(ptr(x), ctypes.c_int32(B), ctypes.c_int32(H), ctypes.c_int32(W), ctypes.c_int32(C),
+                                  ptr(w), ptr(bias), ctypes.c_int32(w.shape[0]), ptr(y), _s()), 'mos_conv_out')
+    return y
+
+
+def upsample2x(x, y, *, B, H, W, C, ldx=None):
+    check(_lib.lib().mos_upsample2x(ptr(x), ctypes.c_int64(C if ldx is None else ldx), ctypes.c_int32(B),
+                                    ctypes.c_int32(H), ctypes.c_int32(W), ctypes.c_int32(C), ptr(y), _s()),
+          'mos_upsample2x')
+    return y
+
+
+def im2col_s2(x, col, *, B, H, W, C, ldx=None):
+    check(_lib.lib().mos_im2col_s2(ptr(x), ctypes.c_int64(C if ldx is None else ldx), ctypes.c_int32(B),
+                                   ctypes.c_int32(H), ctypes.c_int32(W), ctypes.c_int32(C), ptr(col), _s()),
+          'mos_im2col_s2')
+    return col
+
+
+def add_rows(x, r, *, M, C, ldx, ldr):
+    check(_lib.lib().mos_add_rows(ptr(x), ctypes.c_int64(ldx), ptr(r), ctypes.c_int64(ldr), ctypes.c_int64(M),
+                                  ctypes.c_int32(C), _s()), 'mos_add_rows')
+    return x
+
+
+def cfg_dpmpp_step(noise_pred, latents, x0_prev, unet_in, *, cfg, guidance, coef):
+    c_x, c_m0, c_m1, alpha_s, sigma_s = coef
+    check(_lib.lib().mos_cfg_dpmpp_step(ptr(noise_pred), ptr(latents), ptr(x0_prev), ptr(unet_in),
+                                        ctypes.c_int64(latents.numel()), ctypes.c_int32(int(cfg)),
+                                        ctypes.c_float(guidance), ctypes.c_float(c_x), ctypes.c_float(c_m0),
+                                        ctypes.c_float(c_m1), ctypes.c_float(alpha_s), ctypes.c_float(sigma_s), _s()),
+          'mos_cfg_dpmpp_step')
+    return latents
+
+
+def region_combine(glob, region_ptrs_dev, boxes, out, *, B, FH, FW, C, ld):
+    n = len(boxes)
+    arr = (ctypes.c_int32 * (4 * max(n, 1)))()
+    for i, bx in enumerate(boxes):
+        for k in range(4):
+            arr[4 * i + k] = int(bx[k])
+    check(_lib.lib().mos_region_combine(ptr(glob), ptr(region_ptrs_dev), ctypes.c_int32(n), arr, ctypes.c_int32(B),
+                                        ctypes.c_int32(FH), ctypes.c_int32(FW), ctypes.c_int32(C), ctypes.c_int64(ld),
+                                        ptr(out), _s()), 'mos_region_combine')
+    return out
