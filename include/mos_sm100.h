@@ -72,8 +72,8 @@ int mos_gemm_bf16(const mos_gemm_args* args, void* stream);
 
 /* Sum split-K partials and apply bias / bias_batch / residual -> bf16 [M, ldc]. */
 int mos_splitk_finalize(const float* partial, int32_t splits, int64_t M, int64_t N, const float* bias,
-                        const float* bias_batch, int64_t rows_per_batch, const void* residual, int64_t ldr,
-                        void* out, int64_t ldc, void* stream);
+                        const float* bias_batch, int64_t rows_per_batch, int64_t bias_batch_ld,
+                        const void* residual, int64_t ldr, void* out, int64_t ldc, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Flash attention (tcgen05 S = QK^T and PV in TMEM, online softmax in registers), head_dim in {40, 80, 160}.

@@ -331,7 +331,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // ---------------------------------------------------------------------------------------------- split-K finalize
 __global__ void splitk_finalize_kernel(const float* __restrict__ partial, int splits, long long M, long long N,
                                        const float* __restrict__ bias, const float* __restrict__ bias_batch,
-                                       long long rows_per_batch, const __nv_bfloat16* __restrict__ residual,
+                                       long long rows_per_batch, long long bias_batch_ld,
+                                       const __nv_bfloat16* __restrict__ residual,
                                        long long ldr, __nv_bfloat16* __restrict__ out, long long ldc) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 4 columns
   long long n4 = N / 4;
@@ -351,7 +352,7 @@ __global__ void splitk_finalize_kernel(const float* __restrict__ partial, int sp
     acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
   }
   if (bias_batch) {
-    float4 b = __ldg(reinterpret_cast<const float4*>(bias_batch + (m / rows_per_batch) * N + n));
+    float4 b = __ldg(reinterpret_cast<const float4*>(bias_batch + (m / rows_per_batch) * bias_batch_ld + n));
     acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
   }
   if (residual) {
@@ -521,8 +522,8 @@ extern "C" int mos_gemm_bf16(const mos_gemm_args* a, void* stream_) {
 }
 
 extern "C" int mos_splitk_finalize(const float* partial, int32_t splits, int64_t M, int64_t N, const float* bias,
-                                   const float* bias_batch, int64_t rows_per_batch, const void* residual,
-                                   int64_t ldr, void* out, int64_t ldc, void* stream_) {
+                                   const float* bias_batch, int64_t rows_per_batch, int64_t bias_batch_ld,
+                                   const void* residual, int64_t ldr, void* out, int64_t ldc, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MOS_CHECK_ARG(partial && out && splits >= 1 && M > 0 && N > 0 && N % 4 == 0, "mos_splitk_finalize: bad arguments");
   long long total = M * (N / 4);
@@ -530,7 +531,7 @@ extern "C" int mos_splitk_finalize(const float* partial, int32_t splits, int64_t
   long long blocks = ceil_div(total, threads);
   splitk_finalize_kernel<<<(unsigned)blocks, threads, 0, stream>>>(
       partial, splits, M, N, bias, bias_batch, rows_per_batch > 0 ? rows_per_batch : 1,
-      reinterpret_cast<const __nv_bfloat16*>(residual), ldr, reinterpret_cast<__nv_bfloat16*>(out), ldc);
+      bias_batch_ld > 0 ? bias_batch_ld : N, reinterpret_cast<const __nv_bfloat16*>(residual), ldr, reinterpret_cast<__nv_bfloat16*>(out), ldc);
   MOS_CHECK_LAUNCH();
   return MOS_OK;
 }

@@ -78,10 +78,10 @@ def gemm(A, W, out=None, *, bias=None, bias_batch=None, rows_per_batch=0, residu
 
 
 def splitk_finalize(partial, splits, M, N, out, *, bias=None, bias_batch=None, rows_per_batch=0, residual=None,
-                    ldc=None, ldr=None):
+                    ldc=None, ldr=None, bias_batch_ld=0):
     check(_lib.lib().mos_splitk_finalize(
         ptr(partial), ctypes.c_int32(splits), ctypes.c_int64(M), ctypes.c_int64(N), ptr(bias), ptr(bias_batch),
-        ctypes.c_int64(rows_per_batch), ptr(residual),
+        ctypes.c_int64(rows_per_batch), ctypes.c_int64(bias_batch_ld), ptr(residual),
         ctypes.c_int64((residual.stride(0) if ldr is None else ldr) if residual is not None else 0), ptr(out),
         ctypes.c_int64(out.stride(0) if ldc is None else ldc), current_stream()), 'mos_splitk_finalize')
     return out

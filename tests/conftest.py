@@ -19,4 +19,7 @@ def cuda():
     import torch
     if not torch.cuda.is_available():
         pytest.skip('no CUDA device')
+    # the PyTorch references must be true fp32 (no TF32) to serve as the yardstick
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
     return torch.device('cuda:0')
