@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json metric: SD1.5 UNet + ED-LoRA denoise steps/sec @512x512, bf16, on N B200s.
+
+One "step" = one denoise step of EDLoRAPipeline (mixofshow/pipelines/pipeline_edlora.py:273-290): CFG batch-2 UNet
+forward (un-merged rank-4 ED-LoRA on all 128 attention linears, layer-wise text embeddings) + CFG combine +
+DPM-Solver++(2M) update.  Synthetic data: random-init SD1.5-topology weights (seed 0), random latents / embeddings.
+
+  python bench.py --gpus N --steps K --warmup W          (N > 1: launched by torchrun, one rank per GPU, replicas)
+  python bench.py --impl reference ...                    CPU arm: the fp32 oracle port of the reference path
+
+Prints ONE JSON line (see the driver contract in the task description).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, 'mix-of-show_b200')
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = 'SD1.5 UNet+ED-LoRA denoise steps/sec @512x512 bf16'
+UNIT = 'denoise_steps/s'
+WORKLOAD = ('EDLoRAPipeline denoise step: SD1.5 UNet 512x512 (latent 64x64), CFG batch 2, un-merged rank-4 ED-LoRA on '
+            '128 attention linears, 16 layer-wise text embeddings [2,16,77,768], DPM-Solver++(2M) update')
+FLOPS_PER_STEP = 2 * 0.8044e12  # algorithmic FLOPs of one CFG denoise step
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            p = json.load(f)
+        return {'tflops': float(p['bf16_tflops_sustained']), 'hbm': float(p['hbm_gbs']), 'src': 'measured'}
+    except Exception:
+        return {'tflops': 1400.0, 'hbm': 6650.0, 'src': 'fallback'}
+
+
+# ----------------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for s in self.samples:
+            f = [x.strip() for x in s.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- workload
+def build_workload(tiny=False):
+    """Oracle-side construction of the synthetic model (weights + LoRA + inputs). The oracle module is used here
+    only as the weight initialiser / CPU baseline, never on the measured GPU path."""
+    import torch
+    from oracle import inject
+    from oracle import unet as ou
+    cfg = ou.TINY if tiny else None
+    unet = ou.build_unet(0, cfg)
+    inject.install_edlora_processors(unet)
+    lora = inject.random_lora_state(unet, seed=10)
+    sd = {k: v.clone() for k, v in unet.state_dict().items()}
+    H = W = 64
+    lat = torch.randn(1, 4, H, W, generator=torch.Generator().manual_seed(1))
+    ehs = torch.randn(2, 16, 77, 768, generator=torch.Generator().manual_seed(2))
+    return unet, sd, lora, lat, ehs, cfg
+
+
+def cpu_reference_steps(unet, lora, lat, ehs, steps, warmup, budget_s):
+    """Time the reference path on host cores: fp32 oracle UNet (reference processors' restatement + LoRA) + CFG +
+    DPM-Solver++ per step.  Returns (steps_run, seconds)."""
+    import torch
+    from oracle import edlora_ref as er
+    from oracle import inject
+    from oracle.schedulers import DPMSolverMultistepScheduler
+    inject.inject_lora(unet, lora, 1.0)
+    torch.set_num_threads(os.cpu_count())
+    sched = DPMSolverMultistepScheduler()
+    sched.set_timesteps(50)
+    latents = lat.clone()
+
+    def one(i):
+        nonlocal latents
+        t = int(sched.timesteps[i])
+        with torch.no_grad():
+            eps = unet(torch.cat([latents] * 2), torch.tensor([t, t]), ehs).sample
+        latents = sched.step(er.cfg_combine(eps, 7.5), t, latents).prev_sample
+
+    i = 0
+    for _ in range(warmup):
+        one(i)
+        i += 1
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        one(i)
+        i += 1
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    return done, time.perf_counter() - t0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--tiny', action='store_true', help='debug: 2-level UNet')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    import torch
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        unet, sd, lora, lat, ehs, cfg = build_workload(args.tiny)
+        done, secs = cpu_reference_steps(unet, lora, lat, ehs, args.steps, min(args.warmup, 1), budget_s=240.0)
+        v = done / secs
+        print(json.dumps({
+            'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': done,
+            'warmup': min(args.warmup, 1), 'ms_per_step': 1e3 * secs / done, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'note': 'CPU oracle port of the reference path (diffusers absent); '
+                       'steps capped to a 240 s budget'},
+            'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+                             'sample': f'{done} full CFG denoise steps after {min(args.warmup, 1)} warm-up'},
+            'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        }))
+        return
+
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback for the product path)'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    from mos_b200 import ops
+    from mos_b200.engine import UNetEngine, ehs_to_layer_major
+    from mos_b200.scheduler import DPMSolverPP2M
+
+    unet, sd, lora, lat, ehs, cfg = build_workload(args.tiny)
+    kw = dict(block_out=cfg['block_out_channels'], layers=cfg['layers_per_block']) if cfg else {}
+    B, H, W = 2, lat.shape[2], lat.shape[3]
+    eng = UNetEngine(sd, B, H, W, lora=lora, lora_alpha=1.0, device=dev, **kw)
+    nx = len(eng.xattn_names)
+    sched = DPMSolverPP2M()
+    total_steps = args.warmup + args.steps
+    sched.set_timesteps(max(50, total_steps))
+    ts = [float(t) for t in sched.timesteps]
+
+    latents = lat.to(dev).clone()
+    x0_prev = torch.zeros_like(latents)
+    eng.in_ehs.copy_(ehs_to_layer_major(ehs[:, :nx].to(dev), nx))
+    unet_in = eng.in_latents.view(-1)
+
+    def reset():
+        latents.copy_(lat.to(dev))
+        x0_prev.zero_()
+        eng.in_latents.copy_(torch.cat([latents, latents]))
+        eng.in_t.fill_(ts[0])
+
+    def step(i):
+        eng.run()
+        nxt = ts[i + 1] if i + 1 < len(ts) else 0.0
+        ops.cfg_dpmpp_step(eng.out_eps, latents, x0_prev, unet_in, cfg=True, guidance=7.5,
+                           coef=sched.coefficients(i), t_out=eng.in_t, t_next=nxt)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput (`value`)
+    reset()
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.warmup, total_steps):
+        step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = (eng.launches + 1) * args.steps
+    final_lat = latents.clone()
+
+    # ---------------- end-to-end through host buffers (`e2e`): H2D latents + t + embeddings, D2H latents per step
+    h_lat = lat.clone().pin_memory()
+    h_ehs = ehs_to_layer_major(ehs[:, :nx], nx).pin_memory()
+    h_t = torch.zeros(B).pin_memory()
+    h_out = torch.empty_like(h_lat).pin_memory()
+    reset()
+
+    def e2e_step(i):
+        h_t.fill_(ts[i])
+        latents.copy_(h_lat, non_blocking=True)
+        eng.in_latents[0].copy_(h_lat[0], non_blocking=True)
+        eng.in_latents[1].copy_(h_lat[0], non_blocking=True)
+        eng.in_t.copy_(h_t, non_blocking=True)
+        eng.in_ehs.copy_(h_ehs, non_blocking=True)
+        eng.run()
+        ops.cfg_dpmpp_step(eng.out_eps, latents, x0_prev, None, cfg=True, guidance=7.5, coef=sched.coefficients(i))
+        h_out.copy_(latents, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the caller consumes the step result on the host
+        h_lat.copy_(h_out)
+
+    for i in range(args.warmup):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for i in range(args.warmup, total_steps):
+        e2e_step(i)
+    g1.record()
+    barrier()
+    e2e_ms = max(g0.elapsed_time(g1), 1e3 * (time.perf_counter() - t0))
+    h2d = h_lat.numel() * 4 * 2 + h_t.numel() * 4 + h_ehs.numel() * 2
+    d2h = h_out.numel() * 4
+
+    # ---------------- per-kernel roofline of the dominant kernel (tcgen05 GEMM / implicit-GEMM conv), eager mode
+    roof = None
+    if rank == 0:
+        roof = gemm_roofline(eng, ops, torch)
+
+    if world > 1:
+        tt = torch.tensor([ms, e2e_ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = tt[0].item(), tt[1].item()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    value = world * args.steps / (ms / 1e3)
+    e2e_value = world * args.steps / (e2e_ms / 1e3)
+    out = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'bf16', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'parallelism': f'replicas x{world} (independent images per GPU, no data-path '
+                   'collective; SURVEY.md 8e)', 'l2': 'inputs larger than L2: 1.72 GB of bf16 weights streamed per '
+                   'step vs 126 MB L2, no explicit flush', 'cuda_graph': bool(eng.graph is not None)},
+        'clocks': clocks,
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                'ms_per_step': e2e_ms / args.steps},
+        'gpu_launches': launches,
+        'step_tflops': FLOPS_PER_STEP * value / world / 1e12 if not args.tiny else None,
+    }
+    if roof is not None:
+        frac = roof['achieved'] / peaks['tflops']
+        out['roofline'] = {'bound': 'tensor', 'achieved': roof['achieved'], 'peak': peaks['tflops'], 'unit': 'TFLOP/s',
+                           'frac': frac, 'traffic': None, 'peak_source': peaks['src'] + ' (bf16_tflops_sustained)',
+                           'kernel': 'mos::gemm_kernel (tcgen05 GEMM + implicit-GEMM conv3x3)',
+                           'launches_per_step': roof['launches'], 'kernel_ms_per_step': roof['ms'],
+                           'algorithmic_gflop_per_step': roof['gflop']}
+    if world == 1 and not args.no_cpu_baseline:
+        t0 = time.perf_counter()
+        done, secs = cpu_reference_steps(unet, lora, lat, ehs, 2, 1, budget_s=60.0)
+        out['cpu_baseline'] = {'value': done / secs, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+                               'sample': f'{done} full CFG denoise steps (same workload, fp32 oracle) after 1 warm-up'}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def gemm_roofline(eng, ops, torch):
+    """Time every launch of the dominant kernel with CUDA events on the launching stream (eager, no graph) and
+    divide its algorithmic FLOPs (2*M*N*K, LoRA / padding FLOPs excluded) by its device time."""
+    recs = []
+    orig = ops.gemm
+
+    def timed(A, W, out=None, **kw):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        conv = kw.get('conv')
+        if conv is not None:
+            M = conv[0] * conv[1] * conv[2]
+        else:
+            M = kw.get('M') or A.shape[0]
+        fl = 2.0 * M * W.shape[0] * W.shape[1]
+        a.record()
+        r = orig(A, W, out, **kw)
+        b.record()
+        recs.append((a, b, fl))
+        return r
+
+    ops.gemm = timed
+    try:
+        eng._run()       # warm
+        torch.cuda.synchronize()
+        recs.clear()
+        reps = 3
+        for _ in range(reps):
+            eng._run()
+        torch.cuda.synchronize()
+    finally:
+        ops.gemm = orig
+    ms = sum(a.elapsed_time(b) for a, b, _ in recs) / reps
+    fl = sum(f for _, _, f in recs) / reps
+    return {'achieved': fl / (ms * 1e-3) / 1e12, 'ms': ms, 'launches': len(recs) // reps, 'gflop': fl / 1e9}
+
+
+if __name__ == '__main__':
+    main()

@@ -124,10 +124,11 @@ int mos_add_rows(void* x, int64_t ldx, const void* r, int64_t ldr, int64_t M, in
 
 /* One fused kernel for mixofshow/pipelines/pipeline_edlora.py:273-290: classifier-free-guidance combine,
  * DPM-Solver++(2M) data-prediction update and re-duplication of the latents for the next UNet call.
- * noise_pred fp32 [2n] (uncond | cond) when cfg else [n]; coefficients from the host-side schedule. */
+ * noise_pred fp32 [2n] (uncond | cond) when cfg else [n]; coefficients from the host-side schedule.
+ * t_out (optional): t_count floats set to t_next, the timestep input of the next UNet call. */
 int mos_cfg_dpmpp_step(const float* noise_pred, float* latents, float* x0_prev, float* unet_in, int64_t n,
                        int32_t cfg, float guidance, float c_x, float c_m0, float c_m1, float alpha_s, float sigma_s,
-                       void* stream);
+                       float* t_out, int32_t t_count, float t_next, void* stream);
 
 /* Region combine (pipeline_regionally_t2iadapter.py:54-83, replace_ratio = 1): out = global where no region
  * covers the feature pixel, else the mean of the covering regions' attention outputs. boxes_host: int32

@@ -217,8 +217,9 @@ __global__ void add_rows_kernel(__nv_bfloat16* __restrict__ x, long long ldx, co
 __global__ void cfg_dpm_step_kernel(const float* __restrict__ noise_pred, float* __restrict__ latents,
                                     float* __restrict__ x0_prev, float* __restrict__ unet_in, long long n, int cfg,
                                     float guidance, float c_x, float c_m0, float c_m1, float alpha_s,
-                                    float sigma_s) {
+                                    float sigma_s, float* __restrict__ t_out, int t_count, float t_next) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t_out != nullptr && i < t_count) t_out[i] = t_next;  // timestep of the next UNet call
   if (i >= n) return;
   float eps;
   if (cfg) {
@@ -366,10 +367,10 @@ extern "C" int mos_add_rows(void* x, int64_t ldx, const void* r, int64_t ldr, in
 
 extern "C" int mos_cfg_dpmpp_step(const float* noise_pred, float* latents, float* x0_prev, float* unet_in, int64_t n,
                                   int32_t cfg, float guidance, float c_x, float c_m0, float c_m1, float alpha_s,
-                                  float sigma_s, void* stream) {
+                                  float sigma_s, float* t_out, int32_t t_count, float t_next, void* stream) {
   MOS_CHECK_ARG(noise_pred && latents && x0_prev && n > 0, "mos_cfg_dpmpp_step: bad arguments");
   cfg_dpm_step_kernel<<<nblk(n, 256), 256, 0, STREAM(stream)>>>(noise_pred, latents, x0_prev, unet_in, n, cfg, guidance,
-                                                                c_x, c_m0, c_m1, alpha_s, sigma_s);
+                                                                c_x, c_m0, c_m1, alpha_s, sigma_s, t_out, t_count, t_next);
   MOS_CHECK_LAUNCH();
   return MOS_OK;
 }

@@ -251,8 +251,9 @@ class UNetEngine:
         tiles = _r(M, 128) // 128 * (N // 160)
         if tiles >= 96 or kb_total < 16:
             return 1
-        s = min(max(1, 148 // tiles), kb_total // 8)
-        return max(1, min(s, 16))
+        s = max(1, min(max(1, 148 // tiles), kb_total // 8, 16))
+        per = -(-kb_total // s)          # k blocks per split
+        return -(-kb_total // per)       # normalised so that no split is empty
 
     def gemm(self, A, ent, out, *, M, conv=None, residual=None, bias_batch=None, rows_per_batch=0, geglu=False,
              heads=None, lda=None):

@@ -167,12 +167,14 @@ def add_rows(x, r, *, M, C, ldx, ldr):
     return x
 
 
-def cfg_dpmpp_step(noise_pred, latents, x0_prev, unet_in, *, cfg, guidance, coef):
+def cfg_dpmpp_step(noise_pred, latents, x0_prev, unet_in, *, cfg, guidance, coef, t_out=None, t_next=0.0):
     c_x, c_m0, c_m1, alpha_s, sigma_s = coef
     check(_lib.lib().mos_cfg_dpmpp_step(ptr(noise_pred), ptr(latents), ptr(x0_prev), ptr(unet_in),
                                         ctypes.c_int64(latents.numel()), ctypes.c_int32(int(cfg)),
                                         ctypes.c_float(guidance), ctypes.c_float(c_x), ctypes.c_float(c_m0),
-                                        ctypes.c_float(c_m1), ctypes.c_float(alpha_s), ctypes.c_float(sigma_s), _s()),
+                                        ctypes.c_float(c_m1), ctypes.c_float(alpha_s), ctypes.c_float(sigma_s),
+                                        ptr(t_out), ctypes.c_int32(0 if t_out is None else t_out.numel()),
+                                        ctypes.c_float(t_next), _s()),
           'mos_cfg_dpmpp_step')
     return latents
 

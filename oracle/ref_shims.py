@@ -52,7 +52,7 @@ def install_stubs():
 
     _stub('diffusers', StableDiffusionPipeline=_Dummy, DDPMScheduler=_Dummy, DPMSolverMultistepScheduler=_Dummy,
           AutoencoderKL=_Dummy, UNet2DConditionModel=_Dummy)
-    _stub('diffusers.models', AutoencoderKL=_Dummy, UNet2DConditionModel=_Dummy)
+    _stub('diffusers.models', AutoencoderKL=_Dummy, UNet2DConditionModel=_Dummy, T2IAdapter=_Dummy)
     _stub('diffusers.models.attention_processor', AttnProcessor=AttnProcessor)
     _stub('diffusers.utils', deprecate=lambda *a, **k: None,
           logging=types.SimpleNamespace(get_logger=lambda name: __import__('logging').getLogger(name)))

@@ -1,0 +1,95 @@
+"""Host-side logic that needs no GPU: weight packing, concat-slot bookkeeping, schedule coefficients, ordering."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import edlora_ref as er
+from oracle import inject
+from oracle import unet as ou
+
+
+def test_cross_attention_names_match_reference_order():
+    from mos_b200.engine import cross_attention_names
+    with torch.device('meta'):
+        u = ou.UNet2DConditionModel()
+    assert cross_attention_names() == er.cross_attention_layer_order(u)
+    with torch.device('meta'):
+        t = ou.UNet2DConditionModel(ou.TINY)
+    assert cross_attention_names(ou.TINY['block_out_channels'], 1) == er.cross_attention_layer_order(t)
+
+
+def test_engine_packing_on_cpu():
+    from mos_b200.engine import UNetEngine
+    u = ou.build_unet(0, ou.TINY)
+    lora = inject.random_lora_state(u, seed=10)
+    sd = u.state_dict()
+    eng = UNetEngine(sd, 2, 16, 16, lora=lora, lora_alpha=0.5, device='cpu', block_out=ou.TINY['block_out_channels'],
+                     layers=1)
+    tb = 'down_blocks.0.attentions.0.transformer_blocks.0'
+    ent = eng.w[tb + '.attn1.qkv']
+    assert ent['W'].shape == (960, 320) and ent['lora_down'].shape == (16, 320) and ent['lora_up'].shape == (960, 4)
+    assert ent['lora_seg'] == 320
+    # fused q|k|v weight rows and LoRA rows land in the right segments
+    wq = sd[tb + '.attn1.to_q.weight']
+    assert torch.equal(ent['W'][:320].float(), wq.to(torch.bfloat16).float())
+    dv = lora[tb + '.attn1.to_v.lora_down.weight']
+    assert torch.equal(ent['lora_down'][8:12].float(), dv.to(torch.bfloat16).float())
+    assert torch.all(ent['lora_down'][12:] == 0)
+    uk = lora[tb + '.attn1.to_k.lora_up.weight']
+    assert torch.allclose(ent['lora_up'][320:640], uk * 0.5)
+    # GEGLU interleave: tile t = [a rows 80t.. | gate rows 1280+80t..]
+    ff = eng.w[tb + '.ff1']
+    w = sd[tb + '.ff.net.0.proj.weight']
+    assert torch.equal(ff['W'][0:80].float(), w[0:80].to(torch.bfloat16).float())
+    assert torch.equal(ff['W'][80:160].float(), w[1280:1360].to(torch.bfloat16).float())
+    assert torch.equal(ff['W'][160:240].float(), w[80:160].to(torch.bfloat16).float())
+    # conv weights are tap-major [Cout, (kh, kw, cin)]
+    c1 = eng.w['down_blocks.0.resnets.0.conv1']['W']
+    wc = sd['down_blocks.0.resnets.0.conv1.weight']
+    assert torch.equal(c1[:, 320:640].float(), wc[:, :, 0, 1].to(torch.bfloat16).float())
+    # merged mode == W + alpha * up @ down (convert_edlora_to_diffusers.py:67-73)
+    eng_m = UNetEngine(sd, 2, 16, 16, lora=lora, lora_alpha=0.5, merge_lora=True, device='cpu',
+                       block_out=ou.TINY['block_out_channels'], layers=1)
+    em = eng_m.w[tb + '.attn2.q']
+    assert 'lora_down' not in em
+    ref = er.merge_lora_weight(sd[tb + '.attn2.to_q.weight'], lora[tb + '.attn2.to_q.lora_down.weight'],
+                               lora[tb + '.attn2.to_q.lora_up.weight'], 0.5)
+    assert torch.equal(em['W'].float(), ref.to(torch.bfloat16).float())
+
+
+def test_concat_slots_cover_the_unet_skip_wiring():
+    from mos_b200.engine import UNetEngine
+    with torch.device('meta'):
+        u = ou.UNet2DConditionModel()
+    sd = {k: torch.zeros(v.shape) for k, v in u.state_dict().items()}
+    eng = UNetEngine(sd, 2, 8, 8, device='cpu')
+    assert eng.skip_ch == [320, 320, 320, 320, 640, 640, 640, 1280, 1280, 1280, 1280, 1280]
+    assert [a + b for a, b in eng.cat_ch] == [2560, 2560, 2560, 2560, 2560, 1920, 1920, 1280, 960, 960, 640, 640]
+    # resnet input widths of the up path, as the skeleton defines them
+    want = [u.up_blocks[i].resnets[j].conv1.in_channels for i in range(4) for j in range(3)]
+    assert [a + b for a, b in eng.cat_ch] == want
+    rows = [c.shape[0] for c in eng.cat]
+    assert rows == [2 * 1] * 3 + [2 * 4] * 3 + [2 * 16] * 3 + [2 * 64] * 3
+    assert eng.temb_total == sum(u.get_submodule(n).time_emb_proj.out_features for n in eng._resnet_names())
+
+
+def test_product_scheduler_matches_oracle():
+    from mos_b200.scheduler import DPMSolverPP2M
+    from oracle.schedulers import DPMSolverMultistepScheduler
+    for n in (10, 20, 30, 50):
+        a, b = DPMSolverPP2M(), DPMSolverMultistepScheduler()
+        ts = a.set_timesteps(n)
+        b.set_timesteps(n)
+        assert np.array_equal(ts, b.timesteps.numpy())       # integer timesteps: bit exact
+        for i in range(len(ts)):
+            assert np.allclose(a.coefficients(i), b.coefficients(i), rtol=2e-5, atol=1e-6)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from mos_b200 import _lib
+    monkeypatch.setattr(_lib, '_lib', None)
+    monkeypatch.setattr(_lib, 'LIB_PATH', str(tmp_path / 'nope.so'))
+    with pytest.raises(_lib.MosError):
+        _lib.lib()

@@ -1,0 +1,146 @@
+"""The oracle's restatements (oracle/edlora_ref.py, oracle/inject.py) reproduce the golden vectors generated from the
+reference's OWN modules (tests/golden/make_golden.py -> tests/golden/reference_golden.pt).  CPU only."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import edlora_ref as er
+from oracle import inject
+from oracle import unet as ou
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_golden.pt')
+
+
+@pytest.fixture(scope='module')
+def G():
+    return torch.load(GOLD, weights_only=False)
+
+
+def close(a, b, tol=1e-5):
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item() < tol
+
+
+def test_lora_linear_and_conv(G):
+    for key in ('lora_linear', 'lora_conv'):
+        g = G[key]
+        y = er.lora_linear(g['x'], g['w'], g['b'], g['down'], g['up'], g['alpha'])
+        assert close(y, g['y'], 1e-6)
+
+
+def _attn_from_state(state, cross):
+    a = ou.Attention(320, cross, heads=8, dim_head=40)
+    a.load_state_dict(state)
+    return a
+
+
+def test_cross_attention_processor(G):
+    g = G['attn_proc']
+    st = g['state']
+    out, probs = er.edlora_cross_attention(g['hs'], g['ehs'], g['idx'], st['to_q.weight'], st['to_k.weight'],
+                                           st['to_v.weight'], st['to_out.0.weight'], st['to_out.0.bias'], 8,
+                                           return_probs=True)
+    assert close(out, g['out'], 1e-5) and close(out, g['out_ctl'], 1e-5)
+    assert close(probs, g['probs'], 1e-5)
+    assert g['is_cross'] is True and g['place'] == 'down'
+    # module-level restatement (oracle/inject.py) too
+    attn = _attn_from_state(st, 96)
+    with torch.no_grad():
+        out2 = inject.EDLoRAProcessor(g['idx'])(attn, g['hs'], encoder_hidden_states=g['ehs'])
+    assert close(out2, g['out'], 1e-5)
+
+
+@pytest.mark.parametrize('tag,cfg', [('tiny', ou.TINY), ('sd15', None)])
+def test_cross_attention_idx_order_bit_exact(G, tag, cfg):
+    with torch.device('meta'):
+        u = ou.UNet2DConditionModel(cfg)
+    order = er.cross_attention_layer_order(u)
+    gold = G[f'xattn_order_{tag}']
+    assert {n: i for i, n in enumerate(order)} == gold
+    n = inject.install_edlora_processors(u)
+    assert n == len(gold)
+    for name, m in u.named_modules():
+        if name in gold:
+            assert m.processor.cross_attention_idx == gold[name]
+
+
+def test_bind_concept_prompt_bit_exact(G):
+    g = G['bind_concept_prompt']
+    assert er.bind_concept_prompt(g['prompts'], g['cfg']) == g['out']
+    assert er.bind_concept_prompt(g['prompts'][0], g['cfg']) == g['out_single']
+
+
+def test_region_box_indices_bit_exact(G):
+    g = G['region']
+    for (H, W, ds, tag), idx in g['box_index_kat'].items():
+        boxes = g['boxes'] if tag == 'abut' else g['boxes_overlap']
+        fh, fw = er.region_feat_size(H, W, (H // ds) * (W // ds))
+        assert (fh, fw) == (H // ds, W // ds)
+        assert [er.region_box_indices(b, fh, fw) for b in boxes] == [tuple(i) for i in idx]
+
+
+@pytest.mark.parametrize('tag', ['abut', 'overlap'])
+def test_region_processor(G, tag):
+    g = G['region']
+    attn = _attn_from_state(g['state'], 96)
+    boxes = g['boxes'] if tag == 'abut' else g['boxes_overlap']
+    rl = [(g['region_embs'][i], boxes[i]) for i in range(3)]
+    with torch.no_grad():
+        out = inject.RegionProcessor(g['idx'])(attn, g['hs'], encoder_hidden_states=g['ehs'], region_list=rl,
+                                               height=g['height'], width=g['width'])
+    assert close(out, g['out'][tag], 1e-5)
+    attn_s = _attn_from_state(g['self_state'], None)
+    with torch.no_grad():
+        so = inject.RegionProcessor(0)(attn_s, g['hs'], encoder_hidden_states=None, region_list=[], height=96,
+                                       width=192)
+    assert close(so, g['self_out'], 1e-5)
+
+
+def test_quasi_newton_and_merge(G):
+    g = G['quasi_newton']
+    W = er.update_quasi_newton(g['K'], g['V'], g['W0'], 50)
+    assert close(W, g['Wnew'], 1e-5)
+    W2 = er.update_quasi_newton(g['K2'], g['V2'], g['W02'], 50)
+    assert close(W2, g['Wnew2'], 1e-5)
+    m = G['merge_lora']
+    for k, w in m['sd'].items():
+        d = m['lora'][k.replace('.weight', '.lora_down.weight')]
+        u = m['lora'][k.replace('.weight', '.lora_up.weight')]
+        assert close(er.merge_lora_weight(w, d, u, m['alpha']), m['merged'][k], 1e-6)
+
+
+def test_tiny_unet_with_reference_processors_and_lora(G):
+    """The reference's processors + LoRALinearLayer on the skeleton == the oracle's own installers + inject_lora."""
+    g = G['tiny_unet']
+    u = ou.build_unet(g['unet_seed'], ou.TINY)
+    inject.install_edlora_processors(u)
+    lora = inject.random_lora_state(u, seed=g['lora_seed'])
+    assert inject.inject_lora(u, lora, 1.0) == g['n_lora']
+    with torch.no_grad():
+        y = u(g['latents'], torch.tensor([g['t'], g['t']]), g['ehs']).sample
+    assert close(y, g['out'], 1e-5)
+
+
+def test_schedulers_self_consistency():
+    """DPM-Solver++(2M) restatement: closed-form coefficients == step(), and exact on a linear-in-x0 model."""
+    from oracle.schedulers import DDPMScheduler, DPMSolverMultistepScheduler
+    s = DPMSolverMultistepScheduler()
+    s.set_timesteps(50)
+    assert s.timesteps[0].item() == 999 and len(s.timesteps) == 50 and s.timesteps[-1].item() == 20
+    x = torch.randn(1, 4, 8, 8, generator=torch.Generator().manual_seed(0))
+    x0_prev = torch.zeros_like(x)
+    for i in range(5):
+        eps = torch.randn(x.shape, generator=torch.Generator().manual_seed(100 + i))
+        c_x, c_m0, c_m1, a_s, s_s = s.coefficients(i)
+        x0 = (x - s_s * eps) / a_s
+        manual = c_x * x + c_m0 * x0 + c_m1 * x0_prev
+        x = s.step(eps, s.timesteps[i], x).prev_sample
+        assert torch.allclose(manual, x, rtol=1e-4, atol=1e-5)
+        x0_prev = x0
+    d = DDPMScheduler()
+    x0, n = torch.randn(2, 4, 4, 4), torch.randn(2, 4, 4, 4)
+    t = torch.tensor([10, 900])
+    xt = d.add_noise(x0, n, t)
+    ac = d.alphas_cumprod[t].view(2, 1, 1, 1)
+    assert torch.allclose(xt, ac.sqrt() * x0 + (1 - ac).sqrt() * n)
