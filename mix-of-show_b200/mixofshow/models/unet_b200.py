@@ -1,0 +1,283 @@
+"""B200 `UNet2DConditionModel`: the object the reference's entry points call as
+`unet(sample, t, encoder_hidden_states=..., cross_attention_kwargs=..., down_block_additional_residuals=...).sample`
+(mixofshow/pipelines/pipeline_edlora.py:277, trainer_edlora.py:237, gradient_fusion.py:619,
+pipeline_regionally_t2iadapter.py:556).
+
+It is an nn.Module *container*: parameters live in diffusers-named sub-modules (`down_blocks.0.attentions.0.
+transformer_blocks.0.attn2.to_q`, ...; class names `Attention` / `Transformer2DModel` as diffusers) so that the
+reference's `named_modules()`-driven LoRA injection (trainer_edlora.py:121-133), its processor installers
+(edlora.py:176-218) and its checkpoint key mapping (convert_edlora_to_diffusers.py:43-50) work unchanged.
+`forward` never executes those sub-modules: it packs their weights (plus any LoRALinearLayer / processor descriptors
+found on them) into a `mos_b200.engine.UNetEngine` and runs the captured CUDA step.  No torch arithmetic fallback.
+"""
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+
+from mos_b200.engine import UNetEngine, ehs_to_layer_major
+
+SD15 = dict(in_channels=4, out_channels=4, block_out_channels=(320, 640, 1280, 1280), layers_per_block=2,
+            attention_head_dim=8, cross_attention_dim=768, norm_num_groups=32, sample_size=64)
+
+
+def _no_forward(self, *a, **k):
+    raise RuntimeError(f'{self.__class__.__name__}.forward is not executed on the B200 path: call the UNet '
+                       '(whole-step engine) or an attention processor (operator level) instead')
+
+
+class Attention(nn.Module):
+    """Parameter holder + the attribute surface the processors read."""
+
+    def __init__(self, query_dim, cross_attention_dim=None, heads=8, dim_head=64):
+        super().__init__()
+        inner = heads * dim_head
+        cross = cross_attention_dim if cross_attention_dim is not None else query_dim
+        self.heads, self.scale = heads, dim_head ** -0.5
+        self.upcast_attention = self.upcast_softmax = False
+        self.spatial_norm = self.group_norm = self.norm_cross = None
+        self.residual_connection, self.rescale_output_factor = False, 1.0
+        self.to_q = nn.Linear(query_dim, inner, bias=False)
+        self.to_k = nn.Linear(cross, inner, bias=False)
+        self.to_v = nn.Linear(cross, inner, bias=False)
+        self.to_out = nn.ModuleList([nn.Linear(inner, query_dim), nn.Dropout(0.0)])
+        from mixofshow.models.edlora import AttnProcessor
+        self.processor = AttnProcessor()
+
+    def set_processor(self, processor):
+        self.processor = processor
+
+    def prepare_attention_mask(self, attention_mask, target_length, batch_size=None):
+        assert attention_mask is None
+        return None
+
+    def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, **cross_attention_kwargs):
+        return self.processor(self, hidden_states, encoder_hidden_states=encoder_hidden_states,
+                              attention_mask=attention_mask, **cross_attention_kwargs)
+
+
+class GEGLU(nn.Module):
+    forward = _no_forward
+
+    def __init__(self, d_in, d_out):
+        super().__init__()
+        self.proj = nn.Linear(d_in, d_out * 2)
+
+
+class FeedForward(nn.Module):
+    forward = _no_forward
+
+    def __init__(self, dim):
+        super().__init__()
+        self.net = nn.ModuleList([GEGLU(dim, dim * 4), nn.Dropout(0.0), nn.Linear(dim * 4, dim)])
+
+
+class BasicTransformerBlock(nn.Module):
+    forward = _no_forward
+
+    def __init__(self, dim, heads, dim_head, cross_dim):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn1 = Attention(dim, None, heads, dim_head)
+        self.norm2 = nn.LayerNorm(dim)
+        self.attn2 = Attention(dim, cross_dim, heads, dim_head)
+        self.norm3 = nn.LayerNorm(dim)
+        self.ff = FeedForward(dim)
+
+
+class Transformer2DModel(nn.Module):
+    forward = _no_forward
+
+    def __init__(self, heads, dim_head, channels, cross_dim):
+        super().__init__()
+        self.norm = nn.GroupNorm(32, channels, eps=1e-6)
+        self.proj_in = nn.Conv2d(channels, heads * dim_head, 1)
+        self.transformer_blocks = nn.ModuleList([BasicTransformerBlock(heads * dim_head, heads, dim_head, cross_dim)])
+        self.proj_out = nn.Conv2d(heads * dim_head, channels, 1)
+
+
+class ResnetBlock2D(nn.Module):
+    forward = _no_forward
+
+    def __init__(self, cin, cout, temb=1280):
+        super().__init__()
+        self.norm1 = nn.GroupNorm(32, cin, eps=1e-5)
+        self.conv1 = nn.Conv2d(cin, cout, 3, padding=1)
+        self.time_emb_proj = nn.Linear(temb, cout)
+        self.norm2 = nn.GroupNorm(32, cout, eps=1e-5)
+        self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
+        if cin != cout:
+            self.conv_shortcut = nn.Conv2d(cin, cout, 1)
+
+
+class _Resample(nn.Module):
+    forward = _no_forward
+
+    def __init__(self, c, stride):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 3, stride=stride, padding=1)
+
+
+class _Block(nn.Module):
+    forward = _no_forward
+
+
+class TimestepEmbedding(nn.Module):
+    forward = _no_forward
+
+    def __init__(self, cin, dim):
+        super().__init__()
+        self.linear_1 = nn.Linear(cin, dim)
+        self.linear_2 = nn.Linear(dim, dim)
+
+
+class UNet2DConditionModel(nn.Module):
+    def __init__(self, **cfg):
+        super().__init__()
+        cfg = dict(SD15, **cfg)
+        self.config = SimpleNamespace(**cfg)
+        self.in_channels = cfg['in_channels']
+        ch, L = tuple(cfg['block_out_channels']), cfg['layers_per_block']
+        heads, cross = cfg['attention_head_dim'], cfg['cross_attention_dim']
+        nb = len(ch)
+        self.conv_in = nn.Conv2d(cfg['in_channels'], ch[0], 3, padding=1)
+        self.time_embedding = TimestepEmbedding(ch[0], 4 * ch[0])
+        self.down_blocks = nn.ModuleList()
+        out = ch[0]
+        for i, c in enumerate(ch):
+            cin, out = out, c
+            blk = _Block()
+            if i < nb - 1:
+                blk.attentions = nn.ModuleList([Transformer2DModel(heads, c // heads, c, cross) for _ in range(L)])
+            blk.resnets = nn.ModuleList([ResnetBlock2D(cin if j == 0 else c, c, 4 * ch[0]) for j in range(L)])
+            if i < nb - 1:
+                blk.downsamplers = nn.ModuleList([_Resample(c, 2)])
+            self.down_blocks.append(blk)
+        mid = _Block()
+        mid.attentions = nn.ModuleList([Transformer2DModel(heads, ch[-1] // heads, ch[-1], cross)])
+        mid.resnets = nn.ModuleList([ResnetBlock2D(ch[-1], ch[-1], 4 * ch[0]) for _ in range(2)])
+        self.mid_block = mid
+        self.up_blocks = nn.ModuleList()
+        rev = list(reversed(ch))
+        out = rev[0]
+        for i, c in enumerate(rev):
+            prev, out = out, c
+            cin = rev[min(i + 1, nb - 1)]
+            blk = _Block()
+            if i > 0:
+                blk.attentions = nn.ModuleList([Transformer2DModel(heads, c // heads, c, cross) for _ in range(L + 1)])
+            blk.resnets = nn.ModuleList()
+            for j in range(L + 1):
+                skip = cin if j == L else c
+                rin = prev if j == 0 else c
+                blk.resnets.append(ResnetBlock2D(rin + skip, c, 4 * ch[0]))
+            if i < nb - 1:
+                blk.upsamplers = nn.ModuleList([_Resample(c, 1)])
+            self.up_blocks.append(blk)
+        self.conv_norm_out = nn.GroupNorm(32, ch[0], eps=1e-5)
+        self.conv_out = nn.Conv2d(ch[0], cfg['out_channels'], 3, padding=1)
+        self._engines = {}
+        self.merge_lora = False
+        self.use_graph = True
+
+    # ------------------------------------------------------------------------------------------ descriptors
+    def _fingerprint(self):
+        fp = 0
+        for p in self.parameters():
+            fp = (fp * 1000003 + p._version + (p.data_ptr() & 0xFFFF)) & 0xFFFFFFFFFFFF
+        for m in self.modules():
+            l = getattr(m, '_mos_lora', None)
+            if l is not None:
+                fp = (fp * 1000003 + l.lora_down.weight._version + l.lora_up.weight._version * 7
+                      + int(float(l.alpha) * 1e6)) & 0xFFFFFFFFFFFF
+        return fp
+
+    def _collect_lora(self):
+        lora, alpha = {}, None
+        for name, m in self.named_modules():
+            l = getattr(m, '_mos_lora', None)
+            if l is not None:
+                lora[name + '.lora_down.weight'] = l.lora_down.weight
+                lora[name + '.lora_up.weight'] = l.lora_up.weight
+                a = float(l.alpha)
+                if alpha is not None and abs(alpha - a) > 1e-12:
+                    raise ValueError('all LoRA layers of one UNet must share alpha on the fused path')
+                alpha = a
+        return (lora or None), (1.0 if alpha is None else alpha)
+
+    def _collect_processors(self):
+        """Returns (kind, controller): verifies that the installed cross_attention_idx equals the DFS order."""
+        kinds, controller, idx = set(), None, []
+        for name, m in self.named_modules():
+            if m.__class__.__name__ == 'Attention' and name.endswith('attn2'):
+                p = m.processor
+                kinds.add(p.__class__.__name__)
+                idx.append(getattr(p, 'cross_attention_idx', None))
+                controller = getattr(p, 'controller', controller)
+        if any(i is not None for i in idx) and idx != list(range(len(idx))):
+            raise ValueError(f'cross_attention_idx assignment {idx} does not follow the reference order')
+        if len(kinds) > 1:
+            raise ValueError(f'mixed attention processors {kinds} are not supported')
+        return (kinds.pop() if kinds else 'AttnProcessor'), controller
+
+    def _engine(self, B, H, W, device, emit_probs):
+        key = (B, H, W, str(device), emit_probs)
+        fp = self._fingerprint()
+        ent = self._engines.get(key)
+        if ent is None or ent[0] != fp:
+            lora, alpha = self._collect_lora()
+            c = self.config
+            eng = UNetEngine(self.state_dict(), B, H, W, lora=lora, lora_alpha=alpha, merge_lora=self.merge_lora,
+                             device=device, block_out=tuple(c.block_out_channels), layers=c.layers_per_block,
+                             heads=c.attention_head_dim, cross_dim=c.cross_attention_dim, emit_probs=emit_probs,
+                             use_graph=self.use_graph)
+            self._engines = {k: v for k, v in self._engines.items() if v[0] == fp}
+            self._engines[key] = ent = (fp, eng)
+        return ent[1]
+
+    # ------------------------------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, sample, timestep, encoder_hidden_states, cross_attention_kwargs=None,
+                down_block_additional_residuals=None, return_dict=True):
+        if not sample.is_cuda:
+            raise RuntimeError('the B200 UNet needs CUDA tensors (there is no CPU fallback)')
+        B, _, H, W = sample.shape
+        kind, controller = self._collect_processors()
+        emit = kind == 'EDLoRA_Control_AttnProcessor' and controller is not None \
+            and controller.__class__.__name__ != 'DummyController'
+        eng = self._engine(B, H, W, sample.device, emit)
+        nx = len(eng.xattn_names)
+        if not torch.is_tensor(timestep):
+            timestep = torch.tensor([float(timestep)], device=sample.device)
+        timestep = timestep.to(sample.device, torch.float32).reshape(-1)
+        ehs = encoder_hidden_states
+        if ehs.ndim == 4 and kind == 'AttnProcessor':
+            raise ValueError('layer-wise (4-D) embeddings need the ED-LoRA processors '
+                             '(revise_edlora_unet_attention_forward)')
+        kw = cross_attention_kwargs or {}
+        if kind == 'RegionT2I_AttnProcessor':
+            regs = [(ehs_to_layer_major(emb.to(sample.device), nx), box) for emb, box in kw['region_list']]
+            eng.set_regions(regs, (kw['height'], kw['width']))
+        else:
+            eng.set_regions(None, None)
+        if down_block_additional_residuals is not None:
+            eng.set_adapters([a.to(sample.device).permute(0, 2, 3, 1).reshape(-1, a.shape[1]).to(torch.bfloat16)
+                              for a in down_block_additional_residuals])
+        else:
+            eng.set_adapters(None)
+        eng.use_graph = self.use_graph
+        out = eng.forward(sample.float(), timestep, ehs_to_layer_major(ehs.to(sample.device), nx))
+        if emit:
+            self._feed_controller(eng, controller)
+        out = out.to(sample.dtype).clone()
+        return SimpleNamespace(sample=out) if return_dict else (out,)
+
+    def _feed_controller(self, eng, controller):
+        """Hand the 16 probability maps to the controller in layer order, with the reference's call protocol
+        (`controller(probs, is_cross, place)`, mixofshow/utils/ptp_util.py:37-53)."""
+        nb = len(eng.block_out)
+        n_down = (nb - 1) * eng.layers
+        for i in range(len(eng.xattn_names)):
+            place = 'down' if i < n_down else ('mid' if i == n_down else 'up')
+            key = [k for k in eng.bufs if k[0] == f'probs{i}'][0]
+            controller(eng.bufs[key].clone(), True, place)

@@ -1,0 +1,161 @@
+"""Drop-in for the reference's `mixofshow/pipelines/pipeline_edlora.py`: `bind_concept_prompt` and `EDLoRAPipeline`
+with the same constructor / `set_new_concept_cfg` / `set_controller` / `__call__` surface.
+
+The denoise loop (reference :271-301) runs on the B200 engine: per step one captured UNet graph (CFG batch 2) and
+ONE fused kernel for CFG combine + DPM-Solver++(2M) update + re-duplication of the latents (`mos_cfg_dpmpp_step`).
+Prompt encoding (CLIP) and VAE decode are adjacent components: when `text_encoder` / `vae` torch
+modules are supplied they are used as-is; otherwise pass `prompt_embeds` and request `output_type='latent'`.
+"""
+from types import SimpleNamespace
+from typing import List, Optional, Union
+
+import torch
+
+from mixofshow.models.edlora import (revise_edlora_unet_attention_controller_forward,
+                                     revise_edlora_unet_attention_forward)
+from mos_b200 import ops
+from mos_b200.engine import ehs_to_layer_major
+from mos_b200.scheduler import DPMSolverPP2M
+
+
+def bind_concept_prompt(prompts, new_concept_cfg):
+    """Each prompt becomes 16 layer-specific prompts; `concept_name` -> `concept_token_names[layer]`
+    (reference :18-29). Output order: prompt-major, layer fastest."""
+    if isinstance(prompts, str):
+        prompts = [prompts]
+    new_prompts = []
+    for prompt in prompts:
+        per_layer = [prompt] * 16
+        for concept_name, new_token_cfg in new_concept_cfg.items():
+            per_layer = [p.replace(concept_name, new_name)
+                         for p, new_name in zip(per_layer, new_token_cfg['concept_token_names'])]
+        new_prompts.extend(per_layer)
+    return new_prompts
+
+
+class EDLoRAPipeline:
+    def __init__(self, vae=None, text_encoder=None, tokenizer=None, unet=None, scheduler=None, safety_checker=None,
+                 feature_extractor=None, requires_safety_checker: bool = False):
+        assert unet is not None, 'EDLoRAPipeline needs the B200 UNet'
+        revise_edlora_unet_attention_forward(unet)          # reference :93
+        self.vae, self.text_encoder, self.tokenizer, self.unet = vae, text_encoder, tokenizer, unet
+        self.scheduler = scheduler if scheduler is not None else DPMSolverPP2M()
+        self.vae_scale_factor = 8
+        self.new_concept_cfg = None
+        self.device = torch.device('cuda')
+
+    def to(self, device):
+        self.device = torch.device(device)
+        return self
+
+    def set_new_concept_cfg(self, new_concept_cfg=None):
+        self.new_concept_cfg = new_concept_cfg
+
+    def set_controller(self, controller):
+        self.controller = controller
+        revise_edlora_unet_attention_controller_forward(self.unet, controller)
+
+    # reference :111-190
+    def _encode_prompt(self, prompt, new_concept_cfg, device, num_images_per_prompt, do_classifier_free_guidance,
+                       negative_prompt=None, prompt_embeds=None, negative_prompt_embeds=None):
+        assert num_images_per_prompt == 1, 'only support num_images_per_prompt=1 now'
+        if prompt is not None and isinstance(prompt, str):
+            batch_size = 1
+        elif prompt is not None and isinstance(prompt, list):
+            batch_size = len(prompt)
+        else:
+            batch_size = prompt_embeds.shape[0]
+        if prompt_embeds is None:
+            if self.tokenizer is None or self.text_encoder is None:
+                raise ValueError('no tokenizer / text_encoder supplied: pass prompt_embeds [B,16,77,768]')
+            prompt_extend = bind_concept_prompt(prompt, new_concept_cfg)
+            ids = self.tokenizer(prompt_extend, padding='max_length', max_length=self.tokenizer.model_max_length,
+                                 truncation=True, return_tensors='pt').input_ids
+            prompt_embeds = self.text_encoder(ids.to(device))[0]
+            prompt_embeds = prompt_embeds.reshape(batch_size, -1, *prompt_embeds.shape[1:])   # '(b n) m c -> b n m c'
+        prompt_embeds = prompt_embeds.to(device)
+        bs_embed, layer_num, seq_len, _ = prompt_embeds.shape
+        if do_classifier_free_guidance and negative_prompt_embeds is None:
+            if self.tokenizer is None or self.text_encoder is None:
+                raise ValueError('classifier-free guidance needs negative_prompt_embeds [B,77,768] when no text '
+                                 'encoder is supplied')
+            if negative_prompt is None:
+                uncond_tokens = [''] * batch_size
+            elif type(prompt) is not type(negative_prompt):
+                raise TypeError(f'`negative_prompt` should be the same type to `prompt`, but got '
+                                f'{type(negative_prompt)} != {type(prompt)}.')
+            elif isinstance(negative_prompt, str):
+                uncond_tokens = [negative_prompt]
+            elif batch_size != len(negative_prompt):
+                raise ValueError(f'`negative_prompt`: {negative_prompt} has batch size {len(negative_prompt)}, but '
+                                 f'`prompt`: {prompt} has batch size {batch_size}.')
+            else:
+                uncond_tokens = negative_prompt
+            ids = self.tokenizer(uncond_tokens, padding='max_length', max_length=seq_len, truncation=True,
+                                 return_tensors='pt').input_ids
+            negative_prompt_embeds = self.text_encoder(ids.to(device))[0]
+        if do_classifier_free_guidance:
+            seq_len = negative_prompt_embeds.shape[1]
+            negative_prompt_embeds = negative_prompt_embeds.to(device)
+            negative_prompt_embeds = negative_prompt_embeds.view(batch_size, 1, seq_len, -1).repeat(1, layer_num, 1, 1)
+            prompt_embeds = torch.cat([negative_prompt_embeds, prompt_embeds])
+        return prompt_embeds
+
+    @torch.no_grad()
+    def __call__(self, prompt: Union[str, List[str]] = None, height: Optional[int] = None,
+                 width: Optional[int] = None, num_inference_steps: int = 50, guidance_scale: float = 7.5,
+                 negative_prompt=None, num_images_per_prompt: Optional[int] = 1, eta: float = 0.0, generator=None,
+                 latents: Optional[torch.Tensor] = None, prompt_embeds: Optional[torch.Tensor] = None,
+                 negative_prompt_embeds: Optional[torch.Tensor] = None, output_type: Optional[str] = 'pil',
+                 return_dict: bool = True, callback=None, callback_steps: int = 1, cross_attention_kwargs=None):
+        height = height or self.unet.config.sample_size * self.vae_scale_factor
+        width = width or self.unet.config.sample_size * self.vae_scale_factor
+        if height % 8 != 0 or width % 8 != 0:
+            raise ValueError(f'`height` and `width` have to be divisible by 8 but are {height} and {width}.')
+        if prompt is not None and isinstance(prompt, str):
+            batch_size = 1
+        elif prompt is not None and isinstance(prompt, list):
+            batch_size = len(prompt)
+        else:
+            batch_size = prompt_embeds.shape[0]
+        device = self.device
+        do_cfg = guidance_scale > 1.0
+        assert self.new_concept_cfg is not None
+        prompt_embeds = self._encode_prompt(prompt, self.new_concept_cfg, device, num_images_per_prompt, do_cfg,
+                                            negative_prompt, prompt_embeds=prompt_embeds,
+                                            negative_prompt_embeds=negative_prompt_embeds)
+        self.scheduler.set_timesteps(num_inference_steps, device=device)
+        timesteps = [int(t) for t in self.scheduler.timesteps]
+        h, w = height // self.vae_scale_factor, width // self.vae_scale_factor
+        shape = (batch_size, self.unet.in_channels, h, w)
+        if latents is None:
+            latents = torch.randn(shape, generator=generator, device=generator.device if generator is not None
+                                  else 'cpu').to(device)
+        latents = (latents.to(device, torch.float32) * self.scheduler.init_noise_sigma).contiguous()
+        assert tuple(latents.shape) == shape, f'latents shape {tuple(latents.shape)} != {shape}'
+
+        controller = getattr(self, 'controller', None)
+        x0_prev = torch.zeros_like(latents)
+        unet_in = torch.cat([latents] * 2) if do_cfg else latents.clone()
+        for i, t in enumerate(timesteps):
+            noise_pred = self.unet(unet_in, torch.full((unet_in.shape[0],), float(t), device=device),
+                                   encoder_hidden_states=prompt_embeds,
+                                   cross_attention_kwargs=cross_attention_kwargs).sample
+            # CFG combine + scheduler.step + cat([latents]*2), one kernel (reference :285-290, :273)
+            ops.cfg_dpmpp_step(noise_pred.float().contiguous(), latents, x0_prev, unet_in.view(-1), cfg=do_cfg,
+                               guidance=float(guidance_scale), coef=self.scheduler.coefficients(i))
+            if controller is not None and hasattr(controller, 'step_callback'):
+                dtype = latents.dtype
+                latents = controller.step_callback(latents).to(dtype)
+            if callback is not None and i % callback_steps == 0:
+                callback(i, t, latents)
+        if output_type == 'latent':
+            image = latents
+        else:
+            if self.vae is None:
+                raise ValueError("no VAE supplied: use output_type='latent'")
+            image = self.vae.decode(latents / 0.18215).sample
+            image = (image / 2 + 0.5).clamp(0, 1).cpu().permute(0, 2, 3, 1).float().numpy()
+        if not return_dict:
+            return (image)
+        return SimpleNamespace(images=image, nsfw_content_detected=None)

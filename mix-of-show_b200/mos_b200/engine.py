@@ -511,6 +511,38 @@ class UNetEngine:
                      C=self.block_out[0])
         self.launches += 1
 
+    def set_regions(self, regions, region_hw):
+        """regions: list of (ehs_layers bf16 [n_layers,B,77,768], (sh,sw,eh,ew) box fractions) or None.  The embeddings
+        are copied into static buffers; the captured graph is invalidated only when the box signature changes."""
+        sig = None if not regions else (tuple(tuple(float(v) for v in b) for _, b in regions), tuple(region_hw))
+        if sig != getattr(self, '_region_sig', None):
+            self.graph = None
+            self._region_sig = sig
+        if not regions:
+            self.regions, self.region_hw = None, None
+            return
+        static = []
+        for r, (emb, box) in enumerate(regions):
+            buf = self.buf(f'region_ehs{r}', tuple(self.in_ehs.shape))
+            buf.copy_(emb)
+            static.append((buf, tuple(float(v) for v in box)))
+        self.regions, self.region_hw = static, tuple(region_hw)
+
+    def set_adapters(self, adapters):
+        """adapters: list of per-down-block residuals as NHWC bf16 [B*HW_l, C_l] (T2I-Adapter features) or None."""
+        has = adapters is not None
+        if has != (self.adapters is not None):
+            self.graph = None
+        if not has:
+            self.adapters = None
+            return
+        static = []
+        for l, a in enumerate(adapters):
+            buf = self.buf(f'adapter{l}', tuple(a.shape))
+            buf.copy_(a)
+            static.append(buf)
+        self.adapters = static
+
     def forward(self, latents, timesteps, ehs_layers):
         """latents fp32 NCHW [B,4,H,W]; timesteps [B]; ehs_layers [16,B,77,768] (layer-major). -> eps fp32 NCHW."""
         self.in_latents.copy_(latents)

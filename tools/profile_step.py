@@ -1,0 +1,36 @@
+"""Run the denoise step eagerly (no CUDA graph) a few times: the command ncu wraps for launch lists / full captures.
+   ncu --metrics gpu__time_duration.sum --clock-control none -s <skip> -c <n> --csv --log-file out.csv \
+       python tools/profile_step.py --runs 2
+Prints the number of kernel launches per step so that -s / -c can be chosen."""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, 'mix-of-show_b200')):
+    sys.path.insert(0, p)
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument('--runs', type=int, default=2)
+ap.add_argument('--tiny', action='store_true')
+ap.add_argument('--merged', action='store_true')
+ap.add_argument('--height', type=int, default=64)
+ap.add_argument('--width', type=int, default=64)
+args = ap.parse_args()
+from mos_b200.engine import UNetEngine, ehs_to_layer_major  # noqa: E402
+
+unet, sd, lora, lat, ehs, cfg = bench.build_workload(args.tiny)
+kw = dict(block_out=cfg['block_out_channels'], layers=cfg['layers_per_block']) if cfg else {}
+eng = UNetEngine(sd, 2, args.height, args.width, lora=lora, merge_lora=args.merged, use_graph=False, **kw)
+nx = len(eng.xattn_names)
+eng.in_ehs.copy_(ehs_to_layer_major(ehs[:, :nx].cuda(), nx))
+eng.in_latents.normal_()
+eng.in_t.fill_(981.0)
+torch.cuda.synchronize()
+for _ in range(args.runs):
+    eng._run()
+torch.cuda.synchronize()
+print('launches per step:', eng.launches)
