@@ -29,8 +29,11 @@ nx = len(eng.xattn_names)
 eng.in_ehs.copy_(ehs_to_layer_major(ehs[:, :nx].cuda(), nx))
 eng.in_latents.normal_()
 eng.in_t.fill_(981.0)
-torch.cuda.synchronize()
-for _ in range(args.runs):
+for _ in range(args.runs):          # warm-up runs (allocate scratch, set attributes)
     eng._run()
 torch.cuda.synchronize()
+torch.cuda.profiler.start()         # use with: ncu --profile-from-start off
+eng._run()
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print('launches per step:', eng.launches)
