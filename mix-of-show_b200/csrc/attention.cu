@@ -26,17 +26,22 @@ struct AttnCfg {
   static constexpr int DV = ((D + 15) / 16) * 16;
   static constexpr int BKV = D <= 80 ? 128 : 64;
   static constexpr int KVCH = BKV / 64;
-  static constexpr int STAGES = D <= 40 ? 3 : 2;
+  static constexpr int STAGES = 2;
+  // d = 40: single S / P buffers and 256 TMEM columns so that TWO CTAs share an SM (the softmax of one hides the
+  // MMA / TMEM latency of the other); larger head sizes keep double buffering and one CTA per SM.
+  static constexpr int SB = D <= 40 ? 1 : 2;
+  static constexpr int PB = D <= 40 ? 1 : 2;
+  static constexpr int MINB = D <= 40 ? 2 : 1;
   static constexpr int Q_BYTES = QCH * 128 * 128;
   static constexpr int K_BYTES = QCH * BKV * 128;
   static constexpr int V_BYTES = KVCH * DV * 128;
   static constexpr int P_BYTES = KVCH * 128 * 128;
   static constexpr int O_STRIDE = ((DV + 63) / 64) * 64;
   static constexpr int S_COL0 = 0;
-  static constexpr int O_COL0 = 2 * BKV;
-  static constexpr int TMEM_COLS = 512;
-  static constexpr int SMEM_BYTES = Q_BYTES + STAGES * (K_BYTES + V_BYTES) + 2 * P_BYTES + 1024;
-  static_assert(O_COL0 + 2 * O_STRIDE <= 512, "TMEM budget");
+  static constexpr int O_COL0 = SB * BKV;
+  static constexpr int TMEM_COLS = (O_COL0 + 2 * O_STRIDE <= 256) ? 256 : 512;
+  static constexpr int SMEM_BYTES = Q_BYTES + STAGES * (K_BYTES + V_BYTES) + PB * P_BYTES + 1024;
+  static_assert(O_COL0 + 2 * O_STRIDE <= TMEM_COLS, "TMEM budget");
 };
 
 struct AttnDev {
@@ -48,7 +53,7 @@ struct AttnDev {
 };
 
 template <int D>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, AttnCfg<D>::MINB)
 attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
             const __grid_constant__ CUtensorMap tmV, const AttnDev p) {
   using C = AttnCfg<D>;
@@ -91,6 +96,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_holder;
+  pdl_wait();               // Q / K / V^T come from the previous kernel in the stream
+  pdl_launch_dependents();
 
   if (warp == 4) {
     // ================================================================= TMA producer
@@ -120,9 +127,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       mbar_wait(&q_full, 0);
       for (int j = 0; j <= T; ++j) {
         if (j < T) {
-          const int st = j % C::STAGES, sb = j & 1;
+          const int st = j % C::STAGES, sb = j % C::SB;
           mbar_wait(&kv_full[st], (j / C::STAGES) & 1);
-          mbar_wait(&s_empty[sb], ((j >> 1) & 1) ^ 1);
+          mbar_wait(&s_empty[sb], ((j / C::SB) & 1) ^ 1);
           tc_fence_after();
           uint8_t* sK = sKV + st * (C::K_BYTES + C::V_BYTES);
 #pragma unroll
@@ -134,9 +141,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           umma_commit(&s_full[sb]);
         }
         if (j >= 1) {
-          const int jj = j - 1, pb = jj & 1, st = jj % C::STAGES;
-          mbar_wait(&p_full[pb], (jj >> 1) & 1);
-          mbar_wait(&o_empty[pb], ((jj >> 1) & 1) ^ 1);
+          const int jj = j - 1, pb = jj % C::PB, ob = jj & 1, st = jj % C::STAGES;
+          mbar_wait(&p_full[pb], (jj / C::PB) & 1);
+          mbar_wait(&o_empty[ob], ((jj >> 1) & 1) ^ 1);
           tc_fence_after();
           uint8_t* sV = sKV + st * (C::K_BYTES + C::V_BYTES) + C::K_BYTES;
           uint8_t* sPb = sP + pb * C::P_BYTES;
@@ -145,9 +152,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           for (int kk = 0; kk < ksteps; ++kk) {
             uint64_t ad = make_desc_sw128(smem_u32(sPb + (kk >> 2) * 16384)) + 2 * (kk & 3);
             uint64_t bd = make_desc_sw128(smem_u32(sV + (kk >> 2) * (C::DV * 128))) + 2 * (kk & 3);
-            umma_bf16(tmem + C::O_COL0 + pb * C::O_STRIDE, ad, bd, idesc_o, kk > 0 ? 1u : 0u);
+            umma_bf16(tmem + C::O_COL0 + ob * C::O_STRIDE, ad, bd, idesc_o, kk > 0 ? 1u : 0u);
           }
-          umma_commit(&o_full[pb]);
+          umma_commit(&o_full[ob]);
           umma_commit(&p_empty[pb]);
           umma_commit(&kv_empty[st]);
         }
@@ -180,9 +187,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     };
 
     for (int j = 0; j < T; ++j) {
-      const int sb = j & 1;
+      const int sb = j % C::SB, pbuf = j % C::PB;
       const int kv_valid = min(C::BKV, p.nk - j * C::BKV);
-      mbar_wait(&s_full[sb], (j >> 1) & 1);
+      mbar_wait(&s_full[sb], (j / C::SB) & 1);
       tc_fence_after();
       const uint32_t ts = trow + C::S_COL0 + sb * C::BKV;
       // pass 1: row max
@@ -199,8 +206,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       const float m_new = fmaxf(m_run, mx * p.scale_log2);
       const float alpha = exp2f(m_run - m_new);
       // pass 2: probabilities -> bf16 -> swizzled smem
-      mbar_wait(&p_empty[sb], ((j >> 1) & 1) ^ 1);
-      uint8_t* sPb = sP + sb * C::P_BYTES;
+      mbar_wait(&p_empty[pbuf], ((j / C::PB) & 1) ^ 1);
+      uint8_t* sPb = sP + pbuf * C::P_BYTES;
       float rs = 0.f;
 #pragma unroll 1
       for (int c = 0; c < C::BKV / 32; ++c) {
@@ -246,7 +253,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       tc_fence_before();
       mbar_arrive(&s_empty[sb]);
       fence_proxy_async_smem();
-      mbar_arrive(&p_full[sb]);
+      mbar_arrive(&p_full[pbuf]);
       l_run = l_run * alpha + rs;
       m_run = m_new;
       if (j >= 1) accumulate(j - 1, alpha_prev);
@@ -318,8 +325,7 @@ static int launch_attn(const void* Q, const void* K, const void* Vt, void* out, 
     configured = true;
   }
   dim3 grid((unsigned)ceil_div(nq, 128), (unsigned)BH);
-  attn_kernel<D><<<grid, 192, C::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
-  MOS_CHECK_LAUNCH();
+  MOS_CHECK_CUDA(launch_pdl(attn_kernel<D>, grid, dim3(192), (size_t)C::SMEM_BYTES, stream, tmQ, tmK, tmV, p));
   return MOS_OK;
 }
 

@@ -11,6 +11,8 @@ namespace mos {
 // ---------------------------------------------------------------------------------- timestep embedding
 // out[b, :] = [cos(t_b * f_i) | sin(t_b * f_i)], f_i = exp(-ln(10000) * i / half)   (flip_sin_to_cos, shift 0)
 __global__ void timestep_embed_kernel(const float* __restrict__ t, int dim, float* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int b = blockIdx.x, half = dim / 2;
   for (int i = threadIdx.x; i < half; i += blockDim.x) {
     float f = expf(-9.210340371976184f * (float)i / (float)half);
@@ -25,6 +27,8 @@ template <int NB>
 __global__ void gemv_kernel(const float* __restrict__ x, int K, const __nv_bfloat16* __restrict__ W,
                             const float* __restrict__ bias, int N, int act_in, int act_out, float* __restrict__ out,
                             long long ldo) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int n = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
@@ -70,6 +74,8 @@ __global__ void gemv_kernel(const float* __restrict__ x, int K, const __nv_bfloa
 __global__ void conv_in_kernel(const float* __restrict__ x, int B, int Cin, int H, int W,
                                const float* __restrict__ w, const float* __restrict__ bias, int Cout,
                                __nv_bfloat16* __restrict__ y, long long ldy) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int oct = Cout / 8;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * H * W * oct;
@@ -111,6 +117,8 @@ __global__ void conv_in_kernel(const float* __restrict__ x, int B, int Cin, int 
 __global__ void conv_out_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C,
                                 const float* __restrict__ w, const float* __restrict__ bias, int Cout,
                                 float* __restrict__ y) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long pix = (long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (pix >= (long long)B * H * W) return;
@@ -158,6 +166,8 @@ __global__ void conv_out_kernel(const __nv_bfloat16* __restrict__ x, int B, int 
 // y[b, 2h+i, 2w+j, :] = x[b, h, w, :]   (F.interpolate nearest, scale 2)
 __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int B, int H, int W, int C,
                                   __nv_bfloat16* __restrict__ y) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int oct = C / 8;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * 2 * H * 2 * W * oct;
@@ -174,6 +184,8 @@ __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, long long
 // col[(b,ho,wo), tap*C + c] = x[b, 2ho+kh-1, 2wo+kw-1, c] (zero outside): Downsample2D conv 3x3 / stride 2 / pad 1
 __global__ void im2col_s2_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int B, int H, int W, int C,
                                  __nv_bfloat16* __restrict__ col) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int oct = C / 8, Ho = H / 2, Wo = W / 2;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * Ho * Wo * 9 * oct;
@@ -195,6 +207,8 @@ __global__ void im2col_s2_kernel(const __nv_bfloat16* __restrict__ x, long long 
 // x[m, :C] += r[m, :C]   (bf16, row pitches ldx / ldr)
 __global__ void add_rows_kernel(__nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ r,
                                 long long ldr, long long M, int C) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int oct = C / 8;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= M * oct) return;
@@ -218,6 +232,8 @@ __global__ void cfg_dpm_step_kernel(const float* __restrict__ noise_pred, float*
                                     float* __restrict__ x0_prev, float* __restrict__ unet_in, long long n, int cfg,
                                     float guidance, float c_x, float c_m0, float c_m1, float alpha_s,
                                     float sigma_s, float* __restrict__ t_out, int t_count, float t_next) {
+  pdl_wait();
+  pdl_launch_dependents();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t_out != nullptr && i < t_count) t_out[i] = t_next;  // timestep of the next UNet call
   if (i >= n) return;
@@ -248,6 +264,8 @@ struct RegionBoxes {
 __global__ void region_combine_kernel(const __nv_bfloat16* __restrict__ glob, const __nv_bfloat16* const* __restrict__ regs,
                                       RegionBoxes rb, int B, int FH, int FW, int C, long long ld,
                                       __nv_bfloat16* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int oct = C / 8;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * FH * FW * oct;
@@ -293,8 +311,7 @@ static inline unsigned nblk(long long total, int threads) { return (unsigned)((t
 
 extern "C" int mos_timestep_embedding(const float* t, int32_t B, int32_t dim, float* out, void* stream) {
   MOS_CHECK_ARG(t && out && B > 0 && dim % 2 == 0, "mos_timestep_embedding: bad arguments");
-  timestep_embed_kernel<<<B, 160, 0, STREAM(stream)>>>(t, dim, out);
-  MOS_CHECK_LAUNCH();
+  MOS_CHECK_CUDA(launch_pdl(timestep_embed_kernel, dim3(B), dim3(160), 0, STREAM(stream), t, dim, out));
   return MOS_OK;
 }
 
@@ -307,13 +324,15 @@ extern "C" int mos_gemv_bf16(const float* x, int32_t nb, int32_t K, const void* 
   const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(W);
 #define GEMV_CASE(NB)                                                                                   \
   case NB:                                                                                              \
-    gemv_kernel<NB><<<grid, block, 0, STREAM(stream)>>>(x, K, w, bias, N, act_in, act_out, out, ldo); \
+    rc_ = launch_pdl(gemv_kernel<NB>, grid, block, 0, STREAM(stream), x, (int)K, w, bias, (int)N, (int)act_in, \
+                     (int)act_out, out, (long long)ldo);                                        \
     break;
+  cudaError_t rc_ = cudaSuccess;
   switch (nb) {
     GEMV_CASE(1) GEMV_CASE(2) GEMV_CASE(3) GEMV_CASE(4) GEMV_CASE(5) GEMV_CASE(6) GEMV_CASE(7) GEMV_CASE(8)
   }
 #undef GEMV_CASE
-  MOS_CHECK_LAUNCH();
+  MOS_CHECK_CUDA(rc_);
   return MOS_OK;
 }
 
@@ -321,9 +340,8 @@ extern "C" int mos_conv_in(const float* x, int32_t B, int32_t Cin, int32_t H, in
                            const float* bias, int32_t Cout, void* y, int64_t ldy, void* stream) {
   MOS_CHECK_ARG(x && w && bias && y && Cout % 8 == 0 && ldy % 8 == 0, "mos_conv_in: bad arguments");
   long long total = (long long)B * H * W * (Cout / 8);
-  conv_in_kernel<<<nblk(total, 256), 256, 0, STREAM(stream)>>>(x, B, Cin, H, W, w, bias, Cout,
-                                                               reinterpret_cast<__nv_bfloat16*>(y), ldy);
-  MOS_CHECK_LAUNCH();
+  MOS_CHECK_CUDA(launch_pdl(conv_in_kernel, dim3(nblk(total, 256)), dim3(256), 0, STREAM(stream), x, B, Cin, H, W, w, bias, Cout,
+                                                               reinterpret_cast<__nv_bfloat16*>(y), ldy));
   return MOS_OK;
 }
 
@@ -331,9 +349,8 @@ extern "C" int mos_conv_out(const void* x, int32_t B, int32_t H, int32_t W, int3
                             const float* bias, int32_t Cout, float* y, void* stream) {
   MOS_CHECK_ARG(x && w && bias && y && C % 8 == 0 && Cout <= 4, "mos_conv_out: bad arguments");
   long long pix = (long long)B * H * W;
-  conv_out_kernel<<<nblk(pix, 8), 256, 0, STREAM(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), B, H, W, C, w,
-                                                            bias, Cout, y);
-  MOS_CHECK_LAUNCH();
+  MOS_CHECK_CUDA(launch_pdl(conv_out_kernel, dim3(nblk(pix, 8)), dim3(256), 0, STREAM(stream), reinterpret_cast<const __nv_bfloat16*>(x), B, H, W, C, w,
+                                                            bias, Cout, y));
   return MOS_OK;
 }
 
@@ -341,9 +358,8 @@ extern "C" int mos_upsample2x(const void* x, int64_t ldx, int32_t B, int32_t H, 
                               void* stream) {
   MOS_CHECK_ARG(x && y && C % 8 == 0 && ldx % 8 == 0, "mos_upsample2x: bad arguments");
   long long total = (long long)B * 4 * H * W * (C / 8);
-  upsample2x_kernel<<<nblk(total, 256), 256, 0, STREAM(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, B, H,
-                                                                  W, C, reinterpret_cast<__nv_bfloat16*>(y));
-  MOS_CHECK_LAUNCH();
+  MOS_CHECK_CUDA(launch_pdl(upsample2x_kernel, dim3(nblk(total, 256)), dim3(256), 0, STREAM(stream), reinterpret_cast<const __nv_bfloat16*>(x), ldx, B, H,
+                                                                  W, C, reinterpret_cast<__nv_bfloat16*>(y)));
   return MOS_OK;
 }
 
@@ -351,17 +367,16 @@ extern "C" int mos_im2col_s2(const void* x, int64_t ldx, int32_t B, int32_t H, i
                              void* stream) {
   MOS_CHECK_ARG(x && col && C % 8 == 0 && ldx % 8 == 0 && H % 2 == 0 && W % 2 == 0, "mos_im2col_s2: bad arguments");
   long long total = (long long)B * (H / 2) * (W / 2) * 9 * (C / 8);
-  im2col_s2_kernel<<<nblk(total, 256), 256, 0, STREAM(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, B, H,
-                                                                 W, C, reinterpret_cast<__nv_bfloat16*>(col));
-  MOS_CHECK_LAUNCH();
+  MOS_CHECK_CUDA(launch_pdl(im2col_s2_kernel, dim3(nblk(total, 256)), dim3(256), 0, STREAM(stream), reinterpret_cast<const __nv_bfloat16*>(x), ldx, B, H,
+                                                                 W, C, reinterpret_cast<__nv_bfloat16*>(col)));
   return MOS_OK;
 }
 
 extern "C" int mos_add_rows(void* x, int64_t ldx, const void* r, int64_t ldr, int64_t M, int32_t C, void* stream) {
   MOS_CHECK_ARG(x && r && C % 8 == 0 && ldx % 8 == 0 && ldr % 8 == 0, "mos_add_rows: bad arguments");
-  add_rows_kernel<<<nblk(M * (C / 8), 256), 256, 0, STREAM(stream)>>>(
-      reinterpret_cast<__nv_bfloat16*>(x), ldx, reinterpret_cast<const __nv_bfloat16*>(r), ldr, M, C);
-  MOS_CHECK_LAUNCH();
+  MOS_CHECK_CUDA(launch_pdl(add_rows_kernel, dim3(nblk(M * (C / 8), 256)), dim3(256), 0, STREAM(stream),
+                            reinterpret_cast<__nv_bfloat16*>(x), (long long)ldx,
+                            reinterpret_cast<const __nv_bfloat16*>(r), (long long)ldr, (long long)M, (int)C));
   return MOS_OK;
 }
 
@@ -369,9 +384,8 @@ extern "C" int mos_cfg_dpmpp_step(const float* noise_pred, float* latents, float
                                   int32_t cfg, float guidance, float c_x, float c_m0, float c_m1, float alpha_s,
                                   float sigma_s, float* t_out, int32_t t_count, float t_next, void* stream) {
   MOS_CHECK_ARG(noise_pred && latents && x0_prev && n > 0, "mos_cfg_dpmpp_step: bad arguments");
-  cfg_dpm_step_kernel<<<nblk(n, 256), 256, 0, STREAM(stream)>>>(noise_pred, latents, x0_prev, unet_in, n, cfg, guidance,
-                                                                c_x, c_m0, c_m1, alpha_s, sigma_s, t_out, t_count, t_next);
-  MOS_CHECK_LAUNCH();
+  MOS_CHECK_CUDA(launch_pdl(cfg_dpm_step_kernel, dim3(nblk(n, 256)), dim3(256), 0, STREAM(stream), noise_pred, latents, x0_prev, unet_in, n, cfg, guidance,
+                                                                c_x, c_m0, c_m1, alpha_s, sigma_s, t_out, t_count, t_next));
   return MOS_OK;
 }
 
@@ -385,9 +399,8 @@ extern "C" int mos_region_combine(const void* glob, const void* const* region_pt
   for (int r = 0; r < nregions; ++r)
     for (int k = 0; k < 4; ++k) rb.box[r][k] = boxes_host[r * 4 + k];
   long long total = (long long)B * FH * FW * (C / 8);
-  region_combine_kernel<<<nblk(total, 256), 256, 0, STREAM(stream)>>>(
+  MOS_CHECK_CUDA(launch_pdl(region_combine_kernel, dim3(nblk(total, 256)), dim3(256), 0, STREAM(stream), 
       reinterpret_cast<const __nv_bfloat16*>(glob), reinterpret_cast<const __nv_bfloat16* const*>(region_ptrs_dev), rb,
-      B, FH, FW, C, ld, reinterpret_cast<__nv_bfloat16*>(out));
-  MOS_CHECK_LAUNCH();
+      B, FH, FW, C, ld, reinterpret_cast<__nv_bfloat16*>(out)));
   return MOS_OK;
 }

@@ -14,6 +14,8 @@ constexpr int GN_GROUPS = 32;
 __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int HW, int C,
                                 int rows_per_chunk, float* __restrict__ partial) {
   extern __shared__ float red[];  // [blockDim][16]: per-thread channel sums / sums of squares
+  pdl_wait();
+  pdl_launch_dependents();
   const int oct = C / 8;
   const int b = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
   const int lanes = blockDim.x / oct;  // row lanes; blockDim is a multiple of oct
@@ -62,20 +64,31 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long l
                                 const float* __restrict__ beta, float eps, int silu_act, int rows_per_block,
                                 __nv_bfloat16* __restrict__ y, long long ldy) {
   __shared__ float mean[GN_GROUPS], rstd[GN_GROUPS];
+  pdl_wait();
+  pdl_launch_dependents();
   const int b = blockIdx.y;
   const int cpg = C / GN_GROUPS;
-  if (threadIdx.x < GN_GROUPS) {
+  if (threadIdx.x < GN_GROUPS * 4) {   // blockDim >= 160 always
+    // 4 threads per group sum the per-chunk partials (fixed order -> reproducible), then a shuffle tree
+    const int g = threadIdx.x >> 2, sub = threadIdx.x & 3;
     float s = 0.f, q = 0.f;
-    for (int c = 0; c < nchunks; ++c) {
-      const float* src = partial + (((long long)b * nchunks + c) * GN_GROUPS + threadIdx.x) * 2;
-      s += src[0];
-      q += src[1];
+    for (int c = sub; c < nchunks; c += 4) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(partial + (((long long)b * nchunks + c) * GN_GROUPS + g) * 2));
+      s += v.x;
+      q += v.y;
     }
-    const float n = (float)HW * (float)cpg;
-    const float m = s / n;
-    const float var = fmaxf(q / n - m * m, 0.f);
-    mean[threadIdx.x] = m;
-    rstd[threadIdx.x] = rsqrtf(var + eps);
+#pragma unroll
+    for (int d = 2; d > 0; d >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, d);
+      q += __shfl_xor_sync(0xffffffffu, q, d);
+    }
+    if (sub == 0) {
+      const float n = (float)HW * (float)cpg;
+      const float m = s / n;
+      const float var = fmaxf(q / n - m * m, 0.f);
+      mean[g] = m;
+      rstd[g] = rsqrtf(var + eps);
+    }
   }
   __syncthreads();
   const int oct = C / 8;
@@ -120,6 +133,8 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long l
 __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, long long M, int C,
                                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                  __nv_bfloat16* __restrict__ y, long long ldy) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long row = (long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -216,13 +231,13 @@ extern "C" int mos_groupnorm_fwd(const void* x, int64_t ldx, int32_t B, int32_t 
   MOS_CHECK_ARG((long long)B * nchunks * GN_GROUPS * 2 <= partial_capacity_floats,
                 "mos_groupnorm_fwd: partial workspace too small (need %lld floats)",
                 (long long)B * nchunks * GN_GROUPS * 2);
-  gn_stats_kernel<<<dim3(nchunks, B), threads, threads * 16 * sizeof(float), stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, HW, C,
-                                                            rows_per_chunk, partial);
-  MOS_CHECK_LAUNCH();
-  gn_apply_kernel<<<dim3(nchunks, B), threads, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), ldx, HW, C, partial, nchunks, gamma, beta, eps, silu_act,
-      rows_per_chunk, reinterpret_cast<__nv_bfloat16*>(y), ldy);
-  MOS_CHECK_LAUNCH();
+  MOS_CHECK_CUDA(launch_pdl(gn_stats_kernel, dim3(nchunks, B), dim3(threads), threads * 16 * sizeof(float), stream,
+                            reinterpret_cast<const __nv_bfloat16*>(x), (long long)ldx, (int)HW, (int)C, rows_per_chunk,
+                            partial));
+  MOS_CHECK_CUDA(launch_pdl(gn_apply_kernel, dim3(nchunks, B), dim3(threads), 0, stream,
+                            reinterpret_cast<const __nv_bfloat16*>(x), (long long)ldx, (int)HW, (int)C,
+                            (const float*)partial, nchunks, gamma, beta, eps, (int)silu_act, rows_per_chunk,
+                            reinterpret_cast<__nv_bfloat16*>(y), (long long)ldy));
   return MOS_OK;
 }
 
@@ -232,9 +247,8 @@ extern "C" int mos_layernorm_fwd(const void* x, int64_t ldx, int64_t M, int32_t 
   MOS_CHECK_ARG(x && y && gamma && beta, "mos_layernorm_fwd: NULL pointer");
   MOS_CHECK_ARG(C % 8 == 0 && C <= 1280 && ldx % 8 == 0 && ldy % 8 == 0, "mos_layernorm_fwd: bad C=%d", C);
   const int warps = 8;
-  layernorm_kernel<<<(unsigned)ceil_div(M, warps), warps * 32, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), ldx, M, C, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(y),
-      ldy);
-  MOS_CHECK_LAUNCH();
+  MOS_CHECK_CUDA(launch_pdl(layernorm_kernel, dim3((unsigned)ceil_div(M, warps)), dim3(warps * 32), 0, stream,
+                            reinterpret_cast<const __nv_bfloat16*>(x), (long long)ldx, (long long)M, (int)C, gamma, beta,
+                            eps, reinterpret_cast<__nv_bfloat16*>(y), (long long)ldy));
   return MOS_OK;
 }
