@@ -70,6 +70,11 @@ typedef struct mos_gemm_args {
 
 int mos_gemm_bf16(const mos_gemm_args* args, void* stream);
 
+/* Profiling aid: register a device buffer of 64 uint64 (or NULL to disable); the first 8 CTAs of every subsequent
+ * mos_gemm_bf16 launch store %globaltimer stamps [start, setup done, pdl wait done, first TMA landed, epilogue
+ * prefetch done, accumulators ready, accumulators drained, tile written]. */
+int mos_debug_set_timeline(void* buf);
+
 /* Sum split-K partials and apply bias / bias_batch / residual -> bf16 [M, ldc]. */
 int mos_splitk_finalize(const float* partial, int32_t splits, int64_t M, int64_t N, const float* bias,
                         const float* bias_batch, int64_t rows_per_batch, int64_t bias_batch_ld,

@@ -172,7 +172,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 
     auto accumulate = [&](int jj, float a) {
       const int ob = jj & 1;
-      mbar_wait(&o_full[ob], (jj >> 1) & 1);
+      if (lane == 0) mbar_wait(&o_full[ob], (jj >> 1) & 1);   // one polling lane per warp
+      __syncwarp();
       tc_fence_after();
 #pragma unroll
       for (int c = 0; c < C::DV / 16; ++c) {
@@ -189,7 +190,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     for (int j = 0; j < T; ++j) {
       const int sb = j % C::SB, pbuf = j % C::PB;
       const int kv_valid = min(C::BKV, p.nk - j * C::BKV);
-      mbar_wait(&s_full[sb], (j / C::SB) & 1);
+      if (lane == 0) mbar_wait(&s_full[sb], (j / C::SB) & 1);
+      __syncwarp();
       tc_fence_after();
       const uint32_t ts = trow + C::S_COL0 + sb * C::BKV;
       // pass 1: row max
@@ -206,7 +208,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       const float m_new = fmaxf(m_run, mx * p.scale_log2);
       const float alpha = exp2f(m_run - m_new);
       // pass 2: probabilities -> bf16 -> swizzled smem
-      mbar_wait(&p_empty[pbuf], ((j / C::PB) & 1) ^ 1);
+      if (lane == 0) mbar_wait(&p_empty[pbuf], ((j / C::PB) & 1) ^ 1);
+      __syncwarp();
       uint8_t* sPb = sP + pbuf * C::P_BYTES;
       float rs = 0.f;
 #pragma unroll 1

@@ -2,15 +2,21 @@
 //
 //   out[m,n] = epilogue( sum_k A[m,k] W[n,k] )        A, W bf16 K-major; fp32 accumulation in TMEM
 //
-// One CTA computes one 128 x 160 output tile (160 divides every SD1.5 channel count: 320/640/1280/...),
-// optionally one split of the K range.  Roles (192 threads):
-//   warp 0      TMA producer   cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x (160|176) x 16)
-//   warps 2..5  epilogue       tcgen05.ld (32x32b) -> registers -> fused epilogue -> global
+// Persistent kernel: one CTA per SM loops over 128 x 160 output tiles (160 divides every SD1.5 channel count).
+// CTAs are grouped in thread-block clusters of CX x CM (CX = 2 along N, CM = 1/2/4 along M): the A tile is shared by
+// the CX column neighbours and the W tile by the CM row neighbours, so every CTA fetches only 1/CX of A and 1/CM of W
+// from L2 and TMA-multicasts it to its peers (the mainloop is L2-bandwidth bound without this: 73 FLOP/B per tile).
+// Roles (192 threads):
+//   warp 0      TMA producer   cp.async.bulk.tensor(.multicast) -> 128B-swizzled smem ring, mbarrier complete_tx
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x (160|176) x 16), 2 accumulator stages
+//   warps 2..5  epilogue       tcgen05.ld (32x32b) -> registers -> fused epilogue -> smem staging -> coalesced stores;
+//                              runs concurrently with the next tile's mainloop
 // LoRA fusion (edlora.py:244-246): the rank-padded down matrix [16, K] rides along as 16 extra B rows, so the
 // same MMA also produces t = x * down^T in TMEM columns 160..175; the epilogue adds t * (alpha*up)^T.
 // Convolution: the A tile is a TW x TH x TB pixel patch of the NHWC activation fetched by a 4-D tensor map at
 // the tap-shifted coordinate; TMA out-of-bounds zero fill implements the padding.
+#include <stdlib.h>
+
 #include "common.h"
 #include "tc.cuh"
 
@@ -29,6 +35,8 @@ constexpr int ACC_STRIDE = 256;
 constexpr int STG_PITCH = BN * 2 + 16;    // padded row pitch of the epilogue staging tile (bank-conflict free)
 constexpr int STG_BYTES = BM * STG_PITCH;  // 43008
 constexpr int EPI_SMEM_BYTES = STG_BYTES + 4 * BN * 4 + BN * 16;
+constexpr int EPI_THREADS = 256;           // 8 epilogue warps: 2 per TMEM lane quadrant, each half of the tile columns
+constexpr int NUM_THREADS = 64 + EPI_THREADS;
 constexpr int MAX_DYN_SMEM = 227 * 1024 - 2048;  // leave room for the static barriers
 
 struct GemmDev {
@@ -36,12 +44,15 @@ struct GemmDev {
   int kb_total;        // number of 64-wide k blocks over the whole reduction (conv: 9 * C/64)
   int kb_per_split;
   int stages;
-  int conv, H, W, B, kc_per_tap, TW, TH, TB, tiles_w, tiles_h;
+  int conv, H, W, B, kc_per_tap, TW, TH, TB, lgTW, lgTH, tiles_w, tiles_h;
+  int half_dim;        // conv, CX == 2: which box dimension (1 = W, 2 = H, 3 = B) is split between the A halves
+  int half_off;        // coordinate offset of the second half along that dimension
   int lora;
   int geglu;
   int out_mode;
   int splits;
-  int n_tiles, total_items, nbatch;
+  int n_tiles, m_tiles, total_super, nbatch;
+  int cx, cm;          // cluster shape (N x M)
   float* partial;
   const float* bias;
   const float* bias_batch;
@@ -69,7 +80,9 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v)
   *reinterpret_cast<uint4*>(dst) = u;
 }
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // epilogue warps only
+__device__ __forceinline__ void epi_bar() {  // epilogue warps only
+  asm volatile("bar.sync 1, %0;" ::"r"((int)blockDim.x - 64) : "memory");
+}
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
@@ -77,15 +90,29 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
+// ---- optional in-kernel timeline (profiling aid): when a buffer is registered through mos_debug_set_timeline, the
+// first 8 CTAs of every gemm launch record %globaltimer stamps (ns) at their phase boundaries.
+__device__ unsigned long long* g_timeline = nullptr;
+__device__ __forceinline__ void stamp(int slot) {
+  unsigned long long* tl = g_timeline;
+  if (tl != nullptr && blockIdx.x < 8) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    tl[blockIdx.x * 8 + slot] = t;
+  }
+}
+
 struct TileCoord {
   int n0, m0, cb0, ch0, cw0, split;
 };
-__device__ __forceinline__ TileCoord item_coord(const GemmDev& p, int w) {
+// super-item ws (shared by the whole cluster) + cluster rank -> this CTA's tile
+__device__ __forceinline__ TileCoord item_coord(const GemmDev& p, int ws, int nx, int my) {
   TileCoord t;
-  t.split = w % p.splits;
-  const int tt = w / p.splits;
-  const int tn = tt % p.n_tiles;
-  const int tm = tt / p.n_tiles;
+  t.split = ws % p.splits;
+  const int tt = ws / p.splits;
+  const int sn = p.n_tiles / p.cx;
+  const int tn = (tt % sn) * p.cx + nx;
+  const int tm = (tt / sn) * p.cm + my;
   t.n0 = tn * BN;
   t.m0 = tm * BM;
   t.cb0 = t.ch0 = t.cw0 = 0;
@@ -99,7 +126,7 @@ __device__ __forceinline__ TileCoord item_coord(const GemmDev& p, int w) {
 // row r of a tile -> global output row m (and validity)
 __device__ __forceinline__ bool row_coord(const GemmDev& p, const TileCoord& t, int r, long long& m, int& b) {
   if (p.conv) {
-    const int tw = r % p.TW, th = (r / p.TW) % p.TH, tb = r / (p.TW * p.TH);
+    const int tw = r & (p.TW - 1), th = (r >> p.lgTW) & (p.TH - 1), tb = r >> (p.lgTW + p.lgTH);
     b = t.cb0 + tb;
     const int h = t.ch0 + th, w = t.cw0 + tw;
     m = ((long long)b * p.H + h) * p.W + w;
@@ -110,11 +137,44 @@ __device__ __forceinline__ bool row_coord(const GemmDev& p, const TileCoord& t, 
   return m < p.M;
 }
 
-__global__ void __launch_bounds__(192, 1)
+// same without the batch index (no 64-bit division on the copy loops)
+__device__ __forceinline__ bool row_m(const GemmDev& p, const TileCoord& t, int r, long long& m) {
+  if (p.conv) {
+    const int tw = r & (p.TW - 1), th = (r >> p.lgTW) & (p.TH - 1), tb = r >> (p.lgTW + p.lgTH);
+    const int b = t.cb0 + tb, h = t.ch0 + th, w = t.cw0 + tw;
+    m = ((long long)b * p.H + h) * p.W + w;
+    return (b < p.B) && (h < p.H);
+  }
+  m = (long long)t.m0 + r;
+  return m < p.M;
+}
+
+// coalesced copy between the padded staging tile and global rows; CPR = 16-byte chunks per row (20 or 10)
+template <int CPR, bool TO_GLOBAL>
+__device__ __forceinline__ void stage_copy(const GemmDev& p, const TileCoord& t, uint8_t* stg, __nv_bfloat16* gbase,
+                                           long long ld, int col0, int et) {
+#pragma unroll 4
+  const int nthr = (int)blockDim.x - 64;
+  for (int i = et; i < BM * CPR; i += nthr) {
+    const int rr = i / CPR, ch = i - rr * CPR;
+    long long mm;
+    if (row_m(p, t, rr, mm)) {
+      uint8_t* s = stg + rr * STG_PITCH + ch * 16;
+      __nv_bfloat16* g = gbase + mm * ld + col0 + ch * 8;
+      if (TO_GLOBAL)
+        *reinterpret_cast<uint4*>(g) = *reinterpret_cast<const uint4*>(s);
+      else
+        cp_async16(s, g);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmL, const GemmDev p) {
   extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment is required by SWIZZLE_128B; dynamic smem base is only guaranteed 16 B aligned.
+  // 1024-byte alignment is required by SWIZZLE_128B; the dynamic smem base offset is identical in every CTA of the
+  // cluster (same kernel, same static smem), which the multicast addressing relies on.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_bytes = B_STAGE_BYTES + (p.lora ? L_STAGE_BYTES : 0);
   const int stage_bytes = A_STAGE_BYTES + b_bytes;
@@ -130,6 +190,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int csize = p.cx * p.cm;
+  const int crank = csize > 1 ? (int)cluster_ctarank() : 0;
+  const int nx = crank % p.cx, my = crank / p.cx;
+  const int cluster_id = blockIdx.x / csize;
+  const int num_clusters = gridDim.x / csize;
+  if (threadIdx.x == 0) stamp(0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -137,47 +203,70 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (p.lora) tma_prefetch_desc(&tmL);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], csize);   // one tcgen05.commit arrival from every CTA of the cluster
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 128);
+      mbar_init(&tmem_empty_bar[s], blockDim.x - 64);
     }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_holder, TMEM_COLS);
   tc_fence_before();
-  __syncthreads();
+  if (csize > 1)
+    cluster_sync_all();   // peers must see initialised barriers before any remote arrive / multicast lands
+  else
+    __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_holder;
 
   // Everything above touched no global memory written by the previous kernel in the stream.
+  if (threadIdx.x == 0) stamp(1);
   pdl_wait();
   pdl_launch_dependents();
+  if (threadIdx.x == 0) stamp(2);
 
   if (warp == 0) {
     // ===================================================================== TMA producer
     if (lane == 0) {
+      // multicast masks: A goes to the CX column neighbours (same my), W to the CM row neighbours (same nx)
+      uint16_t mask_a = 0, mask_b = 0;
+      for (int j = 0; j < p.cx; ++j) mask_a |= (uint16_t)(1u << (my * p.cx + j));
+      for (int j = 0; j < p.cm; ++j) mask_b |= (uint16_t)(1u << (j * p.cx + nx));
+      const int a_rows = BM / p.cx;           // rows of A this CTA fetches
+      const int b_rows = BN / p.cm;           // rows of W this CTA fetches
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
-        const TileCoord t = item_coord(p, w);
+      for (int ws = cluster_id; ws < p.total_super; ws += num_clusters) {
+        const TileCoord t = item_coord(p, ws, nx, my);
         const int kb_begin = t.split * p.kb_per_split;
         const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait(&empty_bar[stage], phase ^ 1);   // every CTA of the cluster has released this slot
           uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + A_STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+          uint8_t* sa_dst = sa + nx * a_rows * 128;
           if (p.conv) {
             const int tap = kb / p.kc_per_tap;
             const int kc = kb - tap * p.kc_per_tap;
             const int kh = tap / 3, kw = tap - kh * 3;
-            tma_load_4d(sa, &tmA, &full_bar[stage], kc * BK, t.cw0 + kw - 1, t.ch0 + kh - 1, t.cb0);
+            int cw = t.cw0 + kw - 1, chh = t.ch0 + kh - 1, cb = t.cb0;
+            if (nx == 1) {
+              if (p.half_dim == 1) cw += p.half_off;
+              else if (p.half_dim == 2) chh += p.half_off;
+              else cb += p.half_off;
+            }
+            if (p.cx > 1) tma_load_4d_mc(sa_dst, &tmA, &full_bar[stage], kc * BK, cw, chh, cb, mask_a);
+            else tma_load_4d(sa_dst, &tmA, &full_bar[stage], kc * BK, cw, chh, cb);
           } else {
-            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, t.m0);
+            if (p.cx > 1) tma_load_2d_mc(sa_dst, &tmA, &full_bar[stage], kb * BK, t.m0 + nx * a_rows, mask_a);
+            else tma_load_2d(sa_dst, &tmA, &full_bar[stage], kb * BK, t.m0);
           }
-          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, t.n0);
+          if (p.cm > 1)
+            tma_load_2d_mc(sb + my * b_rows * 128, &tmB, &full_bar[stage], kb * BK, t.n0 + my * b_rows, mask_b);
+          else
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, t.n0);
           if (p.lora) tma_load_2d(sb + B_STAGE_BYTES, &tmL, &full_bar[stage], kb * BK, 0);
           if (++stage == p.stages) {
             stage = 0;
@@ -190,11 +279,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ===================================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc(BM, p.lora ? BN + LORA_N : BN, 1);
+      const uint16_t mask_all = (uint16_t)((1u << csize) - 1);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++it) {
-        const TileCoord t = item_coord(p, w);
+      for (int ws = cluster_id; ws < p.total_super; ws += num_clusters, ++it) {
+        const TileCoord t = item_coord(p, ws, nx, my);
         const int kb_begin = t.split * p.kb_per_split;
         const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
         const int acc = it & 1;
@@ -204,6 +294,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (it == 0 && kb == kb_begin) stamp(3);
           uint8_t* sa = smem + stage * stage_bytes;
           const uint64_t adesc = make_desc_sw128(smem_u32(sa));
           const uint64_t bdesc = make_desc_sw128(smem_u32(sa + A_STAGE_BYTES));
@@ -212,7 +303,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             // advance 16 bf16 = 32 B along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
             umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          // frees the smem slot (in every CTA of the cluster) once these MMAs retire
+          if (csize > 1) umma_commit_mc(&empty_bar[stage], mask_all);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
@@ -222,16 +315,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else {
-    // ===================================================================== epilogue (warps 2..5)
-    const int q = warp & 3;             // TMEM lane quadrant this warp may access
-    const int r = q * 32 + lane;        // tile row owned by this thread
-    const int et = threadIdx.x - 64;    // 0..127
+    // ===================================================================== epilogue (warps 2..9)
+    const int q = warp & 3;                  // TMEM lane quadrant this warp may access
+    const int chalf0 = (warp - 2) >> 2;      // first column half this warp handles
+    const int chalf_step = ((int)blockDim.x - 64) >> 7;   // 1 (4 epilogue warps: both halves) or 2 (8 warps)
+    const int r = q * 32 + lane;             // tile row owned by this thread
+    const int et = threadIdx.x - 64;         // 0..255
     const bool staged = (p.splits == 1) && (p.out_mode == MOS_OUT_BF16);
-    const int out_cols = p.geglu ? BN / 2 : BN;
-    const int chunks_per_row = out_cols / 8;   // 16-byte chunks
     int it = 0;
-    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++it) {
-      const TileCoord t = item_coord(p, w);
+    for (int ws = cluster_id; ws < p.total_super; ws += num_clusters, ++it) {
+      const TileCoord t = item_coord(p, ws, nx, my);
       const int acc = it & 1;
       long long m;
       int b;
@@ -241,51 +334,51 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         long long m_first;
         row_coord(p, t, 0, m_first, b_lo);
       }
-      // ---- 1. stage bias (+ per-batch bias) and LoRA-up rows of this tile's columns
+      // ---- 1. residual tile -> staging (coalesced 16-byte cp.async, in flight while the bias tables are staged)
+      if (staged && p.residual) {
+        __nv_bfloat16* rbase = const_cast<__nv_bfloat16*>(p.residual);
+        if (p.geglu) stage_copy<BN / 16, false>(p, t, stg, rbase, p.ldr, t.n0 / 2, et);
+        else stage_copy<BN / 8, false>(p, t, stg, rbase, p.ldr, t.n0, et);
+      }
+      // ---- 2. bias (+ per-batch bias) and LoRA-up rows of this tile's columns
       if (p.splits == 1) {
-        for (int i = et; i < 4 * BN; i += 128) {
+        for (int i = et; i < 4 * BN; i += (int)blockDim.x - 64) {
           const int j = i / BN, n = i - j * BN;
           float v = p.bias ? __ldg(p.bias + t.n0 + n) : 0.f;
-          if (p.bias_batch && (b_lo + j) < p.nbatch) v += __ldg(p.bias_batch + (long long)(b_lo + j) * p.bias_batch_ld + t.n0 + n);
+          if (p.bias_batch && (b_lo + j) < p.nbatch)
+            v += __ldg(p.bias_batch + (long long)(b_lo + j) * p.bias_batch_ld + t.n0 + n);
           cb_s[i] = v;
         }
         if (p.lora)
-          for (int i = et; i < BN; i += 128) up_s[i] = __ldg(reinterpret_cast<const float4*>(p.lora_up) + t.n0 + i);
+          for (int i = et; i < BN; i += (int)blockDim.x - 64)
+            up_s[i] = __ldg(reinterpret_cast<const float4*>(p.lora_up) + t.n0 + i);
       }
-      // ---- 2. residual tile -> staging (coalesced 16-byte cp.async), hidden behind the mainloop
-      if (staged && p.residual) {
-        for (int i = et; i < BM * chunks_per_row; i += 128) {
-          const int rr = i / chunks_per_row, ch = i - rr * chunks_per_row;
-          long long mm;
-          int bb_;
-          if (row_coord(p, t, rr, mm, bb_))
-            cp_async16(stg + rr * STG_PITCH + ch * 16, p.residual + mm * p.ldr + (p.geglu ? t.n0 / 2 : t.n0) + ch * 8);
-        }
-        cp_async_wait_all();
-      }
+      cp_async_wait_all();
       epi_bar();
-      // ---- 3. accumulators ready?
-      mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1);
+      if (et == 0 && it == 0) stamp(4);
+      // ---- 3. accumulators ready?  (one lane per warp polls: 256 spinning threads would steal issue slots from the
+      //         single-thread TMA / MMA roles)
+      if (lane == 0) mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1);
+      __syncwarp();
       tc_fence_after();
+      if (et == 0 && it == 0) stamp(5);
       const uint32_t trow = tmem_base + acc * ACC_STRIDE + (uint32_t(q * 32) << 16);
       const int bsel = min(max(b - b_lo, 0), 3);
       const float* cb = cb_s + bsel * BN;
       uint8_t* srow = stg + r * STG_PITCH;
 
+      for (int chalf = chalf0; chalf < 2; chalf += chalf_step) {
       if (p.splits > 1) {
         float* dst = p.partial + ((long long)t.split * p.M + m) * p.N + t.n0;
 #pragma unroll 1
-        for (int c = 0; c < BN / 16; c += 2) {
-          uint32_t v0[16], v1[16];
-          tmem_ld16(trow + c * 16, v0);
-          tmem_ld16(trow + c * 16 + 16, v1);
+        for (int c = chalf * 5; c < chalf * 5 + 5; ++c) {
+          uint32_t v[16];
+          tmem_ld16(trow + c * 16, v);
           tmem_ld_wait();
           if (valid) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              *reinterpret_cast<uint4*>(dst + c * 16 + j) = make_uint4(v0[j], v0[j + 1], v0[j + 2], v0[j + 3]);
-              *reinterpret_cast<uint4*>(dst + c * 16 + 16 + j) = make_uint4(v1[j], v1[j + 1], v1[j + 2], v1[j + 3]);
-            }
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<uint4*>(dst + c * 16 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           }
         }
       } else {
@@ -298,17 +391,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int j = 0; j < 16; ++j) t4[j] = __uint_as_float(tv[j]);
         }
         if (p.geglu) {
-          // tile columns [0,80) = a, [80,160) = gate for the same 80 outputs
+          // tile columns [0,80) = a, [80,160) = gate for the same 80 outputs; this warp: outputs [40*chalf, +40)
 #pragma unroll 1
-          for (int c = 0; c < (BN / 2) / 16; ++c) {
-            uint32_t va[16], vg[16];
-            tmem_ld16(trow + c * 16, va);
-            tmem_ld16(trow + BN / 2 + c * 16, vg);
+          for (int c = chalf * 5; c < chalf * 5 + 5; ++c) {
+            uint32_t va[8], vg[8];
+            tmem_ld8(trow + c * 8, va);
+            tmem_ld8(trow + BN / 2 + c * 8, vg);
             tmem_ld_wait();
-            float o[16];
+            float o[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int na = c * 16 + j, ng = na + BN / 2;
+            for (int j = 0; j < 8; ++j) {
+              const int na = c * 8 + j, ng = na + BN / 2;
               float a = __uint_as_float(va[j]) + cb[na];
               float g = __uint_as_float(vg[j]) + cb[ng];
               if (p.lora) {
@@ -318,79 +411,80 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               }
               o[j] = a * gelu_erf(g);
             }
-            store_bf16x8(reinterpret_cast<__nv_bfloat16*>(srow + c * 32), o);
-            store_bf16x8(reinterpret_cast<__nv_bfloat16*>(srow + c * 32 + 16), o + 8);
+            store_bf16x8(reinterpret_cast<__nv_bfloat16*>(srow + c * 16), o);
           }
         } else {
 #pragma unroll 1
-          for (int c = 0; c < BN / 16; c += 2) {
-            uint32_t vv[2][16];
-            tmem_ld16(trow + c * 16, vv[0]);
-            tmem_ld16(trow + c * 16 + 16, vv[1]);
+          for (int c = chalf * 5; c < chalf * 5 + 5; ++c) {
+            uint32_t vv[16];
+            tmem_ld16(trow + c * 16, vv);
             tmem_ld_wait();
+            const int nl = c * 16;               // column inside the tile
+            const int nc = t.n0 + nl;            // global column
+            float o[16];
+            float tt[4] = {0.f, 0.f, 0.f, 0.f};
+            if (p.lora) {
+              const int sidx = (int)(nc / p.lora_seg);
 #pragma unroll
-            for (int hlf = 0; hlf < 2; ++hlf) {
-              const int nl = (c + hlf) * 16;       // column inside the tile
-              const int nc = t.n0 + nl;            // global column
-              float o[16];
-              float tt[4] = {0.f, 0.f, 0.f, 0.f};
-              if (p.lora) {
-                const int sidx = (int)(nc / p.lora_seg);
+              for (int i = 0; i < 4; ++i)
+                tt[i] = sidx == 0 ? t4[i] : sidx == 1 ? t4[4 + i] : sidx == 2 ? t4[8 + i] : t4[12 + i];
+            }
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  tt[i] = sidx == 0 ? t4[i] : sidx == 1 ? t4[4 + i] : sidx == 2 ? t4[8 + i] : t4[12 + i];
-              }
+            for (int j4 = 0; j4 < 16; j4 += 4) {
+              const float4 cbv = *reinterpret_cast<const float4*>(cb + nl + j4);
+              o[j4 + 0] = __uint_as_float(vv[j4 + 0]) + cbv.x;
+              o[j4 + 1] = __uint_as_float(vv[j4 + 1]) + cbv.y;
+              o[j4 + 2] = __uint_as_float(vv[j4 + 2]) + cbv.z;
+              o[j4 + 3] = __uint_as_float(vv[j4 + 3]) + cbv.w;
+            }
+            if (p.lora) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                float a = __uint_as_float(vv[hlf][j]) + cb[nl + j];
-                if (p.lora) {
-                  const float4 u = up_s[nl + j];
-                  a += tt[0] * u.x + tt[1] * u.y + tt[2] * u.z + tt[3] * u.w;
-                }
-                o[j] = a;
+                const float4 u = up_s[nl + j];
+                o[j] += tt[0] * u.x + tt[1] * u.y + tt[2] * u.z + tt[3] * u.w;
               }
-              if (p.out_mode == MOS_OUT_BF16) {
-                if (p.residual) {
-                  const uint4 r0 = *reinterpret_cast<const uint4*>(srow + nl * 2);
-                  const uint4 r1 = *reinterpret_cast<const uint4*>(srow + nl * 2 + 16);
-                  const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+            }
+            if (p.out_mode == MOS_OUT_BF16) {
+              if (p.residual) {
+                const uint4 r0 = *reinterpret_cast<const uint4*>(srow + nl * 2);
+                const uint4 r1 = *reinterpret_cast<const uint4*>(srow + nl * 2 + 16);
+                const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    const float2 f = unpack_bf16x2(rr[j]);
-                    o[2 * j] += f.x;
-                    o[2 * j + 1] += f.y;
-                  }
+                for (int j = 0; j < 8; ++j) {
+                  const float2 f = unpack_bf16x2(rr[j]);
+                  o[2 * j] += f.x;
+                  o[2 * j + 1] += f.y;
                 }
-                store_bf16x8(reinterpret_cast<__nv_bfloat16*>(srow + nl * 2), o);
-                store_bf16x8(reinterpret_cast<__nv_bfloat16*>(srow + nl * 2 + 16), o + 8);
-              } else if (p.out_mode == MOS_OUT_F32) {
-                if (valid) {
-                  float* orow = reinterpret_cast<float*>(p.out) + m * p.ldc + nc;
+              }
+              store_bf16x8(reinterpret_cast<__nv_bfloat16*>(srow + nl * 2), o);
+              store_bf16x8(reinterpret_cast<__nv_bfloat16*>(srow + nl * 2 + 16), o + 8);
+            } else if (p.out_mode == MOS_OUT_F32) {
+              if (valid) {
+                float* orow = reinterpret_cast<float*>(p.out) + m * p.ldc + nc;
 #pragma unroll
-                  for (int j = 0; j < 16; j += 4)
-                    *reinterpret_cast<float4*>(orow + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-                }
-              } else if (valid) {  // MOS_OUT_HEADS
-                const int seg_len = p.heads * p.head_dim;
-                const long long bb = m / p.tokens_per_batch;
-                const long long tok = m - bb * p.tokens_per_batch;
+                for (int j = 0; j < 16; j += 4)
+                  *reinterpret_cast<float4*>(orow + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+              }
+            } else if (valid) {  // MOS_OUT_HEADS
+              const int seg_len = p.heads * p.head_dim;
+              const long long bb = m / p.tokens_per_batch;
+              const long long tok = m - bb * p.tokens_per_batch;
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                  const int n = nc + half * 8;
-                  const int seg = n / seg_len;
-                  const int cc = n - seg * seg_len;
-                  const int head = cc / p.head_dim;
-                  const int j0 = cc - head * p.head_dim;
-                  __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(p.seg_ptr[seg]);
-                  const long long bh = bb * p.heads + head;
-                  if (p.seg_kind[seg] == MOS_SEG_ROWS) {
-                    store_bf16x8(base + (bh * p.seg_rows_pad[seg] + tok) * p.dpad + j0, o + half * 8);
-                  } else {
-                    __nv_bfloat16* d = base + (bh * p.dv_pad + j0) * p.seg_rows_pad[seg] + tok;
+              for (int half = 0; half < 2; ++half) {
+                const int n = nc + half * 8;
+                const int seg = n / seg_len;
+                const int cc = n - seg * seg_len;
+                const int head = cc / p.head_dim;
+                const int j0 = cc - head * p.head_dim;
+                __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(p.seg_ptr[seg]);
+                const long long bh = bb * p.heads + head;
+                if (p.seg_kind[seg] == MOS_SEG_ROWS) {
+                  store_bf16x8(base + (bh * p.seg_rows_pad[seg] + tok) * p.dpad + j0, o + half * 8);
+                } else {
+                  __nv_bfloat16* d = base + (bh * p.dv_pad + j0) * p.seg_rows_pad[seg] + tok;
 #pragma unroll
-                    for (int e = 0; e < 8; ++e)
-                      d[(long long)e * p.seg_rows_pad[seg]] = __float2bfloat16(o[half * 8 + e]);
-                  }
+                  for (int e = 0; e < 8; ++e)
+                    d[(long long)e * p.seg_rows_pad[seg]] = __float2bfloat16(o[half * 8 + e]);
                 }
               }
             }
@@ -398,30 +492,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       }
+      }  // column halves
       // ---- 4. accumulator drained: hand it back to the MMA warp (next-but-one tile)
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);
+      if (et == 0 && it == 0) stamp(6);
       // ---- 5. coalesced write-out of the staged bf16 tile
       if (staged) {
         epi_bar();
         __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out);
-        const int ocol0 = p.geglu ? (t.n0 / 2) : t.n0;
-        for (int i = et; i < BM * chunks_per_row; i += 128) {
-          const int rr = i / chunks_per_row, ch = i - rr * chunks_per_row;
-          long long mm;
-          int bb_;
-          if (row_coord(p, t, rr, mm, bb_)) {
-            const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * STG_PITCH + ch * 16);
-            *reinterpret_cast<uint4*>(obase + mm * p.ldc + ocol0 + ch * 8) = v;
-          }
-        }
+        if (p.geglu) stage_copy<BN / 16, true>(p, t, stg, obase, p.ldc, t.n0 / 2, et);
+        else stage_copy<BN / 8, true>(p, t, stg, obase, p.ldc, t.n0, et);
       }
       epi_bar();   // staging / bias tables are reused by the next item
+      if (et == 0 && it == 0) stamp(7);
     }
     tc_fence_before();
   }
 
-  __syncthreads();
+  // no CTA may exit while a peer can still multicast into its smem or arrive on its barriers
+  if (csize > 1)
+    cluster_sync_all();
+  else
+    __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -432,8 +525,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 __global__ void splitk_finalize_kernel(const float* __restrict__ partial, int splits, long long M, long long N,
                                        const float* __restrict__ bias, const float* __restrict__ bias_batch,
                                        long long rows_per_batch, long long bias_batch_ld,
-                                       const __nv_bfloat16* __restrict__ residual,
-                                       long long ldr, __nv_bfloat16* __restrict__ out, long long ldc) {
+                                       const __nv_bfloat16* __restrict__ residual, long long ldr,
+                                       __nv_bfloat16* __restrict__ out, long long ldc) {
   pdl_wait();
   pdl_launch_dependents();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 4 columns
@@ -469,6 +562,11 @@ __global__ void splitk_finalize_kernel(const float* __restrict__ partial, int sp
 }
 
 static bool is_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+static int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
 
 }  // namespace mos
 
@@ -511,6 +609,7 @@ extern "C" int mos_gemm_bf16(const mos_gemm_args* a, void* stream_) {
   p.M = (int)a->M;
   p.N = (int)a->N;
   p.conv = a->conv;
+  p.n_tiles = (int)(a->N / BN);
   int m_tiles;
   if (a->conv) {
     MOS_CHECK_ARG(a->B > 0 && a->H > 0 && a->Wd > 0 && a->C == a->K, "mos_gemm_bf16: bad conv geometry");
@@ -532,6 +631,8 @@ extern "C" int mos_gemm_bf16(const mos_gemm_args* a, void* stream_) {
     p.TW = TW;
     p.TH = best_th;
     p.TB = 128 / (TW * best_th);
+    p.lgTW = ilog2(p.TW);
+    p.lgTH = ilog2(p.TH);
     p.H = a->H;
     p.W = a->Wd;
     p.B = a->B;
@@ -541,31 +642,58 @@ extern "C" int mos_gemm_bf16(const mos_gemm_args* a, void* stream_) {
     m_tiles = p.tiles_w * p.tiles_h * tiles_b;
     p.kc_per_tap = (int)(a->K / BK);
     p.kb_total = 9 * p.kc_per_tap;
+  } else {
+    MOS_CHECK_ARG(a->lda >= a->K && a->lda % 8 == 0, "mos_gemm_bf16: lda=%lld invalid", (long long)a->lda);
+    m_tiles = (int)ceil_div(a->M, BM);
+    p.kb_total = (int)(a->K / BK);
+  }
+  p.m_tiles = m_tiles;
+  // ---- cluster shape: CX column neighbours share A, CM row neighbours share W
+  // Measured on B200 (profiles/README.md): with 4 smem stages the multicast hand-shake (remote slot release + multicast
+  // latency) costs more than the L2 traffic it saves (0.44 vs 0.36 us per k-block on the 320->320 conv), so clusters
+  // are opt-in (MOS_GEMM_CLUSTER=1) until the stage budget grows (2-CTA UMMA, next round).
+  static int use_cluster = -1;
+  if (use_cluster < 0) {
+    const char* e = getenv("MOS_GEMM_CLUSTER");
+    use_cluster = (e && e[0] == '1') ? 1 : 0;
+  }
+  p.cx = p.cm = 1;
+  if (use_cluster) {
+    p.cx = (p.n_tiles % 2 == 0) ? 2 : 1;
+    p.cm = (m_tiles % 4 == 0) ? 4 : (m_tiles % 2 == 0) ? 2 : 1;
+  }
+  const int csize = p.cx * p.cm;
+
+  // ---- tensor maps (the A box is 1/CX of the tile rows, the W box 1/CM of the tile columns)
+  if (a->conv) {
+    uint32_t bw = (uint32_t)p.TW, bh = (uint32_t)p.TH, bb = (uint32_t)p.TB;
+    if (p.cx == 2) {
+      if (bb >= 2) { bb /= 2; p.half_dim = 3; p.half_off = (int)bb; }
+      else if (bh >= 2) { bh /= 2; p.half_dim = 2; p.half_off = (int)bh; }
+      else { bw /= 2; p.half_dim = 1; p.half_off = (int)bw; }
+    }
     uint64_t dims[4] = {(uint64_t)a->C, (uint64_t)a->Wd, (uint64_t)a->H, (uint64_t)a->B};
     const uint64_t pitch = (uint64_t)(a->lda > 0 ? a->lda : a->C);
     MOS_CHECK_ARG(pitch >= (uint64_t)a->C && pitch % 8 == 0, "mos_gemm_bf16: conv pixel pitch %llu invalid",
                   (unsigned long long)pitch);
     uint64_t str[3] = {pitch * 2, (uint64_t)a->Wd * pitch * 2, (uint64_t)a->H * a->Wd * pitch * 2};
-    uint32_t box[4] = {BK, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TB};
+    uint32_t box[4] = {BK, bw, bh, bb};
     int rc = encode_tmap(&tmA, a->A, 2, 4, dims, str, box, 3);
     if (rc) return rc;
     uint64_t wd[2] = {(uint64_t)a->K * 9, (uint64_t)a->N};
     uint64_t ws[1] = {(uint64_t)a->K * 9 * 2};
-    uint32_t wb[2] = {BK, BN};
+    uint32_t wb[2] = {BK, (uint32_t)(BN / p.cm)};
     rc = encode_tmap(&tmB, a->W, 2, 2, wd, ws, wb, 3);
     if (rc) return rc;
   } else {
-    MOS_CHECK_ARG(a->lda >= a->K && a->lda % 8 == 0, "mos_gemm_bf16: lda=%lld invalid", (long long)a->lda);
-    m_tiles = (int)ceil_div(a->M, BM);
-    p.kb_total = (int)(a->K / BK);
     uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->M};
     uint64_t str[1] = {(uint64_t)a->lda * 2};
-    uint32_t box[2] = {BK, BM};
+    uint32_t box[2] = {BK, (uint32_t)(BM / p.cx)};
     int rc = encode_tmap(&tmA, a->A, 2, 2, dims, str, box, 3);
     if (rc) return rc;
     uint64_t wd[2] = {(uint64_t)a->K, (uint64_t)a->N};
     uint64_t ws[1] = {(uint64_t)a->K * 2};
-    uint32_t wb[2] = {BK, BN};
+    uint32_t wb[2] = {BK, (uint32_t)(BN / p.cm)};
     rc = encode_tmap(&tmB, a->W, 2, 2, wd, ws, wb, 3);
     if (rc) return rc;
     if (lora) {
@@ -604,11 +732,9 @@ extern "C" int mos_gemm_bf16(const mos_gemm_args* a, void* stream_) {
   p.dpad = a->dpad;
   p.dv_pad = a->dv_pad;
   p.tokens_per_batch = a->tokens_per_batch > 0 ? a->tokens_per_batch : 1;
-
   if (a->bias_batch && !a->conv)
     MOS_CHECK_ARG(p.rows_per_batch >= 32, "mos_gemm_bf16: bias_batch needs rows_per_batch >= 32 in plain mode");
-  p.n_tiles = (int)(a->N / BN);
-  p.total_items = p.n_tiles * m_tiles * splits;
+  p.total_super = (p.n_tiles / p.cx) * (m_tiles / p.cm) * splits;
   p.nbatch = a->conv ? a->B : (int)ceil_div(a->M, p.rows_per_batch);
 
   const int stage_bytes = A_STAGE_BYTES + B_STAGE_BYTES + (lora ? L_STAGE_BYTES : 0);
@@ -626,21 +752,54 @@ extern "C" int mos_gemm_bf16(const mos_gemm_args* a, void* stream_) {
     MOS_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     MOS_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM));
   }
-  // persistent: one CTA per SM, each loops over its share of (tile, split) work items
-  const int grid = p.total_items < num_sms ? p.total_items : num_sms;
+  // persistent: one CTA per SM; each cluster loops over its share of (super-tile, split) work items
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(192);
-  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  static int epi_warps = 0;
+  if (epi_warps == 0) {
+    const char* e = getenv("MOS_GEMM_EPI_WARPS");
+    epi_warps = (e && e[0] == '4') ? 4 : 8;
+  }
+  cfg.blockDim = dim3(64 + 32 * epi_warps);
+  cfg.dynamicSmemBytes = (size_t)MAX_DYN_SMEM;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = (unsigned)csize;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  static int max_clusters[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // co-resident clusters per cluster size (GPC packing)
+  if (max_clusters[csize] == 0) {
+    int n = 0;
+    cfg.gridDim = dim3((unsigned)(csize * (num_sms / csize)));
+    cfg.numAttrs = 2;
+    if (csize > 1) {
+      cudaLaunchAttribute only_cluster[1] = {attr[1]};
+      cfg.attrs = only_cluster;
+      cfg.numAttrs = 1;
+      MOS_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_kernel, &cfg));
+      cfg.attrs = attr;
+      MOS_CHECK_ARG(n > 0, "mos_gemm_bf16: cluster size %d cannot be scheduled", csize);
+    } else {
+      n = num_sms;
+    }
+    max_clusters[csize] = n;
+  }
+  int clusters = max_clusters[csize];
+  if (clusters > p.total_super) clusters = p.total_super;
+  cfg.gridDim = dim3((unsigned)(clusters * csize));
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cfg.numAttrs = csize > 1 ? 2 : 1;   // no cluster attribute at all for unclustered launches
   MOS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel, tmA, tmB, tmL, p));
-  MOS_CHECK_LAUNCH();
+  return MOS_OK;
+}
+
+extern "C" int mos_debug_set_timeline(void* buf) {
+  unsigned long long* p = reinterpret_cast<unsigned long long*>(buf);
+  MOS_CHECK_CUDA(cudaMemcpyToSymbol(mos::g_timeline, &p, sizeof(p)));
   return MOS_OK;
 }
 
