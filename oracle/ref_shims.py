@@ -94,7 +94,12 @@ def load_reference_module(rel_path, name=None):
         return _loaded[rel_path]
     install_stubs()
     parked = {k: sys.modules.pop(k) for k in list(sys.modules) if k == 'mixofshow' or k.startswith('mixofshow.')}
-    sys.path.insert(0, REFERENCE_ROOT)
+    # the reference's `mixofshow` is a namespace package (no __init__.py): a regular package of the same name anywhere
+    # on sys.path would win, so hide those entries while the reference file executes
+    saved_path = list(sys.path)
+    sys.path[:] = [REFERENCE_ROOT] + [p for p in sys.path
+                                      if not os.path.isfile(os.path.join(p or '.', 'mixofshow', '__init__.py'))]
+    importlib.invalidate_caches()
     try:
         name = name or ('_ref_' + rel_path.replace('/', '_').replace('.py', ''))
         spec = importlib.util.spec_from_file_location(name, os.path.join(REFERENCE_ROOT, rel_path))
@@ -102,7 +107,8 @@ def load_reference_module(rel_path, name=None):
         sys.modules[name] = mod
         spec.loader.exec_module(mod)
     finally:
-        sys.path.remove(REFERENCE_ROOT)
+        sys.path[:] = saved_path
+        importlib.invalidate_caches()
         for k in [k for k in sys.modules if k == 'mixofshow' or k.startswith('mixofshow.')]:
             sys.modules['_ref_pkg_' + k] = sys.modules.pop(k)
         sys.modules.update(parked)

@@ -23,6 +23,25 @@ def gen(seed):
     return torch.Generator().manual_seed(seed)
 
 
+def q16(t):
+    """Round a (large) input to bf16-representable values so it can be stored as bf16 losslessly."""
+    return t.to(torch.bfloat16).float()
+
+
+def pack16(obj):
+    """Store bf16-representable fp32 tensors as bf16 (tests call .float() on load)."""
+    if torch.is_tensor(obj):
+        return obj.to(torch.bfloat16) if (obj.dtype == torch.float32 and torch.equal(obj.to(torch.bfloat16).float(), obj)
+                                          and obj.numel() > 4096) else obj
+    if isinstance(obj, dict):
+        return {k: pack16(v) for k, v in obj.items()}
+    if isinstance(obj, list):
+        return [pack16(v) for v in obj]
+    if isinstance(obj, tuple):
+        return tuple(pack16(v) for v in obj)
+    return obj
+
+
 def main():
     assert ref_shims.reference_available(), 'needs /root/reference'
     ed = ref_shims.load_reference_module('mixofshow/models/edlora.py')
@@ -52,9 +71,9 @@ def main():
 
     # ---- P2/P3 processors on the Attention surface (edlora.py:22-173)
     torch.manual_seed(5)
-    attn = ou.Attention(320, 96, heads=8, dim_head=40)      # small cross dim keeps the fixture small
+    attn = ou.Attention(320, 128, heads=8, dim_head=40)     # small cross dim keeps the fixture small
     hs = torch.randn(2, 64, 320, generator=gen(6))
-    ehs = torch.randn(2, 16, 77, 96, generator=gen(7))
+    ehs = q16(torch.randn(2, 16, 77, 128, generator=gen(7))[:, :8].contiguous())   # idx 5 of 8 stored layers
     with torch.no_grad():
         out_plain = ed.EDLoRA_AttnProcessor(5)(attn, hs, encoder_hidden_states=ehs)
         seen = {}
@@ -94,12 +113,12 @@ def main():
     boxes_overlap = [boxes[0], [14 / Hpx, 440 / Wpx, 1024 / Hpx, 920 / Wpx], boxes[2]]
     proc = reg.RegionT2I_AttnProcessor(3)
     torch.manual_seed(8)
-    attn_r = ou.Attention(320, 96, heads=8, dim_head=40)
+    attn_r = ou.Attention(320, 128, heads=8, dim_head=40)
     fh, fw = 12, 24
     hs_r = torch.randn(2, fh * fw, 320, generator=gen(9))
-    ehs_r = torch.randn(2, 16, 77, 96, generator=gen(10))[:, :4].contiguous()   # idx 3 of 4 stored layers
-    region_embs = [torch.randn(2, 4, 77, 96, generator=gen(11)), torch.randn(2, 77, 96, generator=gen(12)),
-                   torch.randn(2, 77, 96, generator=gen(13))]                       # 4-D and 3-D forms (:120-126)
+    ehs_r = q16(torch.randn(2, 16, 77, 128, generator=gen(10))[:, :4].contiguous())   # idx 3 of 4 stored layers
+    region_embs = [q16(torch.randn(2, 4, 77, 128, generator=gen(11))), q16(torch.randn(2, 77, 128, generator=gen(12))),
+                   q16(torch.randn(2, 77, 128, generator=gen(13)))]                       # 4-D and 3-D forms (:120-126)
     reg_out = {}
     for tag, bx in (('abut', boxes), ('overlap', boxes_overlap)):
         rl = [(region_embs[i], bx[i]) for i in range(3)]
@@ -170,12 +189,31 @@ def main():
             layer.lora_up.weight.data = lora[name + '.lora_up.weight'].clone()
             keep.append(layer)
     lat = torch.randn(2, 4, 16, 16, generator=gen(40))
-    ehs_u = torch.randn(2, 4, 77, 768, generator=gen(41))      # the tiny topology has 4 cross-attention layers
+    ehs_u = q16(torch.randn(2, 4, 77, 768, generator=gen(41)))      # the tiny topology has 4 cross-attention layers
     with torch.no_grad():
         y = u(lat, torch.tensor([981, 981]), ehs_u).sample
     G['tiny_unet'] = dict(latents=lat, ehs=ehs_u, t=981, lora_seed=10, unet_seed=0, out=y, n_lora=len(keep))
 
-    torch.save(G, OUT)
+    # ---- whole tiny UNet through the reference's regional processors + T2I-adapter residuals (regional :88-145,
+    #      UNet call at :556-566); 128x256 px -> 16x32 latent
+    ur = ou.build_unet(0, ou.TINY)
+    reg.revise_regionally_t2iadapter_attention_forward(ur)
+    lat_r = torch.randn(2, 4, 16, 32, generator=gen(50))
+    ehs_ur = q16(torch.randn(2, 4, 77, 768, generator=gen(51)))
+    r_embs = [q16(torch.randn(2, 4, 77, 768, generator=gen(52 + i))) for i in range(3)]
+    adapters = [torch.randn(2, 320, 16, 32, generator=gen(60)) * 0.1, torch.randn(2, 640, 8, 16, generator=gen(61)) * 0.1]
+    out_r = {}
+    for tag, bx in (('abut', boxes), ('overlap', boxes_overlap)):
+        rl = [(r_embs[i], bx[i]) for i in range(3)]
+        with torch.no_grad():
+            out_r[tag] = ur(lat_r, torch.tensor([500, 500]), ehs_ur,
+                            cross_attention_kwargs={'region_list': rl, 'height': 128, 'width': 256},
+                            down_block_additional_residuals=[a.clone() for a in adapters]).sample
+    G['tiny_unet_region'] = dict(latents=lat_r, ehs=ehs_ur, region_embs=r_embs, adapters=adapters, t=500,
+                                 height=128, width=256, boxes=boxes, boxes_overlap=boxes_overlap, out=out_r,
+                                 unet_seed=0)
+
+    torch.save(pack16(G), OUT)
     print('wrote', OUT, os.path.getsize(OUT) / 1e6, 'MB')
 
 

@@ -93,3 +93,19 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, 'LIB_PATH', str(tmp_path / 'nope.so'))
     with pytest.raises(_lib.MosError):
         _lib.lib()
+
+
+def test_product_bind_concept_prompt_and_boxes_match_reference_golden():
+    """bit-exact string / integer outputs of the drop-in functions vs the reference-generated golden"""
+    import os
+    from mixofshow.pipelines.pipeline_edlora import bind_concept_prompt
+    from mixofshow.pipelines.pipeline_regionally_t2iadapter import region_box_indices
+    G = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_golden.pt'),
+                   weights_only=False)
+    g = G['bind_concept_prompt']
+    assert bind_concept_prompt(g['prompts'], g['cfg']) == g['out']
+    assert bind_concept_prompt(g['prompts'][0], g['cfg']) == g['out_single']
+    r = G['region']
+    for (H, W, ds, tag), idx in r['box_index_kat'].items():
+        boxes = r['boxes'] if tag == 'abut' else r['boxes_overlap']
+        assert [region_box_indices(b, H // ds, W // ds) for b in boxes] == [tuple(i) for i in idx]

@@ -13,9 +13,21 @@ from oracle import unet as ou
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_golden.pt')
 
 
+def _f32(obj):
+    if torch.is_tensor(obj):
+        return obj.float() if obj.dtype == torch.bfloat16 else obj
+    if isinstance(obj, dict):
+        return {k: _f32(v) for k, v in obj.items()}
+    if isinstance(obj, list):
+        return [_f32(v) for v in obj]
+    if isinstance(obj, tuple):
+        return tuple(_f32(v) for v in obj)
+    return obj
+
+
 @pytest.fixture(scope='module')
 def G():
-    return torch.load(GOLD, weights_only=False)
+    return _f32(torch.load(GOLD, weights_only=False))   # large bf16-exact inputs are stored as bf16
 
 
 def close(a, b, tol=1e-5):
@@ -45,7 +57,7 @@ def test_cross_attention_processor(G):
     assert close(probs, g['probs'], 1e-5)
     assert g['is_cross'] is True and g['place'] == 'down'
     # module-level restatement (oracle/inject.py) too
-    attn = _attn_from_state(st, 96)
+    attn = _attn_from_state(st, 128)
     with torch.no_grad():
         out2 = inject.EDLoRAProcessor(g['idx'])(attn, g['hs'], encoder_hidden_states=g['ehs'])
     assert close(out2, g['out'], 1e-5)
@@ -83,7 +95,7 @@ def test_region_box_indices_bit_exact(G):
 @pytest.mark.parametrize('tag', ['abut', 'overlap'])
 def test_region_processor(G, tag):
     g = G['region']
-    attn = _attn_from_state(g['state'], 96)
+    attn = _attn_from_state(g['state'], 128)
     boxes = g['boxes'] if tag == 'abut' else g['boxes_overlap']
     rl = [(g['region_embs'][i], boxes[i]) for i in range(3)]
     with torch.no_grad():
@@ -120,6 +132,20 @@ def test_tiny_unet_with_reference_processors_and_lora(G):
     with torch.no_grad():
         y = u(g['latents'], torch.tensor([g['t'], g['t']]), g['ehs']).sample
     assert close(y, g['out'], 1e-5)
+
+
+@pytest.mark.parametrize('tag', ['abut', 'overlap'])
+def test_tiny_unet_regional_with_adapters(G, tag):
+    g = G['tiny_unet_region']
+    u = ou.build_unet(g['unet_seed'], ou.TINY)
+    inject.install_region_processors(u)
+    boxes = g['boxes'] if tag == 'abut' else g['boxes_overlap']
+    rl = [(g['region_embs'][i], boxes[i]) for i in range(3)]
+    with torch.no_grad():
+        y = u(g['latents'], torch.tensor([g['t'], g['t']]), g['ehs'],
+              cross_attention_kwargs={'region_list': rl, 'height': g['height'], 'width': g['width']},
+              down_block_additional_residuals=[a.clone() for a in g['adapters']]).sample
+    assert close(y, g['out'][tag], 1e-5)
 
 
 def test_schedulers_self_consistency():
