@@ -179,7 +179,7 @@ class LoRALinearLayer(nn.Module):
         torch.nn.init.kaiming_uniform_(self.lora_down.weight, a=math.sqrt(5))
         torch.nn.init.zeros_(self.lora_up.weight)
         object.__setattr__(self, '_orig', original_module)   # not a submodule: parameters stay where they are
-        original_module._mos_lora = self                      # descriptor read by the packers
+        object.__setattr__(original_module, '_mos_lora', self)   # descriptor read by the packers (not a child module)
         self.original_forward = original_module.forward
         original_module.forward = self.forward
 

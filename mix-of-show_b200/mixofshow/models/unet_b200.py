@@ -180,6 +180,11 @@ class UNet2DConditionModel(nn.Module):
         self.merge_lora = False
         self.use_graph = True
 
+    def invalidate(self):
+        """Force a re-pack on the next call (needed only after edits that bypass autograd's version counters, e.g.
+        writes through `.data`; optimiser steps and `load_state_dict` are detected automatically)."""
+        self._engines = {}
+
     # ------------------------------------------------------------------------------------------ descriptors
     def _fingerprint(self):
         fp = 0

@@ -573,4 +573,7 @@ def ehs_to_layer_major(ehs, n_layers=16):
     """[B,16,77,768] (pipeline layout, pipeline_edlora.py:145) or [B,77,768] -> bf16 [16,B,77,768]."""
     if ehs.ndim == 3:
         ehs = ehs[:, None].expand(-1, n_layers, -1, -1)
+    elif ehs.shape[1] > n_layers:      # a smaller topology uses the first n_layers embeddings (idx < n_layers)
+        ehs = ehs[:, :n_layers]
+    assert ehs.shape[1] == n_layers, f'need {n_layers} layer-wise embeddings, got {ehs.shape[1]}'
     return ehs.permute(1, 0, 2, 3).to(BF16).contiguous()

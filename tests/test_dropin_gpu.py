@@ -150,7 +150,8 @@ def test_b200_unet_driven_like_the_reference_trainer(cuda, G):
     print(f'B200 UNet (reference recipe) vs reference golden: rel-L2 {e:.3e}')
     assert e < 2e-2
     # a LoRA update (an optimiser step in training) must be picked up by the next call
-    keep[0].lora_up.weight.data.mul_(3.0)
+    with torch.no_grad():
+        keep[0].lora_up.weight.mul_(3.0)          # what optimizer.step() does (bumps the tensor version)
     out2 = unet(g['latents'].cuda(), torch.tensor([g['t'], g['t']]).cuda(), g['ehs'].cuda()).sample
     assert not torch.equal(out2, out)
 
