@@ -44,6 +44,12 @@ struct AttnCfg {
   static_assert(O_COL0 + 2 * O_STRIDE <= TMEM_COLS, "TMEM budget");
 };
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct AttnDev {
   int nq, nk, heads;
   float scale_log2;  // scale * log2(e)
@@ -194,19 +200,25 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       __syncwarp();
       tc_fence_after();
       const uint32_t ts = trow + C::S_COL0 + sb * C::BKV;
-      // pass 1: row max
+      // pass 1: row max   (full tiles take the mask-free path: this kernel is issue-bound, ncu: 69 % issue active)
+      const bool full = kv_valid == C::BKV;
       float mx = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < C::BKV / 32; ++c) {
         uint32_t v[32];
         tmem_ld32(ts + c * 32, v);
         tmem_ld_wait();
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
       }
       const float m_new = fmaxf(m_run, mx * p.scale_log2);
-      const float alpha = exp2f(m_run - m_new);
+      const float alpha = ex2_approx(m_run - m_new);
       // pass 2: probabilities -> bf16 -> swizzled smem
       if (lane == 0) mbar_wait(&p_empty[pbuf], ((j / C::PB) & 1) ^ 1);
       __syncwarp();
@@ -218,11 +230,19 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         tmem_ld32(ts + c * 32, v);
         tmem_ld_wait();
         float pv[32];
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float e = exp2f(__uint_as_float(v[i]) * p.scale_log2 - m_new);
-          pv[i] = (c * 32 + i < kv_valid) ? e : 0.f;
-          rs += pv[i];
+          for (int i = 0; i < 32; ++i) {
+            pv[i] = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
+            rs += pv[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float e = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
+            pv[i] = (c * 32 + i < kv_valid) ? e : 0.f;
+            rs += pv[i];
+          }
         }
         uint8_t* rowp = sPb + (c >> 1) * 16384 + r * 128;
 #pragma unroll

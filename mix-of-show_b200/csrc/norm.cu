@@ -3,6 +3,8 @@
 // (no floating-point atomics to global memory: per-chunk partials are summed in a fixed order).
 // Replaces diffusers GroupNorm / LayerNorm call sites inside ResnetBlock2D, Transformer2DModel and
 // BasicTransformerBlock (reached from mixofshow/pipelines/pipeline_edlora.py:277).
+#include <stdlib.h>
+
 #include "common.h"
 #include "tc.cuh"
 
@@ -25,16 +27,24 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long l
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
   const __nv_bfloat16* base = x + ((long long)b * HW) * ldx + o * 8;
-  for (int r = r0 + rl; r < r1; r += lanes) {
-    uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (long long)r * ldx));
-    uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  for (int rb = r0 + rl; rb < r1; rb += 4 * lanes) {
+    uint4 u4[4];   // four independent 16-byte loads in flight per thread
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float2 f = unpack_bf16x2(w[i]);
-      s[2 * i] += f.x;
-      q[2 * i] += f.x * f.x;
-      s[2 * i + 1] += f.y;
-      q[2 * i + 1] += f.y * f.y;
+    for (int k = 0; k < 4; ++k) {
+      const int r = rb + k * lanes;
+      u4[k] = r < r1 ? __ldg(reinterpret_cast<const uint4*>(base + (long long)r * ldx)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t w[4] = {u4[k].x, u4[k].y, u4[k].z, u4[k].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float2 f = unpack_bf16x2(w[i]);
+        s[2 * i] += f.x;
+        q[2 * i] += f.x * f.x;
+        s[2 * i + 1] += f.y;
+        q[2 * i + 1] += f.y * f.y;
+      }
     }
   }
 #pragma unroll
@@ -106,26 +116,37 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long l
   const int r0 = blockIdx.x * rows_per_block, r1 = min(HW, r0 + rows_per_block);
   const __nv_bfloat16* xb = x + ((long long)b * HW) * ldx + o * 8;
   __nv_bfloat16* yb = y + ((long long)b * HW) * ldy + o * 8;
-  for (int r = r0 + rl; r < r1; r += lanes) {
-    uint4 u = __ldg(reinterpret_cast<const uint4*>(xb + (long long)r * ldx));
-    uint32_t w[4] = {u.x, u.y, u.z, u.w};
-    float v[8];
+  for (int rb = r0 + rl; rb < r1; rb += 4 * lanes) {
+    uint4 u4[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float2 f = unpack_bf16x2(w[i]);
-      v[2 * i] = f.x * sc[2 * i] + sh[2 * i];
-      v[2 * i + 1] = f.y * sc[2 * i + 1] + sh[2 * i + 1];
+    for (int k = 0; k < 4; ++k) {
+      const int r = rb + k * lanes;
+      if (r < r1) u4[k] = __ldg(reinterpret_cast<const uint4*>(xb + (long long)r * ldx));
     }
-    if (silu_act) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = silu(v[i]);
+    for (int k = 0; k < 4; ++k) {
+      const int r = rb + k * lanes;
+      if (r < r1) {
+        const uint32_t w[4] = {u4[k].x, u4[k].y, u4[k].z, u4[k].w};
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float2 f = unpack_bf16x2(w[i]);
+          v[2 * i] = f.x * sc[2 * i] + sh[2 * i];
+          v[2 * i + 1] = f.y * sc[2 * i + 1] + sh[2 * i + 1];
+        }
+        if (silu_act) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = silu(v[i]);
+        }
+        uint4 out;
+        out.x = pack_bf16x2(v[0], v[1]);
+        out.y = pack_bf16x2(v[2], v[3]);
+        out.z = pack_bf16x2(v[4], v[5]);
+        out.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(yb + (long long)r * ldy) = out;
+      }
     }
-    uint4 out;
-    out.x = pack_bf16x2(v[0], v[1]);
-    out.y = pack_bf16x2(v[2], v[3]);
-    out.z = pack_bf16x2(v[4], v[5]);
-    out.w = pack_bf16x2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(yb + (long long)r * ldy) = out;
   }
 }
 
@@ -199,6 +220,157 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long 
   }
 }
 
+// ---------------------------------------------------------------------------------------------- fused GroupNorm
+// Single-kernel GroupNorm(+SiLU): every block keeps its rows in registers, publishes per-chunk partial statistics,
+// passes a per-sample grid barrier (monotonic ticket counter, all blocks co-resident by construction: the host caps
+// the grid at the occupancy limit), reduces the partials in a fixed order and normalises from registers.  One read
+// of x, one write of y, one launch.
+constexpr int GN_MAXR = 8;   // rows per thread kept in registers
+
+__global__ void __launch_bounds__(320, 2)
+gn_fused_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int HW, int C, int rows_per_chunk,
+                float* __restrict__ partial, unsigned int* __restrict__ counters, const float* __restrict__ gamma,
+                const float* __restrict__ beta, float eps, int silu_act, __nv_bfloat16* __restrict__ y, long long ldy) {
+  extern __shared__ float red[];  // [blockDim][16]
+  __shared__ float mean[GN_GROUPS], rstd[GN_GROUPS];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int oct = C / 8;
+  const int b = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+  const int lanes = blockDim.x / oct;
+  const int o = threadIdx.x % oct, rl = threadIdx.x / oct;
+  const int r0 = chunk * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
+  const int cpg = C / GN_GROUPS;
+  uint4 rows[GN_MAXR];
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  const __nv_bfloat16* base = x + ((long long)b * HW) * ldx + o * 8;
+#pragma unroll
+  for (int k = 0; k < GN_MAXR; ++k) {
+    const int r = r0 + rl + k * lanes;
+    if (r < r1) rows[k] = __ldg(reinterpret_cast<const uint4*>(base + (long long)r * ldx));
+  }
+#pragma unroll
+  for (int k = 0; k < GN_MAXR; ++k) {
+    const int r = r0 + rl + k * lanes;
+    if (r < r1) {
+      const uint32_t w[4] = {rows[k].x, rows[k].y, rows[k].z, rows[k].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_bf16x2(w[i]);
+        s[2 * i] += f.x;
+        q[2 * i] += f.x * f.x;
+        s[2 * i + 1] += f.y;
+        q[2 * i + 1] += f.y * f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    red[threadIdx.x * 16 + i] = s[i];
+    red[threadIdx.x * 16 + 8 + i] = q[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < GN_GROUPS) {
+    const int g = threadIdx.x;
+    float gs = 0.f, gq = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      for (int l = 0; l < lanes; ++l) {
+        const float* t = red + (l * oct + (c >> 3)) * 16 + (c & 7);
+        gs += t[0];
+        gq += t[8];
+      }
+    }
+    float* dst = partial + (((long long)b * nchunks + chunk) * GN_GROUPS + g) * 2;
+    dst[0] = gs;
+    dst[1] = gq;
+    __threadfence();
+  }
+  __syncthreads();
+  // ---- per-sample grid barrier (sense reversal: count returns to 0, generation increments; zero-initialised once)
+  if (threadIdx.x == 0) {
+    unsigned int* count = counters + b;
+    unsigned int* gen = counters + 32 + b;
+    unsigned int my_gen, cur;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(my_gen) : "l"(gen) : "memory");
+    const unsigned int old = atomicAdd(count, 1u);
+    if (old == (unsigned)nchunks - 1u) {
+      *count = 0u;
+      __threadfence();
+      atomicAdd(gen, 1u);
+    } else {
+      long long t0 = clock64();
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(gen) : "memory");
+        if (clock64() - t0 > 4000000000LL) {
+          printf("mos: groupnorm grid-barrier timeout\n");
+          __trap();
+        }
+      } while (cur == my_gen);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < GN_GROUPS * 4) {
+    const int g = threadIdx.x >> 2, sub = threadIdx.x & 3;
+    float ss = 0.f, qq = 0.f;
+    for (int c = sub; c < nchunks; c += 4) {
+      const float* src = partial + (((long long)b * nchunks + c) * GN_GROUPS + g) * 2;
+      float a0, a1;
+      asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(a0) : "l"(src) : "memory");   // bypass stale L1
+      asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(a1) : "l"(src + 1) : "memory");
+      ss += a0;
+      qq += a1;
+    }
+#pragma unroll
+    for (int d = 2; d > 0; d >>= 1) {
+      ss += __shfl_xor_sync(0xffffffffu, ss, d);
+      qq += __shfl_xor_sync(0xffffffffu, qq, d);
+    }
+    if (sub == 0) {
+      const float n = (float)HW * (float)cpg;
+      const float m = ss / n;
+      const float var = fmaxf(qq / n - m * m, 0.f);
+      mean[g] = m;
+      rstd[g] = rsqrtf(var + eps);
+    }
+  }
+  __syncthreads();
+  float sc[8], sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = o * 8 + i, g = c / cpg;
+    const float ga = __ldg(gamma + c) * rstd[g];
+    sc[i] = ga;
+    sh[i] = __ldg(beta + c) - mean[g] * ga;
+  }
+  __nv_bfloat16* yb = y + ((long long)b * HW) * ldy + o * 8;
+#pragma unroll
+  for (int k = 0; k < GN_MAXR; ++k) {
+    const int r = r0 + rl + k * lanes;
+    if (r < r1) {
+      const uint32_t w[4] = {rows[k].x, rows[k].y, rows[k].z, rows[k].w};
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_bf16x2(w[i]);
+        v[2 * i] = f.x * sc[2 * i] + sh[2 * i];
+        v[2 * i + 1] = f.y * sc[2 * i + 1] + sh[2 * i + 1];
+      }
+      if (silu_act) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = silu(v[i]);
+      }
+      uint4 out;
+      out.x = pack_bf16x2(v[0], v[1]);
+      out.y = pack_bf16x2(v[2], v[3]);
+      out.z = pack_bf16x2(v[4], v[5]);
+      out.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(yb + (long long)r * ldy) = out;
+    }
+  }
+}
+
 static int gn_block_threads(int C) {
   int oct = C / 8;
   int k = 320 / oct;
@@ -221,10 +393,46 @@ extern "C" int mos_groupnorm_fwd(const void* x, int64_t ldx, int32_t B, int32_t 
   MOS_CHECK_ARG(C % 32 == 0 && C % 8 == 0 && C <= 2560 && ldx % 8 == 0 && ldy % 8 == 0 && ldx >= C && ldy >= C,
                 "mos_groupnorm_fwd: bad C=%d ldx=%lld ldy=%lld", C, (long long)ldx, (long long)ldy);
   const int threads = gn_block_threads(C);
+  const int lanes = threads / (C / 8);
+  // ---- fused single-launch path: grid capped at the co-resident capacity (the kernel contains a grid barrier)
+  static int capacity = 0, use_fused = -1;
+  if (use_fused < 0) {
+    // measured slower than the two-launch path on B200 (grid barrier + 2 blocks/SM): opt-in only
+    const char* e = getenv("MOS_GN_FUSED");
+    use_fused = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (use_fused && capacity == 0) {
+    int dev = 0, sms = 0, per_sm = 0;
+    MOS_CHECK_CUDA(cudaGetDevice(&dev));
+    MOS_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    MOS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_fused_kernel, 320, 320 * 16 * sizeof(float)));
+    capacity = sms * (per_sm > 0 ? per_sm : 1);
+  }
+  if (use_fused) {
+    int nchunks = capacity / B;
+    if (nchunks > (int)ceil_div(HW, lanes)) nchunks = (int)ceil_div(HW, lanes);
+    if (nchunks < 1) nchunks = 1;
+    int rows_per_chunk = (int)ceil_div(HW, nchunks);
+    nchunks = (int)ceil_div(HW, rows_per_chunk);
+    const long long need = (long long)B * nchunks * GN_GROUPS * 2 + 64;   // + per-sample ticket counters
+    if (rows_per_chunk <= GN_MAXR * lanes && B <= 32 && need <= partial_capacity_floats && B * nchunks <= capacity) {
+      unsigned int* counters = reinterpret_cast<unsigned int*>(partial + partial_capacity_floats - 64);
+      MOS_CHECK_CUDA(launch_pdl(gn_fused_kernel, dim3(nchunks, B), dim3(threads), threads * 16 * sizeof(float), stream,
+                                reinterpret_cast<const __nv_bfloat16*>(x), (long long)ldx, (int)HW, (int)C,
+                                rows_per_chunk, partial, counters, gamma, beta, eps, (int)silu_act,
+                                reinterpret_cast<__nv_bfloat16*>(y), (long long)ldy));
+      return MOS_OK;
+    }
+  }
+  // ---- two-launch fallback (very large maps)
   // aim for ~4 blocks per SM overall
-  int nchunks = (int)ceil_div(592, B);
+  int nchunks = (int)ceil_div(2368, B);     // up to ~16 blocks per SM in flight: latency-bound kernels want parallelism
   int min_rows = 4 * (threads / (C / 8));
   if (nchunks > (int)ceil_div(HW, min_rows)) nchunks = (int)ceil_div(HW, min_rows);
+  {
+    const long long cap = ((long long)partial_capacity_floats - 64) / ((long long)B * GN_GROUPS * 2);
+    if (nchunks > cap) nchunks = (int)cap;
+  }
   if (nchunks < 1) nchunks = 1;
   int rows_per_chunk = (int)ceil_div(HW, nchunks);
   nchunks = (int)ceil_div(HW, rows_per_chunk);

@@ -67,6 +67,7 @@ class UNetEngine:
         self.adapters = None    # list of 4 bf16 NHWC tensors [B*HW_l, C_l]
         self.region_hw = None   # (height, width) in pixels passed by the regional pipeline
         self.controller = None
+        self.skip = set()       # profiling aid: op families not launched ('gemm','splitk','attn','gn','ln','misc')
 
     # ------------------------------------------------------------------------------------------ packing
     def _t(self, name):
@@ -221,7 +222,7 @@ class UNetEngine:
         self.in_t = torch.zeros(B, device=self.dev)
         self.in_ehs = torch.zeros(len(self.xattn_names), B, self.n_text, self.cross_dim, device=self.dev, dtype=BF16)
         self.out_eps = torch.zeros(B, 4, H, W, device=self.dev)
-        self.gn_partial = torch.empty(B * 592 * 64, device=self.dev)
+        self.gn_partial = torch.zeros(B * 592 * 64, device=self.dev)   # tail words: grid-barrier state (zero once)
         # concat buffers of the 12 up-block resnets: [h | skip]
         nb = len(self.block_out)
         rev = list(reversed(self.block_out))
@@ -260,6 +261,8 @@ class UNetEngine:
         K = ent['K'] // 9 if conv is not None else ent['K']
         kb_total = ent['K'] // 64
         lora = 'lora_down' in ent
+        if 'gemm' in self.skip:
+            return out
         splits = 1
         if not lora and not geglu and heads is None:
             splits = self._splits(M, ent['N'], kb_total)
@@ -268,9 +271,10 @@ class UNetEngine:
             partial = self.buf('splitk', (16 * 1024 * 1280,), torch.float32)
             assert splits * M * ent['N'] <= partial.numel()
             ops.gemm(A, ent['W'], None, M=M, splits=splits, partial=partial, conv=conv, lda=lda)
-            ops.splitk_finalize(partial, splits, M, ent['N'], out, bias=ent['bias'], bias_batch=bias_batch,
-                                rows_per_batch=rows_per_batch, residual=residual,
-                                bias_batch_ld=self.temb_total if bias_batch is not None else 0)
+            if 'splitk' not in self.skip:
+              ops.splitk_finalize(partial, splits, M, ent['N'], out, bias=ent['bias'], bias_batch=bias_batch,
+                                  rows_per_batch=rows_per_batch, residual=residual,
+                                  bias_batch_ld=self.temb_total if bias_batch is not None else 0)
             self.launches += 2
             return out
         if lora:
@@ -282,12 +286,16 @@ class UNetEngine:
 
     def groupnorm(self, x, key, y, *, HW, C, eps, silu):
         g, b = self.w[key]
+        if 'gn' in self.skip:
+            return
         ops.groupnorm(x, g, b, y, self.gn_partial, B=self.B, HW=HW, C=C, eps=eps, silu=silu, ldx=x.stride(0),
                       ldy=y.stride(0))
         self.launches += 2
 
     def layernorm(self, x, key, y, *, M, C):
         g, b = self.w[key]
+        if 'ln' in self.skip:
+            return
         ops.layernorm(x, g, b, y, M=M, C=C, ldx=x.stride(0), ldy=y.stride(0))
         self.launches += 1
 
@@ -351,7 +359,8 @@ class UNetEngine:
                   heads=self._heads([Q, K, Vt], [MOS_SEG_ROWS, MOS_SEG_ROWS, MOS_SEG_TRANSPOSED],
                                     [N, N, _r(N, 8)], C, N))
         ao = self.buf('tr_ao', (M, C))
-        ops.attention(Q, K, Vt, ao.view(B, N, C), batch=B, heads=Hh, head_dim=d, nq=N, nk=N)
+        if 'attn' not in self.skip:
+            ops.attention(Q, K, Vt, ao.view(B, N, C), batch=B, heads=Hh, head_dim=d, nq=N, nk=N)
         self.launches += 1
         t1 = self.buf('tr_t1', (M, C))
         self.gemm(ao, self.w[tb + '.attn1.out'], t1, M=M, residual=t0)
@@ -362,7 +371,9 @@ class UNetEngine:
         probs = None
         if self.emit_probs:
             probs = self.buf(f'probs{xidx}', (BH, N, self.n_text), torch.float32)
-        ops.attention(Q, Kc, Vc, ao.view(B, N, C), batch=B, heads=Hh, head_dim=d, nq=N, nk=self.n_text, probs=probs)
+        if 'attn' not in self.skip:
+            ops.attention(Q, Kc, Vc, ao.view(B, N, C), batch=B, heads=Hh, head_dim=d, nq=N, nk=self.n_text,
+                          probs=probs)
         self.launches += 1
         if self.regions:
             self._region_rewrite(tb, Q, ao, h, w, C, xidx)
