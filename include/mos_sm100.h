@@ -66,6 +66,7 @@ typedef struct mos_gemm_args {
   int64_t seg_rows_pad[3];   /* padded row count of the destination (tokens or keys) */
   int32_t heads, head_dim, dpad, dv_pad;
   int64_t tokens_per_batch;
+  int32_t accumulate;     /* MOS_OUT_F32 only: out += result (Gram accumulation, gradient fusion) */
 } mos_gemm_args;
 
 int mos_gemm_bf16(const mos_gemm_args* args, void* stream);
@@ -143,6 +144,29 @@ int mos_cfg_dpmpp_step(const float* noise_pred, float* latents, float* x0_prev, 
 int mos_region_combine(const void* glob, const void* const* region_ptrs_dev, int32_t nregions,
                        const int32_t* boxes_host, int32_t B, int32_t FH, int32_t FW, int32_t C, int64_t ld, void* out,
                        void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Gradient fusion in Gram form (gradient_fusion.py:22-96 update_quasi_newton / chunk_compute_mse, :99-143 merge,
+ * :146-167 feature hooks).  Features are reduced on the fly to G_c = X_c^T X_c (mos_transpose_bf16 + mos_gemm_bf16
+ * with MOS_OUT_F32 / accumulate, or mos_gram_small for the handful of text-token rows); a closure of the L-BFGS
+ * driver is mos_sgemm_nn (Y = W G) + mos_ls_grad_loss; the driver's vector algebra uses the mos_vec_* primitives
+ * (fixed reduction order -> reproducible scalars).  `scratch` >= 256 floats, `out`/`loss` 1 float, all on device.
+ * ---------------------------------------------------------------------------------------------------------- */
+int mos_transpose_bf16(const void* x, int64_t ldx, int32_t rows, int32_t C, void* out, int64_t ldo, void* stream);
+int mos_gram_small(const float* X, int32_t n, int32_t d, float* G, int32_t accumulate, void* stream);
+int mos_atb_small(const float* X, const float* Y, int32_t n, int32_t dx, int32_t dy, float* out, int32_t accumulate,
+                  void* stream);
+int mos_sgemm_nn(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, float alpha, float beta,
+                 void* stream);
+int mos_ls_grad_loss(const float* W, const float* Y, const float* Cm, int64_t n, float s, float f0, float* grad,
+                     float* loss, float* scratch, void* stream);
+int mos_vec_dot(const float* a, const float* b, int64_t n, float* out, float* scratch, void* stream);
+int mos_vec_asum(const float* a, int64_t n, float* out, float* scratch, void* stream);
+int mos_vec_absmax(const float* a, int64_t n, float scale, float* out, float* scratch, void* stream);
+int mos_vec_axpby(float* y, const float* x, float alpha, float beta, int64_t n, void* stream);
+/* Batched W_l += alpha * up_l @ down_l (convert_edlora_to_diffusers.py:33-76, gradient_fusion.py:99-143).
+ * table_dev: int64 [n_layers, 6] = {W fp32 ptr, down fp32 ptr, up fp32 ptr, out, in, rank}. */
+int mos_lora_merge(const int64_t* table_dev, int32_t n_layers, float alpha, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,302 @@
+// fusion.cu — K7/K8: kernels of gradient fusion (gradient_fusion.py) in Gram form.
+//
+// The reference solves, per layer,  min_W mean((X W^T - V)^2)  with V = X W_c^T recorded per concept c
+// (gradient_fusion.py:38-96, 394-429, 700-740) by L-BFGS, streaming X and V (GBs) from host memory on every closure
+// call.  Because V_c = X_c W_c^T exactly (bias removed, gradient_fusion.py:155-160), the objective only depends on the
+// per-concept Gram matrices  G_c = X_c^T X_c:
+//     f(W) = s * sum_c tr((W - W_c) G_c (W - W_c)^T),   s = 1 / (n * out)
+//     grad = 2 s (W G - C),  G = sum_c G_c,  C = sum_c W_c G_c,   f = s (<W, W G - 2 C> + vv),  vv = sum_c <W_c, W_c G_c>
+// so features are reduced to [in, in] fp32 on the fly (tcgen05 GEMM with fp32 accumulate output, see gemm.cu) and a
+// closure is one [out, in] x [in, in] fp32 GEMM.  Kernels here: bf16 transpose (Gram operand), small-n Gram, fp32
+// SGEMM, closure epilogue (grad + loss), deterministic vector primitives for the L-BFGS driver, batched LoRA merge.
+#include "common.h"
+#include "tc.cuh"
+
+namespace mos {
+
+// ------------------------------------------------------------------ bf16 transpose: x [rows, ldx](C cols) -> out [C, ldo]
+__global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int rows, int C,
+                                      __nv_bfloat16* __restrict__ out, long long ldo) {
+  __shared__ __nv_bfloat16 tile[32][34];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < C) ? x[(long long)r * ldx + c] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < C && r < rows) out[(long long)c * ldo + r] = tile[threadIdx.x][i];
+  }
+}
+
+// ------------------------------------------------------------------ small-n A^T B: G[i][j] (+)= sum_r X[r][i] Y[r][j]
+__global__ void atb_small_kernel(const float* __restrict__ X, const float* __restrict__ Y, int n, int dx, int dy,
+                                 float* __restrict__ G, int accumulate) {
+  __shared__ float xi[16][17], xj[16][17];
+  const int i0 = blockIdx.y * 16, j0 = blockIdx.x * 16;
+  float acc = 0.f;
+  for (int r0 = 0; r0 < n; r0 += 16) {
+    const int r = r0 + threadIdx.y;
+    xi[threadIdx.y][threadIdx.x] = (r < n && i0 + threadIdx.x < dx) ? X[(long long)r * dx + i0 + threadIdx.x] : 0.f;
+    xj[threadIdx.y][threadIdx.x] = (r < n && j0 + threadIdx.x < dy) ? Y[(long long)r * dy + j0 + threadIdx.x] : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc += xi[k][threadIdx.y] * xj[k][threadIdx.x];
+    __syncthreads();
+  }
+  const int i = i0 + threadIdx.y, j = j0 + threadIdx.x;
+  if (i < dx && j < dy) G[(long long)i * dy + j] = (accumulate ? G[(long long)i * dy + j] : 0.f) + acc;
+}
+
+// ------------------------------------------------------------------ fp32 SGEMM  C = alpha * A[M,K] * B[K,N] + beta * C
+// 64x64 tile, 256 threads, 4x4 micro-tile, K step 16 (CUDA cores: exact fp32 for the closure of the solver)
+__global__ void __launch_bounds__(256)
+sgemm_nn_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int K,
+                float alpha, float beta) {
+  __shared__ float As[16][64 + 4], Bs[16][64 + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      const int m = i >> 4, k = i & 15;   // A tile [64][16]
+      As[k][m] = (m0 + m < M && k0 + k < K) ? A[(long long)(m0 + m) * K + k0 + k] : 0.f;
+      const int kk = i >> 6, n = i & 63;  // B tile [16][64]
+      Bs[kk][n] = (k0 + kk < K && n0 + n < N) ? B[(long long)(k0 + kk) * N + n0 + n] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < N) {
+        float* c = C + (long long)m * N + n;
+        *c = alpha * acc[i][j] + (beta != 0.f ? beta * *c : 0.f);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ deterministic block reductions
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (threadIdx.x < 32) {
+    r = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) r += __shfl_xor_sync(0xffffffffu, r, d);
+  }
+  __syncthreads();
+  return r;   // valid in thread 0
+}
+__device__ __forceinline__ float block_max(float v, float* sh) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (threadIdx.x < 32) {
+    r = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, d));
+  }
+  __syncthreads();
+  return r;
+}
+
+constexpr int RED_BLOCKS = 256;   // fixed grid -> fixed summation order -> bitwise reproducible scalars
+
+// closure epilogue: grad = 2 s (Y - C);  partial[b] = sum W .* (Y - 2 C)
+__global__ void ls_grad_loss_kernel(const float* __restrict__ W, const float* __restrict__ Y, const float* __restrict__ Cm,
+                                    long long n, float s, float* __restrict__ grad, float* __restrict__ partial) {
+  __shared__ float sh[32];
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float y = Y[i], c = Cm[i], w = W[i];
+    grad[i] = 2.f * s * (y - c);
+    acc += w * (y - 2.f * c);
+  }
+  const float t = block_sum(acc, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+// out[0] = scale * sum(partial) + add   (add applied after the scaling: keeps a large constant from swamping the sum)
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int nb, float scale, float add, int is_max,
+                                       float* __restrict__ out) {
+  __shared__ float sh[32];
+  float v = 0.f;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) v = is_max ? fmaxf(v, partial[i]) : v + partial[i];
+  const float t = is_max ? block_max(v, sh) : block_sum(v, sh);
+  if (threadIdx.x == 0) out[0] = is_max ? t : scale * t + add;
+}
+__global__ void vec_dot_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n,
+                               float* __restrict__ partial) {
+  __shared__ float sh[32];
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc += a[i] * b[i];
+  const float t = block_sum(acc, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+__global__ void vec_asum_kernel(const float* __restrict__ a, long long n, float* __restrict__ partial) {
+  __shared__ float sh[32];
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc += fabsf(a[i]);
+  const float t = block_sum(acc, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+__global__ void vec_absmax_kernel(const float* __restrict__ a, long long n, float scale, float* __restrict__ partial) {
+  __shared__ float sh[32];
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc = fmaxf(acc, fabsf(a[i] * scale));
+  const float t = block_max(acc, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+// y = alpha * x + beta * y   (beta = 0: plain scaled copy, y may be uninitialised)
+__global__ void vec_axpby_kernel(float* __restrict__ y, const float* __restrict__ x, float alpha, float beta,
+                                 long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = alpha * x[i] + (beta != 0.f ? beta * y[i] : 0.f);
+}
+
+// ------------------------------------------------------------------ batched LoRA merge: W_l += alpha * up_l @ down_l
+// table[l] = {W ptr, down ptr, up ptr, out, in, rank}; W fp32 [out, in] (4-D 1x1 conv weights have the same layout)
+__global__ void lora_merge_kernel(const long long* __restrict__ table, float alpha) {
+  const long long* e = table + (long long)blockIdx.y * 6;
+  float* W = reinterpret_cast<float*>(e[0]);
+  const float* down = reinterpret_cast<const float*>(e[1]);
+  const float* up = reinterpret_cast<const float*>(e[2]);
+  const long long out = e[3], in = e[4];
+  const int rank = (int)e[5];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < out * in; i += (long long)gridDim.x * blockDim.x) {
+    const long long o = i / in, c = i - o * in;
+    float acc = 0.f;
+    for (int r = 0; r < rank; ++r) acc += up[o * rank + r] * down[(long long)r * in + c];
+    W[i] += alpha * acc;
+  }
+}
+
+}  // namespace mos
+
+using namespace mos;
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int mos_transpose_bf16(const void* x, int64_t ldx, int32_t rows, int32_t C, void* out, int64_t ldo,
+                                  void* stream) {
+  MOS_CHECK_ARG(x && out && rows > 0 && C > 0 && ldo >= rows, "mos_transpose_bf16: bad arguments");
+  dim3 grid((unsigned)ceil_div(C, 32), (unsigned)ceil_div(rows, 32)), block(32, 8);
+  MOS_CHECK_CUDA(launch_pdl(transpose_bf16_kernel, grid, block, 0, STREAM(stream),
+                            reinterpret_cast<const __nv_bfloat16*>(x), (long long)ldx, (int)rows, (int)C,
+                            reinterpret_cast<__nv_bfloat16*>(out), (long long)ldo));
+  return MOS_OK;
+}
+
+extern "C" int mos_gram_small(const float* X, int32_t n, int32_t d, float* G, int32_t accumulate, void* stream) {
+  MOS_CHECK_ARG(X && G && n > 0 && d > 0, "mos_gram_small: bad arguments");
+  dim3 grid((unsigned)ceil_div(d, 16), (unsigned)ceil_div(d, 16)), block(16, 16);
+  atb_small_kernel<<<grid, block, 0, STREAM(stream)>>>(X, X, n, d, d, G, accumulate);
+  MOS_CHECK_LAUNCH();
+  return MOS_OK;
+}
+
+// out [dx, dy] (+)= X^T Y for X [n, dx], Y [n, dy] fp32 (C = V^T K of update_quasi_newton's generic form)
+extern "C" int mos_atb_small(const float* X, const float* Y, int32_t n, int32_t dx, int32_t dy, float* out,
+                             int32_t accumulate, void* stream) {
+  MOS_CHECK_ARG(X && Y && out && n > 0 && dx > 0 && dy > 0, "mos_atb_small: bad arguments");
+  dim3 grid((unsigned)ceil_div(dy, 16), (unsigned)ceil_div(dx, 16)), block(16, 16);
+  atb_small_kernel<<<grid, block, 0, STREAM(stream)>>>(X, Y, n, dx, dy, out, accumulate);
+  MOS_CHECK_LAUNCH();
+  return MOS_OK;
+}
+
+extern "C" int mos_sgemm_nn(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, float alpha,
+                            float beta, void* stream) {
+  MOS_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0, "mos_sgemm_nn: bad arguments");
+  dim3 grid((unsigned)ceil_div(N, 64), (unsigned)ceil_div(M, 64));
+  sgemm_nn_kernel<<<grid, 256, 0, STREAM(stream)>>>(A, B, C, M, N, K, alpha, beta);
+  MOS_CHECK_LAUNCH();
+  return MOS_OK;
+}
+
+// grad = 2 s (Y - C); loss[0] = s * <W, Y - 2C> + f0.  scratch: >= 256 floats.
+extern "C" int mos_ls_grad_loss(const float* W, const float* Y, const float* Cm, int64_t n, float s, float f0,
+                                float* grad, float* loss, float* scratch, void* stream) {
+  MOS_CHECK_ARG(W && Y && Cm && grad && loss && scratch && n > 0, "mos_ls_grad_loss: bad arguments");
+  ls_grad_loss_kernel<<<RED_BLOCKS, 256, 0, STREAM(stream)>>>(W, Y, Cm, n, s, grad, scratch);
+  MOS_CHECK_LAUNCH();
+  reduce_partials_kernel<<<1, 256, 0, STREAM(stream)>>>(scratch, RED_BLOCKS, s, f0, 0, loss);
+  MOS_CHECK_LAUNCH();
+  return MOS_OK;
+}
+
+extern "C" int mos_vec_dot(const float* a, const float* b, int64_t n, float* out, float* scratch, void* stream) {
+  MOS_CHECK_ARG(a && b && out && scratch && n > 0, "mos_vec_dot: bad arguments");
+  vec_dot_kernel<<<RED_BLOCKS, 256, 0, STREAM(stream)>>>(a, b, n, scratch);
+  MOS_CHECK_LAUNCH();
+  reduce_partials_kernel<<<1, 256, 0, STREAM(stream)>>>(scratch, RED_BLOCKS, 1.f, 0.f, 0, out);
+  MOS_CHECK_LAUNCH();
+  return MOS_OK;
+}
+
+extern "C" int mos_vec_asum(const float* a, int64_t n, float* out, float* scratch, void* stream) {
+  MOS_CHECK_ARG(a && out && scratch && n > 0, "mos_vec_asum: bad arguments");
+  vec_asum_kernel<<<RED_BLOCKS, 256, 0, STREAM(stream)>>>(a, n, scratch);
+  MOS_CHECK_LAUNCH();
+  reduce_partials_kernel<<<1, 256, 0, STREAM(stream)>>>(scratch, RED_BLOCKS, 1.f, 0.f, 0, out);
+  MOS_CHECK_LAUNCH();
+  return MOS_OK;
+}
+
+extern "C" int mos_vec_absmax(const float* a, int64_t n, float scale, float* out, float* scratch, void* stream) {
+  MOS_CHECK_ARG(a && out && scratch && n > 0, "mos_vec_absmax: bad arguments");
+  vec_absmax_kernel<<<RED_BLOCKS, 256, 0, STREAM(stream)>>>(a, n, scale, scratch);
+  MOS_CHECK_LAUNCH();
+  reduce_partials_kernel<<<1, 256, 0, STREAM(stream)>>>(scratch, RED_BLOCKS, 1.f, 0.f, 1, out);
+  MOS_CHECK_LAUNCH();
+  return MOS_OK;
+}
+
+extern "C" int mos_vec_axpby(float* y, const float* x, float alpha, float beta, int64_t n, void* stream) {
+  MOS_CHECK_ARG(y && x && n > 0, "mos_vec_axpby: bad arguments");
+  long long blocks = ceil_div(n, 256 * 4);
+  if (blocks > 1184) blocks = 1184;
+  vec_axpby_kernel<<<(unsigned)blocks, 256, 0, STREAM(stream)>>>(y, x, alpha, beta, n);
+  MOS_CHECK_LAUNCH();
+  return MOS_OK;
+}
+
+extern "C" int mos_lora_merge(const int64_t* table_dev, int32_t n_layers, float alpha, void* stream) {
+  MOS_CHECK_ARG(table_dev && n_layers > 0, "mos_lora_merge: bad arguments");
+  dim3 grid(148, (unsigned)n_layers);
+  lora_merge_kernel<<<grid, 256, 0, STREAM(stream)>>>(reinterpret_cast<const long long*>(table_dev), alpha);
+  MOS_CHECK_LAUNCH();
+  return MOS_OK;
+}

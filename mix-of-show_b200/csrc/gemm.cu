@@ -69,6 +69,7 @@ struct GemmDev {
   long long seg_rows_pad[3];
   int heads, head_dim, dpad, dv_pad;
   long long tokens_per_batch;
+  int accum;           // MOS_OUT_F32: out += result (Gram accumulation)
 };
 
 __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v) {
@@ -462,8 +463,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               if (valid) {
                 float* orow = reinterpret_cast<float*>(p.out) + m * p.ldc + nc;
 #pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                  *reinterpret_cast<float4*>(orow + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                for (int j = 0; j < 16; j += 4) {
+                  float4 r4 = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                  if (p.accum) {
+                    const float4 old = *reinterpret_cast<const float4*>(orow + j);
+                    r4.x += old.x; r4.y += old.y; r4.z += old.z; r4.w += old.w;
+                  }
+                  *reinterpret_cast<float4*>(orow + j) = r4;
+                }
               }
             } else if (valid) {  // MOS_OUT_HEADS
               const int seg_len = p.heads * p.head_dim;
@@ -732,6 +739,7 @@ extern "C" int mos_gemm_bf16(const mos_gemm_args* a, void* stream_) {
   p.dpad = a->dpad;
   p.dv_pad = a->dv_pad;
   p.tokens_per_batch = a->tokens_per_batch > 0 ? a->tokens_per_batch : 1;
+  p.accum = a->accumulate;
   if (a->bias_batch && !a->conv)
     MOS_CHECK_ARG(p.rows_per_batch >= 32, "mos_gemm_bf16: bias_batch needs rows_per_batch >= 32 in plain mode");
   p.total_super = (p.n_tiles / p.cx) * (m_tiles / p.cm) * splits;

@@ -1,0 +1,399 @@
+"""B200 gradient fusion — drop-in for the UNet half of the reference's `gradient_fusion.py`.
+
+  update_quasi_newton(K_target, V_target, W, iters, device)     <- gradient_fusion.py:38-96 (+ chunk_compute_mse :22-35)
+  merge_lora_into_weight(original, lora, layer_names, model_type, alpha, device)   <- :99-143
+  merge_kv_in_cross_attention(...)   (text features supplied by the caller)          <- :325-457
+  merge_spatial_attention(...)       (engine-side Gram recording instead of hooks)   <- :146-167, :579-624, :627-747
+
+Design (fusion.cu header): the per-layer objective  mean((X W^T - V)^2)  depends on the recorded
+features only through G = X^T X and C = V^T X.  The reference keeps X, V (GBs) in host RAM and re-streams them to the
+GPU for each of the <= 62 closure evaluations per layer; here the UNet engine reduces the features to per-concept
+Gram matrices on the fly (tcgen05 GEMM, fp32 accumulate), and a closure is one [out,in]x[in,in] fp32 GEMM.
+The optimiser is the same algorithm the reference calls (torch.optim.LBFGS: history 25, lr 1, strong-Wolfe line
+search, tolerance 1e-16, ONE .step of max_iter iterations, best iterate over all closure evaluations), restated here
+over CUDA vector primitives (mos_vec_*), working on the correction D = W - W0 so that the quadratic is evaluated
+without the cancellation of the raw Gram form.  The text-encoder half (merge_text_encoder, merge_new_concepts_) is a
+CLIP-side component: SURVEY.md §8f "next".
+"""
+import math
+
+import torch
+
+from mos_b200 import ops
+
+F32 = torch.float32
+
+
+# ------------------------------------------------------------------------------------------------ L-BFGS (restated)
+def _cubic_min(x1, f1, g1, x2, f2, g2, bounds=None):
+    """Minimiser of the cubic through (x1,f1,g1), (x2,f2,g2), clipped to `bounds` (Nocedal & Wright eq. 3.59)."""
+    lo, hi = bounds if bounds is not None else ((x1, x2) if x1 <= x2 else (x2, x1))
+    d1 = g1 + g2 - 3.0 * (f1 - f2) / (x1 - x2)
+    disc = d1 * d1 - g1 * g2
+    if disc < 0:
+        return 0.5 * (lo + hi)
+    d2 = math.sqrt(disc)
+    if x1 <= x2:
+        pos = x2 - (x2 - x1) * ((g2 + d2 - d1) / (g2 - g1 + 2.0 * d2))
+    else:
+        pos = x1 - (x1 - x2) * ((g1 + d2 - d1) / (g1 - g2 + 2.0 * d2))
+    return min(max(pos, lo), hi)
+
+
+class _GramProblem:
+    """f(D) = s <D, D G - 2 R> + f0,  grad = 2 s (D G - R);  D = W - W0 (flat fp32 on the device)."""
+
+    def __init__(self, G, R, s, f0, W0):
+        self.G, self.R, self.s, self.f0, self.W0 = G, R, float(s), float(f0), W0
+        self.shape = tuple(R.shape)
+        dev = R.device
+        self.Y = torch.empty_like(R)
+        self.scal = torch.zeros(1, device=dev, dtype=F32)
+        self.scratch = torch.empty(256, device=dev, dtype=F32)
+        self.best_loss, self.best_D = float('inf'), None
+        self.evals = 0
+
+    def dot(self, a, b):
+        ops.vec_dot(a, b, self.scal, self.scratch)
+        return self.scal.item()
+
+    def absmax(self, a, scale=1.0):
+        ops.vec_absmax(a, self.scal, self.scratch, scale)
+        return self.scal.item()
+
+    def closure(self, D):
+        """-> (loss float, grad tensor); tracks the best iterate like gradient_fusion.py:72-74."""
+        ops.sgemm_nn(D.view(self.shape), self.G, self.Y)
+        grad = torch.empty_like(D)
+        ops.ls_grad_loss(D, self.Y, self.R, self.s, self.f0, grad, self.scal, self.scratch)
+        loss = self.scal.item()
+        self.evals += 1
+        if loss < self.best_loss:
+            self.best_loss = loss
+            self.best_D = D.clone()
+        return loss, grad
+
+
+def _strong_wolfe(P, x, t, d, f, g, gtd, c1=1e-4, c2=0.9, tol_change=1e-9, max_ls=25):
+    """Strong-Wolfe line search (bracketing + zoom with cubic interpolation), as used by torch.optim.LBFGS."""
+    d_norm = P.absmax(d)
+
+    def phi(step):
+        xt = x.clone()
+        ops.vec_axpby(xt, d, step, 1.0)
+        fv, gv = P.closure(xt)
+        return fv, gv, P.dot(gv, d)
+
+    f_new, g_new, gtd_new = phi(t)
+    evals = 1
+    t_prev, f_prev, g_prev, gtd_prev = 0.0, f, g, gtd
+    done, it = False, 0
+    br = None
+    while it < max_ls:
+        if f_new > f + c1 * t * gtd or (it > 1 and f_new >= f_prev):
+            br = [[t_prev, f_prev, g_prev, gtd_prev], [t, f_new, g_new, gtd_new]]
+            break
+        if abs(gtd_new) <= -c2 * gtd:
+            br = [[t, f_new, g_new, gtd_new]]
+            done = True
+            break
+        if gtd_new >= 0:
+            br = [[t_prev, f_prev, g_prev, gtd_prev], [t, f_new, g_new, gtd_new]]
+            break
+        lo, hi = t + 0.01 * (t - t_prev), t * 10.0
+        t_next = _cubic_min(t_prev, f_prev, gtd_prev, t, f_new, gtd_new, bounds=(lo, hi))
+        t_prev, f_prev, g_prev, gtd_prev = t, f_new, g_new, gtd_new
+        t = t_next
+        f_new, g_new, gtd_new = phi(t)
+        evals += 1
+        it += 1
+    if it == max_ls:
+        br = [[0.0, f, g, gtd], [t, f_new, g_new, gtd_new]]
+    # zoom
+    stalled = False
+    if len(br) == 2:
+        low, high = (0, 1) if br[0][1] <= br[1][1] else (1, 0)
+    while not done and it < max_ls:
+        if abs(br[1][0] - br[0][0]) * d_norm < tol_change:
+            break
+        t = _cubic_min(br[0][0], br[0][1], br[0][3], br[1][0], br[1][1], br[1][3])
+        tmax, tmin = max(br[0][0], br[1][0]), min(br[0][0], br[1][0])
+        eps = 0.1 * (tmax - tmin)
+        if min(tmax - t, t - tmin) < eps:
+            if stalled or t >= tmax or t <= tmin:
+                t = tmax - eps if abs(t - tmax) < abs(t - tmin) else tmin + eps
+                stalled = False
+            else:
+                stalled = True
+        else:
+            stalled = False
+        f_new, g_new, gtd_new = phi(t)
+        evals += 1
+        it += 1
+        if f_new > f + c1 * t * gtd or f_new >= br[low][1]:
+            br[high] = [t, f_new, g_new, gtd_new]
+            low, high = (0, 1) if br[0][1] <= br[1][1] else (1, 0)
+        else:
+            if abs(gtd_new) <= -c2 * gtd:
+                done = True
+            elif gtd_new * (br[high][0] - br[low][0]) >= 0:
+                br[high] = list(br[low])
+            br[low] = [t, f_new, g_new, gtd_new]
+    sel = br[0] if len(br) == 1 else br[low]
+    return sel[1], sel[2], sel[0], evals
+
+
+def lbfgs_minimize(P, x0, max_iter, history=25, lr=1.0, tol_grad=1e-16, tol_change=1e-16):
+    """ONE torch.optim.LBFGS.step(closure) with line_search_fn='strong_wolfe' (gradient_fusion.py:76-85)."""
+    max_eval = max_iter * 5 // 4
+    x = x0.clone()
+    loss, g = P.closure(x)
+    evals = 1
+    if P.absmax(g) <= tol_grad:
+        return x
+    S, Y, rho = [], [], []          # curvature pairs (s_i = step, y_i = gradient change), rho_i = 1 / <y_i, s_i>
+    h_diag, d, t, prev_g, prev_loss = 1.0, None, None, None, None
+    n_iter = 0
+    while n_iter < max_iter:
+        n_iter += 1
+        if n_iter == 1:
+            d = g.clone()
+            ops.vec_axpby(d, g, -1.0, 0.0)                      # d = -g
+        else:
+            y = g.clone()
+            ops.vec_axpby(y, prev_g, -1.0, 1.0)                 # y = g - prev_g
+            s = torch.empty_like(d)
+            ops.vec_axpby(s, d, t, 0.0)                         # s = t d
+            ys = P.dot(y, s)
+            if ys > 1e-10:
+                if len(S) == history:
+                    S.pop(0), Y.pop(0), rho.pop(0)
+                S.append(s), Y.append(y), rho.append(1.0 / ys)
+                h_diag = ys / P.dot(y, y)
+            k = len(S)
+            al = [0.0] * k
+            q = torch.empty_like(g)
+            ops.vec_axpby(q, g, -1.0, 0.0)                      # two-loop recursion on q = -g
+            for i in range(k - 1, -1, -1):
+                al[i] = P.dot(S[i], q) * rho[i]
+                ops.vec_axpby(q, Y[i], -al[i], 1.0)
+            d = q
+            ops.vec_axpby(d, d, h_diag, 0.0)                    # r = H0 q
+            for i in range(k):
+                be = P.dot(Y[i], d) * rho[i]
+                ops.vec_axpby(d, S[i], al[i] - be, 1.0)
+        prev_g, prev_loss = g.clone(), loss
+        if n_iter == 1:
+            ops.vec_asum(g, P.scal, P.scratch)                  # |g|_1
+            t = min(1.0, 1.0 / P.scal.item()) * lr
+        else:
+            t = lr
+        gtd = P.dot(g, d)
+        if gtd > -tol_change:
+            break
+        loss, g, t, ls_evals = _strong_wolfe(P, x, t, d, loss, g, gtd)
+        ops.vec_axpby(x, d, t, 1.0)
+        evals += ls_evals
+        if n_iter == max_iter or evals >= max_eval:
+            break
+        if P.absmax(g) <= tol_grad or P.absmax(d, t) <= tol_change or abs(loss - prev_loss) < tol_change:
+            break
+    return x
+
+
+# ------------------------------------------------------------------------------------------------ solver front ends
+def solve_from_gram(G, Cm, vv, n_rows, W0, iters):
+    """min_W (1/(n out)) (tr(W G W^T) - 2 tr(W C^T) + vv) by the reference's L-BFGS recipe, starting at W0.
+    G [in,in], Cm [out,in] fp32 on the device; returns the best W over all closure evaluations (fp32, device)."""
+    out_f, in_f = Cm.shape
+    dev = Cm.device
+    W0 = W0.to(dev, F32).contiguous()
+    G = G.to(dev, F32).contiguous()
+    s = 1.0 / (float(n_rows) * out_f)
+    R = Cm.to(dev, F32).clone().contiguous()
+    ops.sgemm_nn(W0, G, R, alpha=-1.0, beta=1.0)               # R = C - W0 G
+    # f(W0) once, in float64 (host-side setup scalar; keeps the shifted quadratic free of cancellation)
+    W0d, Gd, Cd = W0.double(), G.double(), Cm.double()
+    f0 = s * (float((W0d * (W0d @ Gd - 2.0 * Cd)).sum()) + float(vv))
+    P = _GramProblem(G, R, s, f0, W0)
+    D0 = torch.zeros(out_f * in_f, device=dev, dtype=F32)
+    lbfgs_minimize(P, D0, iters)
+    Wn = W0.clone()
+    ops.vec_axpby(Wn.view(-1), P.best_D, 1.0, 1.0)
+    return Wn
+
+
+def update_quasi_newton(K_target, V_target, W, iters, device='cuda'):
+    """Reference signature (gradient_fusion.py:38): K [n,in], V [n,out], W [out,in] (or 1x1-conv 4-D) -> Wnew."""
+    shape = W.shape
+    W2 = W.detach().reshape(shape[0], -1)
+    if K_target.ndim == 4:                                     # 1x1 conv features [n, in, h, w] (:66-68)
+        K_target = K_target.permute(0, 2, 3, 1).reshape(-1, K_target.shape[1])
+        V_target = V_target.permute(0, 2, 3, 1).reshape(-1, V_target.shape[1])
+    K = K_target.detach().to(device, F32).contiguous()
+    V = V_target.detach().to(device, F32).contiguous()
+    n, d_in = K.shape
+    G = torch.empty(d_in, d_in, device=device, dtype=F32)
+    Cm = torch.empty(V.shape[1], d_in, device=device, dtype=F32)
+    ops.gram_small(K, G)
+    ops.atb_small(V, K, Cm)
+    scal, scratch = torch.zeros(1, device=device), torch.empty(256, device=device)
+    ops.vec_dot(V.view(-1), V.view(-1), scal, scratch)
+    Wn = solve_from_gram(G, Cm, scal.item(), n, W2, iters)
+    return Wn.reshape(shape).cpu()
+
+
+def merge_lora_into_weight(original_state_dict, lora_state_dict, modification_layer_names, model_type, alpha, device):
+    """W' = W + alpha * up @ down for every listed layer that has a LoRA pair (gradient_fusion.py:99-143), one
+    batched kernel launch for all layers."""
+    assert model_type in ['unet', 'text_encoder']
+    subs = (('q_proj', 'k_proj', 'v_proj', 'out_proj', 'fc1', 'fc2') if model_type == 'text_encoder' else
+            ('to_q', 'to_k', 'to_v', 'to_out.0', 'ff.net.0.proj', 'ff.net.2', 'proj_out', 'proj_in'))
+    new_sd = {k: v.clone() for k, v in original_state_dict.items()}
+    rows, keep = [], []
+    for k in modification_layer_names:
+        down_name = k
+        for sname in subs:
+            down_name = down_name.replace(f'{sname}.weight', f'{sname}.lora_down.weight')
+        up_name = down_name.replace('lora_down', 'lora_up')
+        if up_name not in lora_state_dict:
+            continue
+        Wd = new_sd[k].to(device, F32).contiguous()
+        dn = lora_state_dict[down_name].to(device, F32).contiguous()
+        up = lora_state_dict[up_name].to(device, F32).contiguous()
+        out_f, rank = up.shape[0], dn.shape[0]
+        rows.append([Wd.data_ptr(), dn.data_ptr(), up.data_ptr(), out_f, Wd.numel() // out_f, rank])
+        keep.append((k, Wd, dn, up))
+    if rows:
+        table = torch.tensor(rows, dtype=torch.int64, device=device)
+        ops.lora_merge(table, len(rows), float(alpha))
+        for k, Wd, _, _ in keep:
+            new_sd[k] = Wd.to(original_state_dict[k].dtype).reshape(original_state_dict[k].shape)
+    return new_sd
+
+
+def _merged(W0, down, up, alpha, device):
+    """W0 + alpha * up @ down through the batched merge kernel."""
+    Wc = W0.to(device, F32).clone().contiguous()
+    dn = down.to(device, F32).reshape(down.shape[0], -1).contiguous()
+    u = up.to(device, F32).reshape(up.shape[0], -1).contiguous()
+    table = torch.tensor([[Wc.data_ptr(), dn.data_ptr(), u.data_ptr(), u.shape[0], dn.shape[1], dn.shape[0]]],
+                         dtype=torch.int64, device=device)
+    ops.lora_merge(table, 1, float(alpha))
+    torch.cuda.current_stream().synchronize()      # dn / u are temporaries of this call
+    return Wc
+
+
+def merge_kv_in_cross_attention(unet_state_dict, cross_kv_layer_names, text_features, unet_crosskv_list, alphas,
+                                optimize_iters, device='cuda'):
+    """Cross-attention K/V fusion (gradient_fusion.py:325-457).  text_features[c][layer_idx] = CLIP features of
+    concept c at its concept-token (+EOS) positions [n_pos, 768] (gradient_fusion.py:182-199; CLIP runs upstream).
+    cross_kv_layer_names: [(layer_idx, 'down_blocks....attn2.to_k.weight'), ...] in the reference's order."""
+    new_w = {}
+    for layer_idx, name in cross_kv_layer_names:
+        W0 = unet_state_dict[name].to(device, F32)
+        d_in = W0.shape[1]
+        G = torch.zeros(d_in, d_in, device=device)
+        Cm = torch.zeros(W0.shape[0], d_in, device=device)
+        vv, n = 0.0, 0
+        dn_name = name.replace('to_k.weight', 'to_k.lora_down.weight').replace('to_v.weight', 'to_v.lora_down.weight')
+        for c, tuned in enumerate(unet_crosskv_list):
+            X = text_features[c][layer_idx].to(device, F32).contiguous()
+            Wc = _merged(W0, tuned[dn_name], tuned[dn_name.replace('lora_down', 'lora_up')], alphas[c], device)  # :403-409
+            Gc = torch.empty(d_in, d_in, device=device)
+            ops.gram_small(X, Gc)
+            WG = torch.empty_like(Cm)
+            ops.sgemm_nn(Wc.contiguous(), Gc, WG)
+            ops.vec_axpby(G.view(-1), Gc.view(-1), 1.0, 1.0)
+            ops.vec_axpby(Cm.view(-1), WG.view(-1), 1.0, 1.0)
+            vv += float((Wc.double() * WG.double()).sum())
+            n += X.shape[0]
+        new_w[name] = solve_from_gram(G, Cm, vv, n, W0, optimize_iters).cpu()
+    return new_w
+
+
+class GramRecorder:
+    """Engine-side replacement of the reference's forward hooks (gradient_fusion.py:146-167): instead of copying
+    every (input, output - bias) pair to host RAM, accumulate G += X^T X per recorded GEMM input on the tensor
+    cores (transpose -> tcgen05 GEMM with fp32 accumulate output)."""
+
+    def __init__(self, device):
+        self.dev, self.G, self.rows, self._xt = device, {}, {}, {}
+
+    def __call__(self, key, A, M, C):
+        G = self.G.get(key)
+        first = G is None
+        if first:
+            G = self.G[key] = torch.zeros(C, C, device=self.dev, dtype=F32)
+            self.rows[key] = 0
+        xt = self._xt.get((C, M))
+        if xt is None:
+            xt = self._xt[(C, M)] = torch.empty(C, M, device=self.dev, dtype=torch.bfloat16)
+        ops.transpose_bf16(A, xt, rows=M, C=C, ldx=A.stride(0))
+        ops.gemm(xt, xt, G, out_f32=True, accumulate=True)
+        self.rows[key] += M
+
+
+SPATIAL_KEYS = (('attn1.to_q', 'attn1.in'), ('attn1.to_k', 'attn1.in'), ('attn1.to_v', 'attn1.in'),
+                ('attn1.to_out.0', 'attn1.to_out.0'), ('attn2.to_q', 'attn2.to_q'), ('attn2.to_out.0', 'attn2.to_out.0'))
+
+
+def merge_spatial_attention(unet_state_dict, unet_spatial_attn_list, alphas, concept_embeds, optimize_iters,
+                            latent_hw=(64, 64), num_inference_steps=20, seed=0, device='cuda', block_out=None,
+                            layers=None):
+    """Spatial-attention fusion (gradient_fusion.py:627-747).  concept_embeds[c] = layer-wise prompt embeddings
+    [1,16,77,768] of 'photo of a <concept c>' (CLIP runs upstream).  For every concept: merge its LoRA, run the
+    20-step DPM-Solver++ sampling (batch 1, no CFG, all steps recorded, :579-624) on the engine with the Gram
+    recorder, then solve every LoRA'd layer from the accumulated Gram matrices."""
+    from mos_b200.engine import UNetEngine, ehs_to_layer_major
+    from mos_b200.scheduler import DPMSolverPP2M
+    H, Wd = latent_hw
+    kw = {}
+    if block_out is not None:
+        kw = dict(block_out=block_out, layers=layers)
+    grams, merged_w = [], []
+    for c, tuned in enumerate(unet_spatial_attn_list):
+        eng = UNetEngine(unet_state_dict, 1, H, Wd, lora=tuned, lora_alpha=alphas[c], merge_lora=True, device=device,
+                         use_graph=False, **kw)
+        rec = GramRecorder(device)
+        eng.gram_rec = rec
+        nx = len(eng.xattn_names)
+        sched = DPMSolverPP2M()
+        sched.set_timesteps(num_inference_steps)
+        g = torch.Generator(device='cpu').manual_seed(seed + c)
+        latents = torch.randn(1, 4, H, Wd, generator=g).to(device)
+        x0_prev = torch.zeros_like(latents)
+        eng.in_ehs.copy_(ehs_to_layer_major(concept_embeds[c].to(device), nx))
+        eng.in_latents.copy_(latents)
+        for i, t in enumerate(sched.timesteps):
+            eng.in_t.fill_(float(t))
+            eng.run()
+            ops.cfg_dpmpp_step(eng.out_eps, latents, x0_prev, eng.in_latents.view(-1), cfg=False, guidance=1.0,
+                               coef=sched.coefficients(i))
+        grams.append(rec)
+        merged_w.append(tuned)
+        eng.gram_rec = None
+    names = sorted({k.replace('.lora_down', '').replace('.lora_up', '') for t in unet_spatial_attn_list for k in t})
+    new_w = {}
+    for name in names:                                          # e.g. '...attn1.to_q.weight'
+        mod = name[:-len('.weight')]
+        tb, leaf = mod.rsplit('.attn', 1)
+        leaf = 'attn' + leaf
+        rec_key = tb + '.' + dict(SPATIAL_KEYS)[leaf]
+        W0 = unet_state_dict[name].to(device, F32).reshape(unet_state_dict[name].shape[0], -1)
+        d_in = W0.shape[1]
+        G = torch.zeros(d_in, d_in, device=device)
+        Cm = torch.zeros(W0.shape[0], d_in, device=device)
+        vv, n = 0.0, 0
+        for c, tuned in enumerate(unet_spatial_attn_list):
+            Gc = grams[c].G[rec_key]
+            Wc = _merged(W0, tuned[mod + '.lora_down.weight'], tuned[mod + '.lora_up.weight'], alphas[c], device) \
+                if (mod + '.lora_down.weight') in tuned else W0
+            WG = torch.empty_like(Cm)
+            ops.sgemm_nn(Wc.contiguous(), Gc, WG)
+            ops.vec_axpby(G.view(-1), Gc.view(-1), 1.0, 1.0)
+            ops.vec_axpby(Cm.view(-1), WG.view(-1), 1.0, 1.0)
+            vv += float((Wc.double() * WG.double()).sum())
+            n += grams[c].rows[rec_key]
+        new_w[name] = solve_from_gram(G, Cm, vv, n, W0, optimize_iters).reshape(unet_state_dict[name].shape).cpu()
+    return new_w

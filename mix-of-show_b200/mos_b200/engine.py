@@ -67,6 +67,7 @@ class UNetEngine:
         self.adapters = None    # list of 4 bf16 NHWC tensors [B*HW_l, C_l]
         self.region_hw = None   # (height, width) in pixels passed by the regional pipeline
         self.controller = None
+        self.gram_rec = None    # gradient fusion: callable(key, A [M,C] bf16 view, M, C) fed with recorded GEMM inputs
         self.skip = set()       # profiling aid: op families not launched ('gemm','splitk','attn','gn','ln','misc')
 
     # ------------------------------------------------------------------------------------------ packing
@@ -352,6 +353,8 @@ class UNetEngine:
         ln = self.buf('tr_ln', (M, C))
         # --- attn1 (self)
         self.layernorm(t0, tb + '.norm1', ln, M=M, C=C)
+        if self.gram_rec is not None:
+            self.gram_rec(tb + '.attn1.in', ln, M, C)
         Q = self.buf('Q', (BH, N, _r(d, 64)), zero=True)
         K = self.buf('K', (BH, N, _r(d, 64)), zero=True)
         Vt = self.buf('Vt', (BH, _r(d, 16), _r(N, 8)), zero=True)
@@ -362,10 +365,14 @@ class UNetEngine:
         if 'attn' not in self.skip:
             ops.attention(Q, K, Vt, ao.view(B, N, C), batch=B, heads=Hh, head_dim=d, nq=N, nk=N)
         self.launches += 1
+        if self.gram_rec is not None:
+            self.gram_rec(tb + '.attn1.to_out.0', ao, M, C)
         t1 = self.buf('tr_t1', (M, C))
         self.gemm(ao, self.w[tb + '.attn1.out'], t1, M=M, residual=t0)
         # --- attn2 (cross, layer-wise text embedding: edlora.py:129-131)
         self.layernorm(t1, tb + '.norm2', ln, M=M, C=C)
+        if self.gram_rec is not None:
+            self.gram_rec(tb + '.attn2.to_q', ln, M, C)
         self.gemm(ln, self.w[tb + '.attn2.q'], None, M=M, heads=self._heads([Q], [MOS_SEG_ROWS], [N], C, N))
         Kc, Vc = self._cross_kv(tb, self.in_ehs[xidx], C, '')
         probs = None
@@ -377,6 +384,8 @@ class UNetEngine:
         self.launches += 1
         if self.regions:
             self._region_rewrite(tb, Q, ao, h, w, C, xidx)
+        if self.gram_rec is not None:
+            self.gram_rec(tb + '.attn2.to_out.0', ao, M, C)
         t2 = self.buf('tr_t2', (M, C))
         self.gemm(ao, self.w[tb + '.attn2.out'], t2, M=M, residual=t1)
         # --- feed-forward (GEGLU fused in the first GEMM's epilogue)

@@ -20,7 +20,7 @@ def _is_bf16(t):
 
 def gemm(A, W, out=None, *, bias=None, bias_batch=None, rows_per_batch=0, residual=None, geglu=False,
          lora_down=None, lora_up=None, lora_seg=0, conv=None, splits=1, partial=None, stages=0,
-         out_f32=False, heads=None, M=None, lda=None, ldc=None, ldr=None, bias_batch_ld=0):
+         out_f32=False, heads=None, M=None, lda=None, ldc=None, ldr=None, bias_batch_ld=0, accumulate=False):
     """out = epilogue(A @ W^T [+ LoRA]).
 
     A: bf16 [M, K] (row pitch lda) or, with conv=(B, H, Wd, C), the NHWC activation [B, H, Wd, C].
@@ -70,6 +70,7 @@ def gemm(A, W, out=None, *, bias=None, bias_batch=None, rows_per_batch=0, residu
         a.tokens_per_batch = heads['tokens_per_batch']
     else:
         a.out_mode = MOS_OUT_F32 if out_f32 else MOS_OUT_BF16
+        a.accumulate = 1 if accumulate else 0
         a.out = ptr(out)
         if out is not None:
             a.ldc = out.stride(0) if ldc is None else ldc
@@ -189,3 +190,66 @@ def region_combine(glob, region_ptrs_dev, boxes, out, *, B, FH, FW, C, ld):
                                         ctypes.c_int32(FH), ctypes.c_int32(FW), ctypes.c_int32(C), ctypes.c_int64(ld),
                                         ptr(out), _s()), 'mos_region_combine')
     return out
+
+
+# ----------------------------------------------------------------------------------------------- gradient fusion
+def transpose_bf16(x, out, *, rows, C, ldx=None, ldo=None):
+    check(_lib.lib().mos_transpose_bf16(ptr(x), ctypes.c_int64(x.stride(0) if ldx is None else ldx),
+                                        ctypes.c_int32(rows), ctypes.c_int32(C), ptr(out),
+                                        ctypes.c_int64(out.stride(0) if ldo is None else ldo), _s()),
+          'mos_transpose_bf16')
+    return out
+
+
+def gram_small(X, G, accumulate=False):
+    n, d = X.shape
+    check(_lib.lib().mos_gram_small(ptr(X), ctypes.c_int32(n), ctypes.c_int32(d), ptr(G),
+                                    ctypes.c_int32(int(accumulate)), _s()), 'mos_gram_small')
+    return G
+
+
+def atb_small(X, Y, out, accumulate=False):
+    n, dx = X.shape
+    check(_lib.lib().mos_atb_small(ptr(X), ptr(Y), ctypes.c_int32(n), ctypes.c_int32(dx), ctypes.c_int32(Y.shape[1]),
+                                   ptr(out), ctypes.c_int32(int(accumulate)), _s()), 'mos_atb_small')
+    return out
+
+
+def sgemm_nn(A, B, C, alpha=1.0, beta=0.0):
+    M, K = A.shape
+    N = B.shape[1]
+    check(_lib.lib().mos_sgemm_nn(ptr(A), ptr(B), ptr(C), ctypes.c_int32(M), ctypes.c_int32(N), ctypes.c_int32(K),
+                                  ctypes.c_float(alpha), ctypes.c_float(beta), _s()), 'mos_sgemm_nn')
+    return C
+
+
+def ls_grad_loss(W, Y, Cm, s, f0, grad, loss, scratch):
+    """grad = 2 s (Y - Cm); loss = s <W, Y - 2 Cm> + f0"""
+    check(_lib.lib().mos_ls_grad_loss(ptr(W), ptr(Y), ptr(Cm), ctypes.c_int64(W.numel()), ctypes.c_float(s),
+                                      ctypes.c_float(f0), ptr(grad), ptr(loss), ptr(scratch), _s()),
+          'mos_ls_grad_loss')
+
+
+def vec_dot(a, b, out, scratch):
+    check(_lib.lib().mos_vec_dot(ptr(a), ptr(b), ctypes.c_int64(a.numel()), ptr(out), ptr(scratch), _s()),
+          'mos_vec_dot')
+
+
+def vec_asum(a, out, scratch):
+    check(_lib.lib().mos_vec_asum(ptr(a), ctypes.c_int64(a.numel()), ptr(out), ptr(scratch), _s()), 'mos_vec_asum')
+
+
+def vec_absmax(a, out, scratch, scale=1.0):
+    check(_lib.lib().mos_vec_absmax(ptr(a), ctypes.c_int64(a.numel()), ctypes.c_float(scale), ptr(out), ptr(scratch),
+                                    _s()), 'mos_vec_absmax')
+
+
+def vec_axpby(y, x, alpha, beta=1.0):
+    check(_lib.lib().mos_vec_axpby(ptr(y), ptr(x), ctypes.c_float(alpha), ctypes.c_float(beta),
+                                   ctypes.c_int64(y.numel()), _s()), 'mos_vec_axpby')
+    return y
+
+
+def lora_merge(table_dev, n_layers, alpha):
+    check(_lib.lib().mos_lora_merge(ptr(table_dev), ctypes.c_int32(n_layers), ctypes.c_float(alpha), _s()),
+          'mos_lora_merge')

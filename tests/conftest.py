@@ -5,7 +5,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, 'mix-of-show_b200')
-for p in (ROOT, PKG):
+for p in (ROOT, PKG):  # PKG also exposes the top-level gradient_fusion module
     if p not in sys.path:
         sys.path.insert(0, p)
 
