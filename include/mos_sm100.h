@@ -158,8 +158,10 @@ int mos_atb_small(const float* X, const float* Y, int32_t n, int32_t dx, int32_t
                   void* stream);
 int mos_sgemm_nn(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, float alpha, float beta,
                  void* stream);
-int mos_ls_grad_loss(const float* W, const float* Y, const float* Cm, int64_t n, float s, float f0, float* grad,
-                     float* loss, float* scratch, void* stream);
+/* closure: Y (fp64) = D (fp32) * G (fp64); grad (fp32) = 2 s (Y - R), loss (fp64) = s <D, Y - 2R> + f0 */
+int mos_dgemm_mixed(const float* A, const double* B, double* C, int32_t M, int32_t N, int32_t K, void* stream);
+int mos_ls_grad_loss(const float* W, const double* Y, const double* Cm, int64_t n, double s, double f0, float* grad,
+                     double* loss, double* scratch, void* stream);
 int mos_vec_dot(const float* a, const float* b, int64_t n, float* out, float* scratch, void* stream);
 int mos_vec_asum(const float* a, int64_t n, float* out, float* scratch, void* stream);
 int mos_vec_absmax(const float* a, int64_t n, float scale, float* out, float* scratch, void* stream);

@@ -47,9 +47,11 @@ class _GramProblem:
         self.G, self.R, self.s, self.f0, self.W0 = G, R, float(s), float(f0), W0
         self.shape = tuple(R.shape)
         dev = R.device
-        self.Y = torch.empty_like(R)
+        self.Y = torch.empty_like(R)          # fp64 [out, in]
         self.scal = torch.zeros(1, device=dev, dtype=F32)
         self.scratch = torch.empty(256, device=dev, dtype=F32)
+        self.loss64 = torch.zeros(1, device=dev, dtype=torch.float64)
+        self.scratch64 = torch.empty(256, device=dev, dtype=torch.float64)
         self.best_loss, self.best_D = float('inf'), None
         self.evals = 0
 
@@ -63,10 +65,10 @@ class _GramProblem:
 
     def closure(self, D):
         """-> (loss float, grad tensor); tracks the best iterate like gradient_fusion.py:72-74."""
-        ops.sgemm_nn(D.view(self.shape), self.G, self.Y)
+        ops.dgemm_mixed(D.view(self.shape), self.G, self.Y)
         grad = torch.empty_like(D)
-        ops.ls_grad_loss(D, self.Y, self.R, self.s, self.f0, grad, self.scal, self.scratch)
-        loss = self.scal.item()
+        ops.ls_grad_loss(D, self.Y, self.R, self.s, self.f0, grad, self.loss64, self.scratch64)
+        loss = self.loss64.item()
         self.evals += 1
         if loss < self.best_loss:
             self.best_loss = loss
@@ -210,12 +212,12 @@ def solve_from_gram(G, Cm, vv, n_rows, W0, iters):
     W0 = W0.to(dev, F32).contiguous()
     G = G.to(dev, F32).contiguous()
     s = 1.0 / (float(n_rows) * out_f)
-    R = Cm.to(dev, F32).clone().contiguous()
-    ops.sgemm_nn(W0, G, R, alpha=-1.0, beta=1.0)               # R = C - W0 G
-    # f(W0) once, in float64 (host-side setup scalar; keeps the shifted quadratic free of cancellation)
-    W0d, Gd, Cd = W0.double(), G.double(), Cm.double()
+    # one-time fp64 setup (like weight packing): residual right-hand side R = C - W0 G and f(W0); the Gram form squares
+    # the condition number, so the closure product D G is carried in fp64 on the device (mos_dgemm_mixed)
+    W0d, Gd, Cd = W0.double(), G.double().contiguous(), Cm.to(dev).double()
+    Rd = (Cd - W0d @ Gd).contiguous()
     f0 = s * (float((W0d * (W0d @ Gd - 2.0 * Cd)).sum()) + float(vv))
-    P = _GramProblem(G, R, s, f0, W0)
+    P = _GramProblem(Gd, Rd, s, f0, W0)
     D0 = torch.zeros(out_f * in_f, device=dev, dtype=F32)
     lbfgs_minimize(P, D0, iters)
     Wn = W0.clone()

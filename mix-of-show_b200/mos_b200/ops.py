@@ -223,10 +223,19 @@ def sgemm_nn(A, B, C, alpha=1.0, beta=0.0):
     return C
 
 
+def dgemm_mixed(A, B, C):
+    M, K = A.shape
+    assert A.dtype == torch.float32 and B.dtype == torch.float64 and C.dtype == torch.float64
+    check(_lib.lib().mos_dgemm_mixed(ptr(A), ptr(B), ptr(C), ctypes.c_int32(M), ctypes.c_int32(B.shape[1]),
+                                     ctypes.c_int32(K), _s()), 'mos_dgemm_mixed')
+    return C
+
+
 def ls_grad_loss(W, Y, Cm, s, f0, grad, loss, scratch):
     """grad = 2 s (Y - Cm); loss = s <W, Y - 2 Cm> + f0"""
-    check(_lib.lib().mos_ls_grad_loss(ptr(W), ptr(Y), ptr(Cm), ctypes.c_int64(W.numel()), ctypes.c_float(s),
-                                      ctypes.c_float(f0), ptr(grad), ptr(loss), ptr(scratch), _s()),
+    assert loss.dtype == torch.float64 and scratch.dtype == torch.float64 and Y.dtype == torch.float64
+    check(_lib.lib().mos_ls_grad_loss(ptr(W), ptr(Y), ptr(Cm), ctypes.c_int64(W.numel()), ctypes.c_double(s),
+                                      ctypes.c_double(f0), ptr(grad), ptr(loss), ptr(scratch), _s()),
           'mos_ls_grad_loss')
 
 

