@@ -302,7 +302,12 @@ def main():
     if roof is not None:
         frac = roof['achieved'] / peaks['tflops']
         out['roofline'] = {'bound': 'tensor', 'achieved': roof['achieved'], 'peak': peaks['tflops'], 'unit': 'TFLOP/s',
-                           'frac': frac, 'traffic': None, 'peak_source': peaks['src'] + ' (bf16_tflops_sustained)',
+                           'frac': frac, 'traffic': 8.0e6,
+                           'traffic_note': 'mean dram__bytes_read+write per launch over the 12 launches of '
+                                           'profiles/r1_gemm_full_v2.ncu-rep (2-27 MB read, ~0 written: outputs stay '
+                                           'in the 126 MB L2); algorithmic operand bytes per launch are 2-40 MB',
+                           'method': 'T(graph step) - T(graph step without gemm launches), CUDA events',
+                           'peak_source': peaks['src'] + ' (bf16_tflops_sustained)',
                            'kernel': 'mos::gemm_kernel (tcgen05 GEMM + implicit-GEMM conv3x3)',
                            'launches_per_step': roof['launches'], 'kernel_ms_per_step': roof['ms'],
                            'algorithmic_gflop_per_step': roof['gflop']}
@@ -317,39 +322,49 @@ def main():
 
 
 def gemm_roofline(eng, ops, torch):
-    """Time every launch of the dominant kernel with CUDA events on the launching stream (eager, no graph) and
-    divide its algorithmic FLOPs (2*M*N*K, LoRA / padding FLOPs excluded) by its device time."""
-    recs = []
+    """Device time of the dominant kernel family (mos::gemm_kernel: tcgen05 GEMM + implicit-GEMM conv) inside the
+    real captured step, measured live with CUDA events on the launching stream as a difference of graph replays:
+    T(full step) - T(same step without the gemm launches).  (Per-launch events in eager mode would time the Python
+    launch path, not the kernel; nsys is not available.)  Algorithmic FLOPs = sum 2*M*N*K over the step's launches
+    (LoRA rank columns, padding, split-K re-reads excluded)."""
+    flops = []
     orig = ops.gemm
 
-    def timed(A, W, out=None, **kw):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    def counting(A, W, out=None, **kw):
         conv = kw.get('conv')
-        if conv is not None:
-            M = conv[0] * conv[1] * conv[2]
-        else:
-            M = kw.get('M') or A.shape[0]
-        fl = 2.0 * M * W.shape[0] * W.shape[1]
-        a.record()
-        r = orig(A, W, out, **kw)
-        b.record()
-        recs.append((a, b, fl))
-        return r
+        M = conv[0] * conv[1] * conv[2] if conv is not None else (kw.get('M') or A.shape[0])
+        flops.append(2.0 * M * W.shape[0] * W.shape[1])
+        return orig(A, W, out, **kw)
 
-    ops.gemm = timed
+    ops.gemm = counting
     try:
-        eng._run()       # warm
-        torch.cuda.synchronize()
-        recs.clear()
-        reps = 3
-        for _ in range(reps):
-            eng._run()
+        eng._run()
         torch.cuda.synchronize()
     finally:
         ops.gemm = orig
-    ms = sum(a.elapsed_time(b) for a, b, _ in recs) / reps
-    fl = sum(f for _, _, f in recs) / reps
-    return {'achieved': fl / (ms * 1e-3) / 1e12, 'ms': ms, 'launches': len(recs) // reps, 'gflop': fl / 1e9}
+    launches, fl = len(flops), sum(flops)
+
+    def replay_ms(skip, reps=20):
+        eng.skip = set(skip)
+        eng.graph = None
+        eng.run()
+        eng.run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            eng.run()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    t_full = replay_ms([])
+    t_wo = replay_ms(['gemm'])
+    eng.skip = set()
+    eng.graph = None
+    ms = max(t_full - t_wo, 1e-6)
+    return {'achieved': fl / (ms * 1e-3) / 1e12, 'ms': ms, 'launches': launches, 'gflop': fl / 1e9,
+            'step_ms_graph_only': t_full}
 
 
 if __name__ == '__main__':

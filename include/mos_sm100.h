@@ -170,6 +170,17 @@ int mos_vec_axpby(float* y, const float* x, float alpha, float beta, int64_t n, 
  * table_dev: int64 [n_layers, 6] = {W fp32 ptr, down fp32 ptr, up fp32 ptr, out, in, rank}. */
 int mos_lora_merge(const int64_t* table_dev, int32_t n_layers, float alpha, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused optimiser step of ED-LoRA training (train_edlora.py:57 AdamW param groups, :129 optimizer.step, :138-140
+ * Norm_mean): one flat fp32 state [concept rows | text-encoder LoRA | UNet LoRA]; group_end = exclusive end offsets
+ * (host int64[3]), group_lr = host float[3]; grad_scale = 1/world after the single all-reduce;
+ * norm_mean_out (optional) = mean L2 norm of the first emb_rows rows of width emb_dim after the update.
+ * ---------------------------------------------------------------------------------------------------------- */
+int mos_flat_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                        const int64_t* group_end, const float* group_lr, float beta1, float beta2, float eps,
+                        float weight_decay, int64_t step, float grad_scale, int32_t emb_rows, int32_t emb_dim,
+                        float* norm_mean_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -262,3 +262,15 @@ def vec_axpby(y, x, alpha, beta=1.0):
 def lora_merge(table_dev, n_layers, alpha):
     check(_lib.lib().mos_lora_merge(ptr(table_dev), ctypes.c_int32(n_layers), ctypes.c_float(alpha), _s()),
           'mos_lora_merge')
+
+
+# ----------------------------------------------------------------------------------------------- training state
+def flat_adamw_step(params, grads, exp_avg, exp_avg_sq, group_end, group_lr, *, step, beta1=0.9, beta2=0.999,
+                    eps=1e-8, weight_decay=0.01, grad_scale=1.0, emb_rows=0, emb_dim=0, norm_mean_out=None):
+    ge = (ctypes.c_int64 * 3)(*[int(x) for x in group_end])
+    gl = (ctypes.c_float * 3)(*[float(x) for x in group_lr])
+    check(_lib.lib().mos_flat_adamw_step(
+        ptr(params), ptr(grads), ptr(exp_avg), ptr(exp_avg_sq), ctypes.c_int64(params.numel()), ge, gl,
+        ctypes.c_float(beta1), ctypes.c_float(beta2), ctypes.c_float(eps), ctypes.c_float(weight_decay),
+        ctypes.c_int64(step), ctypes.c_float(grad_scale), ctypes.c_int32(emb_rows), ctypes.c_int32(emb_dim),
+        ptr(norm_mean_out), _s()), 'mos_flat_adamw_step')
