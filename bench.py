@@ -270,6 +270,7 @@ def main():
     d2h = h_out.numel() * 4
 
     # ---------------- per-kernel roofline of the dominant kernel (tcgen05 GEMM / implicit-GEMM conv), eager mode
+    used_graph = eng.graph is not None
     roof = None
     if rank == 0:
         roof = gemm_roofline(eng, ops, torch)
@@ -292,7 +293,7 @@ def main():
         'dtype': 'bf16', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'parallelism': f'replicas x{world} (independent images per GPU, no data-path '
                    'collective; SURVEY.md 8e)', 'l2': 'inputs larger than L2: 1.72 GB of bf16 weights streamed per '
-                   'step vs 126 MB L2, no explicit flush', 'cuda_graph': bool(eng.graph is not None)},
+                   'step vs 126 MB L2, no explicit flush', 'cuda_graph': bool(used_graph)},
         'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': e2e_ms / args.steps},
