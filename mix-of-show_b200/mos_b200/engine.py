@@ -67,6 +67,7 @@ class UNetEngine:
         self.adapters = None    # list of 4 bf16 NHWC tensors [B*HW_l, C_l]
         self.region_hw = None   # (height, width) in pixels passed by the regional pipeline
         self.controller = None
+        self.side = None        # side CUDA stream (created lazily on the device) for independent branches
         self.gram_rec = None    # gradient fusion: callable(key, A [M,C] bf16 view, M, C) fed with recorded GEMM inputs
         self.skip = set()       # profiling aid: op families not launched ('gemm','splitk','attn','gn','ln','misc')
 
@@ -306,6 +307,16 @@ class UNetEngine:
         B = self.B
         HW = h * w
         M = B * HW
+        # the 1x1 shortcut only needs x: it runs on the side stream, concurrently with norm1 -> conv1 -> norm2
+        res = x
+        has_sc = name + '.conv_shortcut' in self.w
+        if has_sc:
+            main = torch.cuda.current_stream()
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side):
+                sc = self.buf('rn_sc', (M, cout))
+                self.gemm(x, self.w[name + '.conv_shortcut'], sc, M=M, lda=x.stride(0))
+            res = sc
         n1 = self.buf('rn_n', (M, cin))
         self.groupnorm(x, name + '.norm1', n1, HW=HW, C=cin, eps=1e-5, silu=True)
         h1 = self.buf('rn_h', (M, cout))
@@ -313,12 +324,8 @@ class UNetEngine:
         self.gemm(n1, self.w[name + '.conv1'], h1, M=M, conv=(B, h, w, cin), bias_batch=tb, rows_per_batch=HW)
         n2 = self.buf('rn_n2', (M, cout))
         self.groupnorm(h1, name + '.norm2', n2, HW=HW, C=cout, eps=1e-5, silu=True)
-        if name + '.conv_shortcut' in self.w:
-            sc = self.buf('rn_sc', (M, cout))
-            self.gemm(x, self.w[name + '.conv_shortcut'], sc, M=M, lda=x.stride(0))
-            res = sc
-        else:
-            res = x
+        if has_sc:
+            torch.cuda.current_stream().wait_stream(self.side)
         self.gemm(n2, self.w[name + '.conv2'], out, M=M, conv=(B, h, w, cout), residual=res)
         return out
 
@@ -374,7 +381,10 @@ class UNetEngine:
         if self.gram_rec is not None:
             self.gram_rec(tb + '.attn2.to_q', ln, M, C)
         self.gemm(ln, self.w[tb + '.attn2.q'], None, M=M, heads=self._heads([Q], [MOS_SEG_ROWS], [N], C, N))
-        Kc, Vc = self._cross_kv(tb, self.in_ehs[xidx], C, '')
+        if not self._kv_joined:     # the 16 text K/V projections were issued on the side stream at step start
+            torch.cuda.current_stream().wait_stream(self.side)
+            self._kv_joined = True
+        Kc, Vc = self.kv[xidx]
         probs = None
         if self.emit_probs:
             probs = self.buf(f'probs{xidx}', (BH, N, self.n_text), torch.float32)
@@ -440,16 +450,42 @@ class UNetEngine:
         ch, cs = self.cat_ch[k]
         return self.cat[k][:, ch:ch + cs]
 
+    def _xattn_channels(self):
+        nb = len(self.block_out)
+        ch = []
+        for i in range(nb - 1):
+            ch += [self.block_out[i]] * self.layers
+        ch.append(self.block_out[-1])
+        rev = list(reversed(self.block_out))
+        for i in range(1, nb):
+            ch += [rev[i]] * (self.layers + 1)
+        return ch
+
     def _run(self):
         B, H, W = self.B, self.H, self.W
         nb = len(self.block_out)
         self.launches = 0
-        self._time()
+        # side stream: timestep MLP + all 22 time_emb_proj, then the 16 text K/V projections (they depend only on the
+        # prompt embeddings), concurrently with conv_in and the first blocks on the main stream
+        main = torch.cuda.current_stream()
+        if self.side is None:
+            self.side = torch.cuda.Stream(device=self.dev)
+            self.ev_time = torch.cuda.Event()
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            self._time()
+            self.ev_time.record(self.side)
+            self.kv = {}
+            for xidx, (an, C) in enumerate(zip(self.xattn_names, self._xattn_channels())):
+                tbn = an[:-len('.attn2')]
+                self.kv[xidx] = self._cross_kv(tbn, self.in_ehs[xidx], C, f'_x{xidx}')
+        self._kv_joined = False
         si = 0
         x = self._skip_slot(si)
         ops.conv_in(self.in_latents, self.w['conv_in'][0], self.w['conv_in'][1], x, ldy=x.stride(0))
         self.launches += 1
         si += 1
+        main.wait_event(self.ev_time)      # resnets need the time_emb_proj table
         h, w, cin = H, W, self.block_out[0]
         xi = 0
         for i, c in enumerate(self.block_out):
