@@ -18,19 +18,21 @@
 
 namespace mos {
 
-template <int D>
+// WIDE: d = 160 cross-attention variant (nk <= 128): one 128-key tile, single-buffered, so that the probability maps of
+// the controller path come from a single kv tile at every head size.
+template <int D, bool WIDE = false>
 struct AttnCfg {
   static constexpr int KSTEPS = (D + 15) / 16;
   static constexpr int DP = ((D + 63) / 64) * 64;
   static constexpr int QCH = DP / 64;
   static constexpr int DV = ((D + 15) / 16) * 16;
-  static constexpr int BKV = D <= 80 ? 128 : 64;
+  static constexpr int BKV = (D <= 80 || WIDE) ? 128 : 64;
   static constexpr int KVCH = BKV / 64;
-  static constexpr int STAGES = 2;
+  static constexpr int STAGES = WIDE ? 1 : 2;
   // d = 40: single S / P buffers and 256 TMEM columns so that TWO CTAs share an SM (the softmax of one hides the
   // MMA / TMEM latency of the other); larger head sizes keep double buffering and one CTA per SM.
-  static constexpr int SB = D <= 40 ? 1 : 2;
-  static constexpr int PB = D <= 40 ? 1 : 2;
+  static constexpr int SB = (D <= 40 || WIDE) ? 1 : 2;
+  static constexpr int PB = (D <= 40 || WIDE) ? 1 : 2;
   static constexpr int MINB = D <= 40 ? 2 : 1;
   static constexpr int Q_BYTES = QCH * 128 * 128;
   static constexpr int K_BYTES = QCH * BKV * 128;
@@ -58,11 +60,11 @@ struct AttnDev {
   float* probs;  // optional [B*H, nq, nk] fp32 (single kv tile only)
 };
 
-template <int D>
-__global__ void __launch_bounds__(192, AttnCfg<D>::MINB)
+template <int D, bool WIDE>
+__global__ void __launch_bounds__(192, AttnCfg<D, WIDE>::MINB)
 attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
             const __grid_constant__ CUtensorMap tmV, const AttnDev p) {
-  using C = AttnCfg<D>;
+  using C = AttnCfg<D, WIDE>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -308,10 +310,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   }
 }
 
-template <int D>
+template <int D, bool WIDE>
 static int launch_attn(const void* Q, const void* K, const void* Vt, void* out, int64_t ldo, float* probs, int BH,
                        int heads, int nq, int nk, int nk8, float scale, cudaStream_t stream) {
-  using C = AttnCfg<D>;
+  using C = AttnCfg<D, WIDE>;
   CUtensorMap tmQ, tmK, tmV;
   {
     uint64_t dims[3] = {(uint64_t)C::DP, (uint64_t)nq, (uint64_t)BH};
@@ -344,11 +346,11 @@ static int launch_attn(const void* Q, const void* K, const void* Vt, void* out, 
   p.probs = probs;
   static bool configured = false;
   if (!configured) {
-    MOS_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    MOS_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel<D, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
   }
   dim3 grid((unsigned)ceil_div(nq, 128), (unsigned)BH);
-  MOS_CHECK_CUDA(launch_pdl(attn_kernel<D>, grid, dim3(192), (size_t)C::SMEM_BYTES, stream, tmQ, tmK, tmV, p));
+  MOS_CHECK_CUDA(launch_pdl(attn_kernel<D, WIDE>, grid, dim3(192), (size_t)C::SMEM_BYTES, stream, tmQ, tmK, tmV, p));
   return MOS_OK;
 }
 
@@ -365,11 +367,13 @@ extern "C" int mos_attention_fwd(const void* Q, const void* K, const void* Vt, v
   MOS_CHECK_ARG(nk8 >= nk && nk8 % 8 == 0, "mos_attention_fwd: nk8=%d must be >= nk=%d and a multiple of 8", nk8, nk);
   MOS_CHECK_ARG(ldo >= (int64_t)heads * head_dim && ldo % 8 == 0, "mos_attention_fwd: bad ldo");
   const int BH = batch * heads;
-  if (probs) MOS_CHECK_ARG(nk <= 128 && head_dim <= 80 || nk <= 64, "mos_attention_fwd: probs output needs a single kv tile");
+  if (probs) MOS_CHECK_ARG(nk <= 128, "mos_attention_fwd: probs output needs a single kv tile (nk <= 128)");
   switch (head_dim) {
-    case 40: return launch_attn<40>(Q, K, Vt, out, ldo, probs, BH, heads, nq, nk, nk8, scale, stream);
-    case 80: return launch_attn<80>(Q, K, Vt, out, ldo, probs, BH, heads, nq, nk, nk8, scale, stream);
-    case 160: return launch_attn<160>(Q, K, Vt, out, ldo, probs, BH, heads, nq, nk, nk8, scale, stream);
+    case 40: return launch_attn<40, false>(Q, K, Vt, out, ldo, probs, BH, heads, nq, nk, nk8, scale, stream);
+    case 80: return launch_attn<80, false>(Q, K, Vt, out, ldo, probs, BH, heads, nq, nk, nk8, scale, stream);
+    case 160:
+      if (nk <= 128) return launch_attn<160, true>(Q, K, Vt, out, ldo, probs, BH, heads, nq, nk, nk8, scale, stream);
+      return launch_attn<160, false>(Q, K, Vt, out, ldo, probs, BH, heads, nq, nk, nk8, scale, stream);
     default: return set_err(MOS_EUNSUPPORTED, "mos_attention_fwd: head_dim %d not in {40, 80, 160}", head_dim);
   }
 }

@@ -371,6 +371,294 @@ gn_fused_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int HW, int 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------- backward (training)
+// GroupNorm(+SiLU) backward for the ED-LoRA training step (trainer_edlora.py:237 reached through loss.backward()):
+// gamma / beta are frozen, so only dx is produced.   z = xhat*gamma + beta, y = act(z), dz = dy * act'(z),
+//   dx = rstd * (dz*gamma - mean_g(dz*gamma) - xhat * mean_g(dz*gamma*xhat))        (means over the group's HW*cpg)
+__device__ __forceinline__ float silu_grad(float z) {
+  const float sg = 1.0f / (1.0f + __expf(-z));
+  return sg * (1.0f + z * (1.0f - sg));
+}
+
+__device__ __forceinline__ void gn_load_stats(const float* __restrict__ partial, int nchunks, int b, int HW, int cpg,
+                                              float eps, float* mean, float* rstd) {
+  if (threadIdx.x < GN_GROUPS * 4) {
+    const int g = threadIdx.x >> 2, sub = threadIdx.x & 3;
+    float s = 0.f, q = 0.f;
+    for (int c = sub; c < nchunks; c += 4) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(partial + (((long long)b * nchunks + c) * GN_GROUPS + g) * 2));
+      s += v.x;
+      q += v.y;
+    }
+#pragma unroll
+    for (int d = 2; d > 0; d >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, d);
+      q += __shfl_xor_sync(0xffffffffu, q, d);
+    }
+    if (sub == 0) {
+      const float n = (float)HW * (float)cpg;
+      const float m = s / n;
+      mean[g] = m;
+      rstd[g] = rsqrtf(fmaxf(q / n - m * m, 0.f) + eps);
+    }
+  }
+}
+
+// partial2[b][chunk][g][2] = (sum dz*gamma, sum dz*gamma*xhat)
+__global__ void gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+                                     const __nv_bfloat16* __restrict__ dy, long long lddy, int HW, int C,
+                                     const float* __restrict__ partial, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, float eps, int silu_act, int rows_per_chunk,
+                                     float* __restrict__ partial2) {
+  extern __shared__ float red[];  // [blockDim][16]
+  __shared__ float mean[GN_GROUPS], rstd[GN_GROUPS];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int b = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+  const int cpg = C / GN_GROUPS;
+  gn_load_stats(partial, nchunks, b, HW, cpg, eps, mean, rstd);
+  __syncthreads();
+  const int oct = C / 8;
+  const int lanes = blockDim.x / oct;
+  const int o = threadIdx.x % oct, rl = threadIdx.x / oct;
+  float ga[8], be[8], mu[8], rs[8], a[8], bb[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = o * 8 + i, g = c / cpg;
+    ga[i] = __ldg(gamma + c);
+    be[i] = __ldg(beta + c);
+    mu[i] = mean[g];
+    rs[i] = rstd[g];
+    a[i] = bb[i] = 0.f;
+  }
+  const int r0 = chunk * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
+  const __nv_bfloat16* xb = x + ((long long)b * HW) * ldx + o * 8;
+  const __nv_bfloat16* db = dy + ((long long)b * HW) * lddy + o * 8;
+  for (int r = r0 + rl; r < r1; r += lanes) {
+    const uint4 ux = __ldg(reinterpret_cast<const uint4*>(xb + (long long)r * ldx));
+    const uint4 ud = __ldg(reinterpret_cast<const uint4*>(db + (long long)r * lddy));
+    const uint32_t wx[4] = {ux.x, ux.y, ux.z, ux.w}, wd[4] = {ud.x, ud.y, ud.z, ud.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 fx = unpack_bf16x2(wx[i]), fd = unpack_bf16x2(wd[i]);
+      const float xv[2] = {fx.x, fx.y}, dv[2] = {fd.x, fd.y};
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = 2 * i + h;
+        const float xh = (xv[h] - mu[k]) * rs[k];
+        float dz = dv[h];
+        if (silu_act) dz *= silu_grad(xh * ga[k] + be[k]);
+        const float t = dz * ga[k];
+        a[k] += t;
+        bb[k] += t * xh;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    red[threadIdx.x * 16 + i] = a[i];
+    red[threadIdx.x * 16 + 8 + i] = bb[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < GN_GROUPS) {  // fixed summation order
+    const int g = threadIdx.x;
+    float gs = 0.f, gq = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      for (int l = 0; l < lanes; ++l) {
+        const float* t = red + (l * oct + (c >> 3)) * 16 + (c & 7);
+        gs += t[0];
+        gq += t[8];
+      }
+    }
+    float* dst = partial2 + (((long long)b * nchunks + chunk) * GN_GROUPS + g) * 2;
+    dst[0] = gs;
+    dst[1] = gq;
+  }
+}
+
+__global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+                                    const __nv_bfloat16* __restrict__ dy, long long lddy, int HW, int C,
+                                    const float* __restrict__ partial, const float* __restrict__ partial2,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                    int silu_act, int rows_per_chunk, const __nv_bfloat16* __restrict__ add,
+                                    long long ldadd, __nv_bfloat16* __restrict__ dx, long long lddx) {
+  __shared__ float mean[GN_GROUPS], rstd[GN_GROUPS], ma[GN_GROUPS], mb[GN_GROUPS];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int b = blockIdx.y, nchunks = gridDim.x;
+  const int cpg = C / GN_GROUPS;
+  gn_load_stats(partial, nchunks, b, HW, cpg, eps, mean, rstd);
+  if (threadIdx.x < GN_GROUPS * 4) {
+    const int g = threadIdx.x >> 2, sub = threadIdx.x & 3;
+    float s = 0.f, q = 0.f;
+    for (int c = sub; c < nchunks; c += 4) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(partial2 + (((long long)b * nchunks + c) * GN_GROUPS + g) * 2));
+      s += v.x;
+      q += v.y;
+    }
+#pragma unroll
+    for (int d = 2; d > 0; d >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, d);
+      q += __shfl_xor_sync(0xffffffffu, q, d);
+    }
+    if (sub == 0) {
+      const float n = (float)HW * (float)cpg;
+      ma[g] = s / n;
+      mb[g] = q / n;
+    }
+  }
+  __syncthreads();
+  const int oct = C / 8;
+  const int lanes = blockDim.x / oct;
+  const int o = threadIdx.x % oct, rl = threadIdx.x / oct;
+  float ga[8], be[8], mu[8], rs[8], A[8], Bm[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = o * 8 + i, g = c / cpg;
+    ga[i] = __ldg(gamma + c);
+    be[i] = __ldg(beta + c);
+    mu[i] = mean[g];
+    rs[i] = rstd[g];
+    A[i] = ma[g];
+    Bm[i] = mb[g];
+  }
+  const int r0 = blockIdx.x * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
+  const __nv_bfloat16* xb = x + ((long long)b * HW) * ldx + o * 8;
+  const __nv_bfloat16* db = dy + ((long long)b * HW) * lddy + o * 8;
+  const __nv_bfloat16* ab = add ? add + ((long long)b * HW) * ldadd + o * 8 : nullptr;
+  __nv_bfloat16* ob = dx + ((long long)b * HW) * lddx + o * 8;
+  for (int r = r0 + rl; r < r1; r += lanes) {
+    const uint4 ux = __ldg(reinterpret_cast<const uint4*>(xb + (long long)r * ldx));
+    const uint4 ud = __ldg(reinterpret_cast<const uint4*>(db + (long long)r * lddy));
+    uint4 ua = make_uint4(0, 0, 0, 0);
+    if (ab) ua = __ldg(reinterpret_cast<const uint4*>(ab + (long long)r * ldadd));
+    const uint32_t wx[4] = {ux.x, ux.y, ux.z, ux.w}, wd[4] = {ud.x, ud.y, ud.z, ud.w}, wa[4] = {ua.x, ua.y, ua.z, ua.w};
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 fx = unpack_bf16x2(wx[i]), fd = unpack_bf16x2(wd[i]), fa = unpack_bf16x2(wa[i]);
+      const float xv[2] = {fx.x, fx.y}, dv[2] = {fd.x, fd.y}, av[2] = {fa.x, fa.y};
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = 2 * i + h;
+        const float xh = (xv[h] - mu[k]) * rs[k];
+        float dz = dv[h];
+        if (silu_act) dz *= silu_grad(xh * ga[k] + be[k]);
+        v[k] = rs[k] * (dz * ga[k] - A[k] - xh * Bm[k]) + av[h];
+      }
+    }
+    uint4 out;
+    out.x = pack_bf16x2(v[0], v[1]);
+    out.y = pack_bf16x2(v[2], v[3]);
+    out.z = pack_bf16x2(v[4], v[5]);
+    out.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(ob + (long long)r * lddx) = out;
+  }
+}
+
+// LayerNorm backward, one warp per row (C <= 1280); statistics recomputed from x in registers.
+__global__ void layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+                                     const __nv_bfloat16* __restrict__ dy, long long lddy, long long M, int C,
+                                     const float* __restrict__ gamma, float eps, const __nv_bfloat16* __restrict__ add,
+                                     long long ldadd, __nv_bfloat16* __restrict__ dx, long long lddx) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long row = (long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const int oct = C / 8;
+  float v[5][8], g[5][8];
+  float s = 0.f;
+  const __nv_bfloat16* xr = x + row * ldx;
+  const __nv_bfloat16* dr = dy + row * lddy;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int o = lane + k * 32;
+    if (o < oct) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + o * 8));
+      const uint4 d = __ldg(reinterpret_cast<const uint4*>(dr + o * 8));
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + o * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + o * 8 + 4));
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w}, wd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_bf16x2(w[i]), fd = unpack_bf16x2(wd[i]);
+        v[k][2 * i] = f.x;
+        v[k][2 * i + 1] = f.y;
+        g[k][2 * i] = fd.x * gg[2 * i];
+        g[k][2 * i + 1] = fd.y * gg[2 * i + 1];
+        s += f.x + f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  const float mean = s / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    if (lane + k * 32 < oct) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float d = v[k][i] - mean;
+        q += d * d;
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) q += __shfl_xor_sync(0xffffffffu, q, d);
+  const float rstd = rsqrtf(q / (float)C + eps);
+  float sa = 0.f, sb = 0.f;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    if (lane + k * 32 < oct) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v[k][i] = (v[k][i] - mean) * rstd;   // xhat
+        sa += g[k][i];
+        sb += g[k][i] * v[k][i];
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    sa += __shfl_xor_sync(0xffffffffu, sa, d);
+    sb += __shfl_xor_sync(0xffffffffu, sb, d);
+  }
+  sa /= (float)C;
+  sb /= (float)C;
+  __nv_bfloat16* outr = dx + row * lddx;
+  const __nv_bfloat16* ar = add ? add + row * ldadd : nullptr;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int o = lane + k * 32;
+    if (o < oct) {
+      float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (ar) {
+        const uint4 ua = __ldg(reinterpret_cast<const uint4*>(ar + o * 8));
+        const uint32_t wa[4] = {ua.x, ua.y, ua.z, ua.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = unpack_bf16x2(wa[i]);
+          a8[2 * i] = f.x;
+          a8[2 * i + 1] = f.y;
+        }
+      }
+      float r[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[i] = rstd * (g[k][i] - sa - v[k][i] * sb) + a8[i];
+      uint4 out;
+      out.x = pack_bf16x2(r[0], r[1]);
+      out.y = pack_bf16x2(r[2], r[3]);
+      out.z = pack_bf16x2(r[4], r[5]);
+      out.w = pack_bf16x2(r[6], r[7]);
+      *reinterpret_cast<uint4*>(outr + o * 8) = out;
+    }
+  }
+}
+
 static int gn_block_threads(int C) {
   int oct = C / 8;
   int k = 320 / oct;
@@ -458,5 +746,61 @@ extern "C" int mos_layernorm_fwd(const void* x, int64_t ldx, int64_t M, int32_t 
   MOS_CHECK_CUDA(launch_pdl(layernorm_kernel, dim3((unsigned)ceil_div(M, warps)), dim3(warps * 32), 0, stream,
                             reinterpret_cast<const __nv_bfloat16*>(x), (long long)ldx, (long long)M, (int)C, gamma, beta,
                             eps, reinterpret_cast<__nv_bfloat16*>(y), (long long)ldy));
+  return MOS_OK;
+}
+
+
+// GroupNorm(+SiLU) backward (frozen affine):  dx = d/dx [ act(GN(x)) ] . dy  (+ add).  Statistics are recomputed from x.
+// workspace: fp32, >= 2 * B * nchunks * 64 floats (the entry point picks nchunks to fit `workspace_floats`).
+extern "C" int mos_groupnorm_bwd(const void* x, int64_t ldx, const void* dy, int64_t lddy, int32_t B, int32_t HW,
+                                 int32_t C, const float* gamma, const float* beta, float eps, int32_t silu_act,
+                                 float* workspace, int32_t workspace_floats, const void* add, int64_t ldadd, void* dx,
+                                 int64_t lddx, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MOS_CHECK_ARG(x && dy && dx && gamma && beta && workspace, "mos_groupnorm_bwd: NULL pointer");
+  MOS_CHECK_ARG(C % 32 == 0 && C <= 2560 && ldx % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0 && ldx >= C && lddy >= C &&
+                    lddx >= C && (!add || (ldadd % 8 == 0 && ldadd >= C)),
+                "mos_groupnorm_bwd: bad C=%d / pitches", C);
+  const int threads = gn_block_threads(C);
+  int nchunks = (int)ceil_div(1184, B);
+  const int min_rows = 4 * (threads / (C / 8));
+  if (nchunks > (int)ceil_div(HW, min_rows)) nchunks = (int)ceil_div(HW, min_rows);
+  {
+    const long long cap = (long long)workspace_floats / ((long long)B * GN_GROUPS * 4);
+    if (nchunks > cap) nchunks = (int)cap;
+  }
+  MOS_CHECK_ARG(nchunks >= 1, "mos_groupnorm_bwd: workspace too small (need >= %d floats)", B * GN_GROUPS * 4);
+  const int rows_per_chunk = (int)ceil_div(HW, nchunks);
+  nchunks = (int)ceil_div(HW, rows_per_chunk);
+  float* p1 = workspace;
+  float* p2 = workspace + (long long)B * nchunks * GN_GROUPS * 2;
+  const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
+  const __nv_bfloat16* db = reinterpret_cast<const __nv_bfloat16*>(dy);
+  MOS_CHECK_CUDA(launch_pdl(gn_stats_kernel, dim3(nchunks, B), dim3(threads), threads * 16 * sizeof(float), stream, xb,
+                            (long long)ldx, (int)HW, (int)C, rows_per_chunk, p1));
+  MOS_CHECK_CUDA(launch_pdl(gn_bwd_reduce_kernel, dim3(nchunks, B), dim3(threads), threads * 16 * sizeof(float), stream,
+                            xb, (long long)ldx, db, (long long)lddy, (int)HW, (int)C, (const float*)p1, gamma, beta, eps,
+                            (int)silu_act, rows_per_chunk, p2));
+  MOS_CHECK_CUDA(launch_pdl(gn_bwd_apply_kernel, dim3(nchunks, B), dim3(threads), 0, stream, xb, (long long)ldx, db,
+                            (long long)lddy, (int)HW, (int)C, (const float*)p1, (const float*)p2, gamma, beta, eps,
+                            (int)silu_act, rows_per_chunk, reinterpret_cast<const __nv_bfloat16*>(add), (long long)ldadd,
+                            reinterpret_cast<__nv_bfloat16*>(dx), (long long)lddx));
+  return MOS_OK;
+}
+
+// LayerNorm backward (frozen affine): dx = d/dx LN(x) . dy (+ add); one warp per row.
+extern "C" int mos_layernorm_bwd(const void* x, int64_t ldx, const void* dy, int64_t lddy, int64_t M, int32_t C,
+                                 const float* gamma, float eps, const void* add, int64_t ldadd, void* dx, int64_t lddx,
+                                 void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MOS_CHECK_ARG(x && dy && dx && gamma, "mos_layernorm_bwd: NULL pointer");
+  MOS_CHECK_ARG(C % 8 == 0 && C <= 1280 && ldx % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0 && (!add || ldadd % 8 == 0),
+                "mos_layernorm_bwd: bad C=%d / pitches", C);
+  const int warps = 8;
+  MOS_CHECK_CUDA(launch_pdl(layernorm_bwd_kernel, dim3((unsigned)ceil_div(M, warps)), dim3(warps * 32), 0, stream,
+                            reinterpret_cast<const __nv_bfloat16*>(x), (long long)ldx,
+                            reinterpret_cast<const __nv_bfloat16*>(dy), (long long)lddy, (long long)M, (int)C, gamma, eps,
+                            reinterpret_cast<const __nv_bfloat16*>(add), (long long)ldadd,
+                            reinterpret_cast<__nv_bfloat16*>(dx), (long long)lddx));
   return MOS_OK;
 }

@@ -145,9 +145,8 @@ def attention_block(attn, hidden_states, encoder_hidden_states=None, want_probs=
         K, Vt = _project_kv(attn, encoder_hidden_states, Hh, d, dev)
     o = torch.empty(B, N, inner, device=dev, dtype=BF16)
     probs = torch.empty(BH, N, M, device=dev, dtype=torch.float32) if want_probs else None
-    if want_probs and (M > 128 or (d == 160 and M > 64)):
-        raise ValueError('attention-probability output is limited to one key tile (cross-attention, <= 128 keys; '
-                         '<= 64 for head_dim 160)')
+    if want_probs and M > 128:
+        raise ValueError('attention-probability output is limited to one key tile (cross-attention, <= 128 keys)')
     ops.attention(Q, K, Vt, o, batch=B, heads=Hh, head_dim=d, nq=N, nk=M, scale=float(attn.scale), probs=probs)
     if regions:
         fh, fw = region_hw

@@ -208,3 +208,62 @@ def test_edlora_pipeline_loop(cuda):
     e = rel_l2(res, x)
     print(f'EDLoRAPipeline 4-step loop vs oracle: latents rel-L2 {e:.3e}')
     assert e < 2e-2
+
+
+def test_attention_store_controller_whole_unet(cuda):
+    """revise_edlora_unet_attention_controller_forward + AttentionStore(training=True) (trainer_edlora.py:96-101 recipe):
+    after one UNet call the store holds one probability map per cross-attention layer, grouped by place, equal to the
+    fp32 oracle's maps (same controller class driven by the oracle's processors)."""
+    from mixofshow.models.edlora import revise_edlora_unet_attention_controller_forward
+    from mixofshow.utils.ptp_util import AttentionStore
+    from oracle import inject
+    from oracle import unet as ou
+    ref = ou.build_unet(0, ou.TINY)
+    ctl_ref = AttentionStore(training=True)
+    n_ref = inject.install_control_processors(ref, ctl_ref)
+    unet = _tiny_b200_unet(0)
+    ctl = AttentionStore(training=True)
+    revise_edlora_unet_attention_controller_forward(unet, ctl)
+    assert ctl.num_att_layers == n_ref == ctl_ref.num_att_layers
+    g = torch.Generator().manual_seed(11)
+    lat = torch.randn(2, 4, 16, 16, generator=g)
+    ehs = torch.randn(2, n_ref, 77, 768, generator=g).to(torch.bfloat16).float()
+    t = torch.tensor([441, 441])
+    with torch.no_grad():
+        ref(lat, t, ehs)
+    unet(lat.cuda(), t.cuda(), ehs.cuda())
+    assert ctl.cur_step == ctl_ref.cur_step == 1
+    for place in AttentionStore.PLACES:
+        a, b = ctl.attention_store[place], ctl_ref.attention_store[place]
+        assert len(a) == len(b)
+        for ma, mb in zip(a, b):
+            assert tuple(ma.shape) == tuple(mb.shape)
+            assert rel_l2(ma, mb) < 2e-2
+            assert (ma.sum(-1) - 1).abs().max().item() < 1e-4
+
+
+def test_control_processor_head_dim_160(cuda):
+    """The deepest SD1.5 cross-attention (1280 channels, head_dim 160, 8x8 tokens) with the control processor: the
+    probability maps come from the single-tile d=160 attention variant."""
+    from mixofshow.models.edlora import EDLoRA_Control_AttnProcessor
+    from mixofshow.models.unet_b200 import Attention
+    torch.manual_seed(5)
+    attn = Attention(1280, 768, heads=8, dim_head=160).cuda()
+    hs = torch.randn(2, 64, 1280, device=cuda)
+    ehs = torch.randn(2, 16, 77, 768, device=cuda).to(torch.bfloat16).float()
+    seen = {}
+
+    class Ctl:
+        def __call__(self, probs, is_cross, place):
+            seen['probs'] = probs
+            return probs
+    out = EDLoRA_Control_AttnProcessor(6, 'mid', Ctl())(attn, hs, encoder_hidden_states=ehs)
+    e = ehs[:, 6].cpu()
+    w = {k: v.detach().cpu() for k, v in attn.state_dict().items()}
+    q = (hs.cpu() @ w['to_q.weight'].T).view(2, 64, 8, 160).transpose(1, 2)
+    k = (e @ w['to_k.weight'].T).view(2, 77, 8, 160).transpose(1, 2)
+    v = (e @ w['to_v.weight'].T).view(2, 77, 8, 160).transpose(1, 2)
+    p = (q @ k.transpose(-1, -2) * 160 ** -0.5).softmax(-1)
+    o = (p @ v).transpose(1, 2).reshape(2, 64, 1280) @ w['to_out.0.weight'].T + w['to_out.0.bias']
+    assert rel_l2(seen['probs'], p.reshape(16, 64, 77)) < 1.5e-2
+    assert rel_l2(out, o) < 1.5e-2

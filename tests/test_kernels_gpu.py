@@ -53,7 +53,7 @@ def test_attention(cuda, d, nq, nk):
     assert rel_l2(out, ref) < 8e-3
 
 
-@pytest.mark.parametrize('d,nq', [(40, 4096), (80, 1024)])
+@pytest.mark.parametrize('d,nq', [(40, 4096), (80, 1024), (160, 256), (160, 64)])
 def test_attention_probs(cuda, d, nq):
     """probability maps for the attention controller (edlora.py:81-82): [B*heads, N, 77], rows sum to 1."""
     from mos_b200 import ops
