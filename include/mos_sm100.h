@@ -181,6 +181,65 @@ int mos_flat_adamw_step(float* params, const float* grads, float* exp_avg, float
                         float weight_decay, int64_t step, float grad_scale, int32_t emb_rows, int32_t emb_dim,
                         float* norm_mean_out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Training step (EDLoRATrainer.forward, trainer_edlora.py:202-261, + loss.backward(), train_edlora.py:120-123).
+ * All base weights are frozen (trainer_edlora.py:88-90), so the backward pass only produces activation gradients
+ * and the rank-4 LoRA gradients.  Linear / conv activation gradients reuse mos_gemm_bf16 on transposed weight packs.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* forward attention that also saves lse2 [B*H, nq] (log2-domain log-sum-exp of scale*S) and, for cross-attention,
+ * the per-head probabilities at key columns pos[b][0..1] -> pcols [B*H, nq, 2] (attention regulariser :263-313). */
+int mos_attention_fwd_train(const void* Q, const void* K, const void* Vt, void* out, int64_t ldo, float* lse2,
+                            float* pcols, const int32_t* pos, int32_t batch, int32_t heads, int32_t head_dim,
+                            int32_t nq, int32_t nk, int32_t nk8, float scale, void* stream);
+/* flash-attention backward.  Q, K, V, dO: head-split rows [B*H, n, DP]; Qt, Kt, dOt: transposed copies [B*H, DV, n8]
+ * (mos_heads_transpose); delta from mos_attn_delta; gcols/pos (optional): gradient on the probabilities at the two
+ * key columns pos[b][0..1], [B, nq, 2].  dq/dk/dv: token-major bf16 [B*n, ld] (head h in columns h*d..). */
+int mos_attention_bwd(const void* Q, const void* K, const void* V, const void* dO, const void* Qt, const void* Kt,
+                      const void* dOt, const float* lse2, const float* delta, const float* gcols, const int32_t* pos,
+                      void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int32_t batch,
+                      int32_t heads, int32_t head_dim, int32_t nq, int32_t nk, int32_t nq8, int32_t nk8, float scale,
+                      void* stream);
+/* dst[bh, j, r] = src[bh, r, j]: rows [BH, R, DP] -> transposed [BH, DV, R8] (dst zero-initialised by the caller). */
+int mos_heads_transpose(const void* src, int32_t BH, int32_t R, int32_t DP, int32_t DV, int32_t R8, void* dst,
+                        void* stream);
+/* delta[bh, q] = sum_j dO[bh, q, j] O[b*N + q, h*d + j]  (+ sum_c pcols[bh, q, c] gcols[b, q, c]) */
+int mos_attn_delta(const void* dO, int32_t DP, const void* O, int64_t ldo, int32_t batch, int32_t heads,
+                   int32_t head_dim, int32_t N, const float* pcols, const float* gcols, float* delta, void* stream);
+/* GroupNorm(32)(+SiLU) / LayerNorm backward with frozen affine: dx = J^T dy (+ add); statistics recomputed from x.
+ * workspace (GroupNorm): fp32, >= B * 128 floats (more = more parallel chunks). */
+int mos_groupnorm_bwd(const void* x, int64_t ldx, const void* dy, int64_t lddy, int32_t B, int32_t HW, int32_t C,
+                      const float* gamma, const float* beta, float eps, int32_t silu_act, float* workspace,
+                      int32_t workspace_floats, const void* add, int64_t ldadd, void* dx, int64_t lddx, void* stream);
+int mos_layernorm_bwd(const void* x, int64_t ldx, const void* dy, int64_t lddy, int64_t M, int32_t C,
+                      const float* gamma, float eps, const void* add, int64_t ldadd, void* dx, int64_t lddx,
+                      void* stream);
+/* GEGLU in un-fused form: z [M, 2H] in 160-column tiles [80 a | 80 gate] (the fused GEMM's weight-row interleave),
+ * y = a * gelu(gate) [M, H]; backward writes dz in the same interleaved layout. */
+int mos_geglu_fwd(const void* z, int64_t ldz, int64_t M, int32_t H, void* y, int64_t ldy, void* stream);
+int mos_geglu_bwd(const void* z, int64_t ldz, const void* dy, int64_t lddy, int64_t M, int32_t H, void* dz,
+                  int64_t lddz, void* stream);
+/* backward of nearest x2 (sum of each 2x2 block), of the stride-2 im2col (col2im gather, optional + add) and of
+ * conv_out (dy fp32 NCHW -> dx bf16 NHWC; w fp32 [Cout][9][C]). */
+int mos_upsample2x_bwd(const void* dy, int64_t lddy, int32_t B, int32_t H, int32_t W, int32_t C, void* dx,
+                       int64_t lddx, void* stream);
+int mos_col2im_s2(const void* dcol, int32_t B, int32_t H, int32_t W, int32_t C, const void* add, int64_t ldadd,
+                  void* dx, int64_t lddx, void* stream);
+int mos_conv_out_bwd(const float* dy, int32_t B, int32_t H, int32_t W, int32_t C, const float* w, int32_t Cout,
+                     void* dx, void* stream);
+/* masked MSE (trainer_edlora.py:251-252): loss = mean_b sum_{c,hw}((pred-target)^2 mask_b) / sum_hw mask_b ;
+ * dpred = grad_scale * dloss/dpred.  pred/target fp32 [B, Cc, HW], mask fp32 [B, HW]; ws >= 2B floats. */
+int mos_masked_mse(const float* pred, const float* target, const float* mask, int32_t B, int32_t Cc, int32_t HW,
+                   float grad_scale, float* ws, float* loss, float* dpred, void* stream);
+/* DDPMScheduler.add_noise (trainer_edlora.py:218): out = sqrt(ac[t_b]) x0 + sqrt(1 - ac[t_b]) noise */
+int mos_add_noise(const float* x0, const float* noise, const int32_t* timesteps, const float* alphas_cumprod,
+                  int32_t B, int64_t per_sample, float* out, void* stream);
+/* LoRA gradients of y = x W^T + alpha (x D^T) U^T (edlora.py:244-246):  d_up [N, 4] (+)= alpha dY^T (x D^T),
+ * d_down [4, K] (+)= alpha (dY U)^T x.  x bf16 [M, K], dy bf16 [M, N], down fp32 [4, K], up fp32 [N, 4];
+ * workspace >= ceil(M/64) * 4 * (K + N) floats; fixed-order reduction (bitwise reproducible). */
+int mos_lora_grad(const void* x, int64_t ldx, const void* dy, int64_t lddy, int64_t M, int32_t K, int32_t N,
+                  const float* down, const float* up, float alpha, float* workspace, int64_t workspace_floats,
+                  int32_t accumulate, float* d_down, float* d_up, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

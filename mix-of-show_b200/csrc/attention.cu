@@ -58,6 +58,9 @@ struct AttnDev {
   __nv_bfloat16* out;
   long long ldo;
   float* probs;  // optional [B*H, nq, nk] fp32 (single kv tile only)
+  float* lse2;   // optional [B*H, nq]: log2-domain log-sum-exp of scale*S (saved for the backward kernels)
+  float* pcols;  // optional [B*H, nq, 2]: probabilities at key columns pos[b][0..1] (single kv tile only)
+  const int* pos;
 };
 
 template <int D, bool WIDE>
@@ -226,6 +229,13 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       __syncwarp();
       uint8_t* sPb = sP + pbuf * C::P_BYTES;
       float rs = 0.f;
+      float pc0 = 0.f, pc1 = 0.f;
+      int pos0 = -1, pos1 = -1;
+      if (p.pcols != nullptr) {
+        const int bb = bh / p.heads;
+        pos0 = __ldg(p.pos + bb * 2) - j * C::BKV;
+        pos1 = __ldg(p.pos + bb * 2 + 1) - j * C::BKV;
+      }
 #pragma unroll 1
       for (int c = 0; c < C::BKV / 32; ++c) {
         uint32_t v[32];
@@ -246,6 +256,13 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
             rs += pv[i];
           }
         }
+        if (p.pcols != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            pc0 = (c * 32 + i == pos0) ? pv[i] : pc0;
+            pc1 = (c * 32 + i == pos1) ? pv[i] : pc1;
+          }
+        }
         uint8_t* rowp = sPb + (c >> 1) * 16384 + r * 128;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -257,6 +274,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           const int c16 = (c & 1) * 4 + g;  // 16-byte chunk inside the 128-byte row
           *reinterpret_cast<uint4*>(rowp + ((c16 ^ (r & 7)) << 4)) = u;
         }
+      }
+      if (p.pcols != nullptr && T == 1 && q_idx < p.nq) {
+        const float inv = 1.0f / rs;
+        *reinterpret_cast<float2*>(p.pcols + ((long long)bh * p.nq + q_idx) * 2) = make_float2(pc0 * inv, pc1 * inv);
       }
       if (p.probs != nullptr && T == 1) {
         // normalised probabilities for the attention controller (edlora.py:81-82): single kv tile, so l = rs
@@ -289,6 +310,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     if (q_idx < p.nq) {
       const float inv = 1.0f / l_run;
       const int b = bh / p.heads, h = bh - b * p.heads;
+      if (p.lse2 != nullptr) p.lse2[(long long)bh * p.nq + q_idx] = m_run + log2f(l_run);
       __nv_bfloat16* orow = p.out + ((long long)b * p.nq + q_idx) * p.ldo + h * D;
 #pragma unroll
       for (int c = 0; c < D / 8; ++c) {
@@ -312,7 +334,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 
 template <int D, bool WIDE>
 static int launch_attn(const void* Q, const void* K, const void* Vt, void* out, int64_t ldo, float* probs, int BH,
-                       int heads, int nq, int nk, int nk8, float scale, cudaStream_t stream) {
+                       int heads, int nq, int nk, int nk8, float scale, cudaStream_t stream, float* lse2 = nullptr,
+                       float* pcols = nullptr, const int* pos = nullptr) {
   using C = AttnCfg<D, WIDE>;
   CUtensorMap tmQ, tmK, tmV;
   {
@@ -344,6 +367,9 @@ static int launch_attn(const void* Q, const void* K, const void* Vt, void* out, 
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
   p.probs = probs;
+  p.lse2 = lse2;
+  p.pcols = pcols;
+  p.pos = pos;
   static bool configured = false;
   if (!configured) {
     MOS_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel<D, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -375,5 +401,33 @@ extern "C" int mos_attention_fwd(const void* Q, const void* K, const void* Vt, v
       if (nk <= 128) return launch_attn<160, true>(Q, K, Vt, out, ldo, probs, BH, heads, nq, nk, nk8, scale, stream);
       return launch_attn<160, false>(Q, K, Vt, out, ldo, probs, BH, heads, nq, nk, nk8, scale, stream);
     default: return set_err(MOS_EUNSUPPORTED, "mos_attention_fwd: head_dim %d not in {40, 80, 160}", head_dim);
+  }
+}
+
+
+// Training forward: same kernel, additionally saves the log2-domain log-sum-exp [B*H, nq] for mos_attention_bwd and
+// (cross-attention, nk <= 128) the per-head probabilities at the two concept-token columns pos[b][0..1] -> pcols
+// [B*H, nq, 2] for the attention regulariser (trainer_edlora.py:263-313).
+extern "C" int mos_attention_fwd_train(const void* Q, const void* K, const void* Vt, void* out, int64_t ldo, float* lse2,
+                                       float* pcols, const int32_t* pos, int32_t batch, int32_t heads,
+                                       int32_t head_dim, int32_t nq, int32_t nk, int32_t nk8, float scale,
+                                       void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MOS_CHECK_ARG(Q && K && Vt && out && lse2, "mos_attention_fwd_train: NULL pointer");
+  MOS_CHECK_ARG(batch > 0 && heads > 0 && nq > 0 && nk > 0, "mos_attention_fwd_train: bad shape");
+  MOS_CHECK_ARG(nk8 >= nk && nk8 % 8 == 0, "mos_attention_fwd_train: nk8 must be >= nk and a multiple of 8");
+  MOS_CHECK_ARG(ldo >= (int64_t)heads * head_dim && ldo % 8 == 0, "mos_attention_fwd_train: bad ldo");
+  MOS_CHECK_ARG(!pcols == !pos, "mos_attention_fwd_train: pcols and pos go together");
+  if (pcols) MOS_CHECK_ARG(nk <= 128, "mos_attention_fwd_train: pcols needs a single kv tile (nk <= 128)");
+  const int BH = batch * heads;
+  const int* ip = reinterpret_cast<const int*>(pos);
+  switch (head_dim) {
+    case 40: return launch_attn<40, false>(Q, K, Vt, out, ldo, nullptr, BH, heads, nq, nk, nk8, scale, stream, lse2, pcols, ip);
+    case 80: return launch_attn<80, false>(Q, K, Vt, out, ldo, nullptr, BH, heads, nq, nk, nk8, scale, stream, lse2, pcols, ip);
+    case 160:
+      if (nk <= 128)
+        return launch_attn<160, true>(Q, K, Vt, out, ldo, nullptr, BH, heads, nq, nk, nk8, scale, stream, lse2, pcols, ip);
+      return launch_attn<160, false>(Q, K, Vt, out, ldo, nullptr, BH, heads, nq, nk, nk8, scale, stream, lse2, pcols, ip);
+    default: return set_err(MOS_EUNSUPPORTED, "mos_attention_fwd_train: head_dim %d not in {40, 80, 160}", head_dim);
   }
 }

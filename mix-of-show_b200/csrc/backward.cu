@@ -1,0 +1,494 @@
+// backward.cu — HBM-bound kernels of the ED-LoRA training step (EDLoRATrainer.forward, trainer_edlora.py:202-261, and the
+// loss.backward() that follows it at train_edlora.py:120-123).  All base weights are frozen: only activation gradients
+// and the rank-4 LoRA gradients exist.
+//   geglu fwd / bwd (un-fused form: the pre-activation is kept for backward)
+//   upsample2x bwd, stride-2 col2im (Downsample2D bwd), conv_out bwd
+//   masked MSE loss + gradient (trainer_edlora.py:251-252), add_noise (DDPMScheduler.add_noise)
+//   head-split transpose, attention delta (rowsum(dO * O)), LoRA gradients (dU, dD)
+#include "common.h"
+#include "tc.cuh"
+
+namespace mos {
+
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+static inline unsigned nblk(long long total, int threads) { return (unsigned)((total + threads - 1) / threads); }
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* v) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = unpack_bf16x2(w[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]);
+  u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]);
+  u.w = pack_bf16x2(v[6], v[7]);
+  return u;
+}
+
+// ------------------------------------------------------------------------------------------------ GEGLU
+// z [M, 2H] in 160-column tiles [80 a | 80 gate] (the weight-row interleave of the fused GEMM), y [M, H]
+__global__ void geglu_fwd_kernel(const __nv_bfloat16* __restrict__ z, long long ldz, long long M, int H,
+                                 __nv_bfloat16* __restrict__ y, long long ldy) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int oct = H / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * oct) return;
+  const int o = (int)(idx % oct);
+  const long long m = idx / oct;
+  const int tile = (o * 8) / 80, j = (o * 8) % 80;
+  const __nv_bfloat16* zr = z + m * ldz + tile * 160 + j;
+  float a[8], g[8], r[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(zr)), a);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(zr + 80)), g);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = a[i] * gelu_erf(g[i]);
+  *reinterpret_cast<uint4*>(y + m * ldy + o * 8) = pack8(r);
+}
+
+__global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ z, long long ldz,
+                                 const __nv_bfloat16* __restrict__ dy, long long lddy, long long M, int H,
+                                 __nv_bfloat16* __restrict__ dz, long long lddz) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int oct = H / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * oct) return;
+  const int o = (int)(idx % oct);
+  const long long m = idx / oct;
+  const int tile = (o * 8) / 80, j = (o * 8) % 80;
+  const __nv_bfloat16* zr = z + m * ldz + tile * 160 + j;
+  float a[8], g[8], d[8], da[8], dg[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(zr)), a);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(zr + 80)), g);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(dy + m * lddy + o * 8)), d);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float cdf = 0.5f * (1.0f + erff(g[i] * 0.70710678118654752f));
+    const float pdf = 0.3989422804014327f * __expf(-0.5f * g[i] * g[i]);
+    da[i] = d[i] * g[i] * cdf;
+    dg[i] = d[i] * a[i] * (cdf + g[i] * pdf);
+  }
+  __nv_bfloat16* dr = dz + m * lddz + tile * 160 + j;
+  *reinterpret_cast<uint4*>(dr) = pack8(da);
+  *reinterpret_cast<uint4*>(dr + 80) = pack8(dg);
+}
+
+// ------------------------------------------------------------------------------------------------ resampling
+// dx[b, h, w, :] = sum of the 2x2 block of dy  (backward of nearest x2)
+__global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, int B, int H, int W, int C,
+                                      __nv_bfloat16* __restrict__ dx, long long lddx) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int oct = C / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * H * W * oct) return;
+  const int o = (int)(idx % oct);
+  const long long pix = idx / oct;
+  const int w = (int)(pix % W), h = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const long long src = ((long long)b * 2 * H + 2 * h + (t >> 1)) * 2 * W + 2 * w + (t & 1);
+    float v[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy + src * lddy + o * 8)), v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += v[i];
+  }
+  *reinterpret_cast<uint4*>(dx + pix * lddx + o * 8) = pack8(acc);
+}
+
+// dx[b, y, x, c] = sum over taps (kh, kw) with (y+1-kh, x+1-kw) even and in range of dcol[(b, oy, ox), tap*C + c]
+__global__ void col2im_s2_kernel(const __nv_bfloat16* __restrict__ dcol, int B, int H, int W, int C,
+                                 const __nv_bfloat16* __restrict__ add, long long ldadd,
+                                 __nv_bfloat16* __restrict__ dx, long long lddx) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int oct = C / 8, Ho = H / 2, Wo = W / 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * H * W * oct) return;
+  const int o = (int)(idx % oct);
+  const long long pix = idx / oct;
+  const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (add) unpack8(__ldg(reinterpret_cast<const uint4*>(add + pix * ldadd + o * 8)), acc);
+  for (int kh = 0; kh < 3; ++kh) {
+    const int ty = y + 1 - kh;
+    if (ty < 0 || (ty & 1) || (ty >> 1) >= Ho) continue;
+    for (int kw = 0; kw < 3; ++kw) {
+      const int tx = x + 1 - kw;
+      if (tx < 0 || (tx & 1) || (tx >> 1) >= Wo) continue;
+      const long long op = ((long long)b * Ho + (ty >> 1)) * Wo + (tx >> 1);
+      float v[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(dcol + op * 9 * C + (long long)(kh * 3 + kw) * C + o * 8)), v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v[i];
+    }
+  }
+  *reinterpret_cast<uint4*>(dx + pix * lddx + o * 8) = pack8(acc);
+}
+
+// conv_out backward: dy fp32 NCHW [B, Cout<=4, H, W], w fp32 [Cout][9][C] -> dx bf16 [B*H*W, C]
+__global__ void conv_out_bwd_kernel(const float* __restrict__ dy, int B, int H, int W, int C,
+                                    const float* __restrict__ w, int Cout, __nv_bfloat16* __restrict__ dx) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int oct = C / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * H * W * oct) return;
+  const int o = (int)(idx % oct);
+  const long long pix = idx / oct;
+  const int wq = (int)(pix % W), hq = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int tap = 0; tap < 9; ++tap) {
+    const int hh = hq - (tap / 3 - 1), ww = wq - (tap % 3 - 1);   // output pixel that read this input through `tap`
+    if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+    for (int oc = 0; oc < Cout; ++oc) {
+      const float g = __ldg(dy + (((long long)b * Cout + oc) * H + hh) * W + ww);
+      const float* wp = w + ((long long)oc * 9 + tap) * C + o * 8;
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
+      acc[0] += g * w0.x; acc[1] += g * w0.y; acc[2] += g * w0.z; acc[3] += g * w0.w;
+      acc[4] += g * w1.x; acc[5] += g * w1.y; acc[6] += g * w1.z; acc[7] += g * w1.w;
+    }
+  }
+  *reinterpret_cast<uint4*>(dx + pix * C + o * 8) = pack8(acc);
+}
+
+// ------------------------------------------------------------------------------------------------ loss
+// per-sample sums: ws[b] = (sum_{c,h,w} (pred - target)^2 * mask[b, hw], sum_{hw} mask[b, hw])
+__global__ void mse_sums_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                const float* __restrict__ mask, int Cc, int HW, float* __restrict__ ws) {
+  __shared__ float sn[32], sd[32];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int b = blockIdx.x;
+  float num = 0.f, den = 0.f;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    const float m = mask[(long long)b * HW + i];
+    den += m;
+    for (int c = 0; c < Cc; ++c) {
+      const long long k = ((long long)b * Cc + c) * HW + i;
+      const float d = pred[k] - target[k];
+      num += d * d * m;
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    num += __shfl_xor_sync(0xffffffffu, num, d);
+    den += __shfl_xor_sync(0xffffffffu, den, d);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sn[threadIdx.x >> 5] = num;
+    sd[threadIdx.x >> 5] = den;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, c = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+      a += sn[i];
+      c += sd[i];
+    }
+    ws[2 * b] = a;
+    ws[2 * b + 1] = c;
+  }
+}
+
+// dpred = grad_scale * 2 (pred - target) mask / (den_b * B);  loss[0] = mean_b num_b / den_b
+__global__ void mse_grad_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                const float* __restrict__ mask, int B, int Cc, int HW, const float* __restrict__ ws,
+                                float grad_scale, float* __restrict__ dpred, float* __restrict__ loss) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx == 0) {
+    float l = 0.f;
+    for (int b = 0; b < B; ++b) l += ws[2 * b] / ws[2 * b + 1];
+    loss[0] = l / (float)B;
+  }
+  if (idx >= (long long)B * Cc * HW) return;
+  const int i = (int)(idx % HW);
+  const int b = (int)(idx / ((long long)Cc * HW));
+  const float m = mask[(long long)b * HW + i];
+  dpred[idx] = grad_scale * 2.0f * (pred[idx] - target[idx]) * m / (ws[2 * b + 1] * (float)B);
+}
+
+// noisy = sqrt(ac[t_b]) x0 + sqrt(1 - ac[t_b]) noise
+__global__ void add_noise_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
+                                 const int* __restrict__ t, const float* __restrict__ alphas_cumprod, long long per,
+                                 long long total, float* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const float ac = alphas_cumprod[t[idx / per]];
+  out[idx] = sqrtf(ac) * x0[idx] + sqrtf(1.0f - ac) * noise[idx];
+}
+
+// ------------------------------------------------------------------------------------------------ attention glue
+// dst[bh, j, r] = src[bh, r, j]   src [BH, R, DP] -> dst [BH, DV, R8] (r >= R left untouched: buffers are zero-initialised)
+__global__ void heads_transpose_kernel(const __nv_bfloat16* __restrict__ src, int R, int DP, int DV, int R8,
+                                       __nv_bfloat16* __restrict__ dst) {
+  __shared__ __nv_bfloat16 tile[32][34];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int bh = blockIdx.z;
+  const int r0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+  const __nv_bfloat16* s = src + (long long)bh * R * DP;
+  __nv_bfloat16* d = dst + (long long)bh * DV * R8;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, j = j0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && j < DP) ? s[(long long)r * DP + j] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int j = j0 + i, r = r0 + threadIdx.x;
+    if (j < DV && r < R) d[(long long)j * R8 + r] = tile[threadIdx.x][i];
+  }
+}
+
+// delta[bh, q] = sum_j dO[bh, q, j] * O[b*N + q, h*d + j]  (+ sum_c pcols[bh, q, c] * gcols[b, q, c] for the attn-reg path)
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, int DP, const __nv_bfloat16* __restrict__ O,
+                                  long long ldo, int heads, int d, int N, long long total,
+                                  const float* __restrict__ pcols, const float* __restrict__ gcols,
+                                  float* __restrict__ delta) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // bh * N + q
+  if (idx >= total) return;
+  const int q = (int)(idx % N);
+  const int bh = (int)(idx / N);
+  const int b = bh / heads, h = bh - b * heads;
+  const __nv_bfloat16* dr = dO + idx * DP;
+  const __nv_bfloat16* orow = O + ((long long)b * N + q) * ldo + h * d;
+  float acc = 0.f;
+  for (int c = 0; c < d / 8; ++c) {
+    float a[8], g[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dr + c * 8)), a);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(orow + c * 8)), g);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc += a[i] * g[i];
+  }
+  if (pcols) {
+    const float2 pc = *reinterpret_cast<const float2*>(pcols + idx * 2);
+    const float2 gc = *reinterpret_cast<const float2*>(gcols + ((long long)b * N + q) * 2);
+    acc += pc.x * gc.x + pc.y * gc.y;
+  }
+  delta[idx] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------ LoRA gradients
+// y = x W^T + alpha (x D^T) U^T  (edlora.py:244-246), dY given:
+//   dU[n, r] = alpha sum_m dY[m, n] t[m, r],  t = x D^T ;   dD[r, k] = alpha sum_m s[m, r] x[m, k],  s = dY U
+// One block = LG_ROWS rows; partial sums per block, reduced in a fixed order by lora_grad_reduce_kernel.
+constexpr int LG_ROWS = 64;
+
+__global__ void __launch_bounds__(256)
+lora_grad_partial_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ dy,
+                         long long lddy, long long M, int K, int N, const float* __restrict__ down,
+                         const float* __restrict__ up, float* __restrict__ pD, float* __restrict__ pU) {
+  __shared__ float ts[LG_ROWS][8];  // t[0..3], s[0..3]
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long m0 = (long long)blockIdx.x * LG_ROWS;
+  const int rows = (int)min((long long)LG_ROWS, M - m0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < LG_ROWS; r += 8) {
+    float t[4] = {0.f, 0.f, 0.f, 0.f}, s[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < rows) {
+      const __nv_bfloat16* xr = x + (m0 + r) * ldx;
+      for (int k = lane * 8; k < K; k += 256) {
+        float v[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(xr + k)), v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float* dp = down + (long long)q * K + k;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t[q] += v[i] * __ldg(dp + i);
+        }
+      }
+      const __nv_bfloat16* dr = dy + (m0 + r) * lddy;
+      for (int n = lane * 8; n < N; n += 256) {
+        float v[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dr + n)), v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 u = __ldg(reinterpret_cast<const float4*>(up + (long long)(n + i) * 4));
+          s[0] += v[i] * u.x;
+          s[1] += v[i] * u.y;
+          s[2] += v[i] * u.z;
+          s[3] += v[i] * u.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        t[q] += __shfl_xor_sync(0xffffffffu, t[q], d);
+        s[q] += __shfl_xor_sync(0xffffffffu, s[q], d);
+      }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        ts[r][q] = t[q];
+        ts[r][4 + q] = s[q];
+      }
+    }
+  }
+  __syncthreads();
+  float* pd = pD + (long long)blockIdx.x * 4 * K;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < rows; ++r) {
+      const float xv = __bfloat162float(x[(m0 + r) * ldx + k]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) a[q] += ts[r][4 + q] * xv;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) pd[(long long)q * K + k] = a[q];
+  }
+  float* pu = pU + (long long)blockIdx.x * 4 * N;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < rows; ++r) {
+      const float dv = __bfloat162float(dy[(m0 + r) * lddy + n]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) a[q] += ts[r][q] * dv;
+    }
+    *reinterpret_cast<float4*>(pu + (long long)n * 4) = make_float4(a[0], a[1], a[2], a[3]);
+  }
+}
+
+// grad[i] (+)= alpha * sum_blk partial[blk][i]
+__global__ void lora_grad_reduce_kernel(const float* __restrict__ partial, int nblk_, long long n, float alpha,
+                                        int accumulate, float* __restrict__ grad) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a = 0.f;
+  for (int b = 0; b < nblk_; ++b) a += partial[(long long)b * n + i];
+  grad[i] = (accumulate ? grad[i] : 0.f) + alpha * a;
+}
+
+}  // namespace mos
+
+using namespace mos;
+
+extern "C" int mos_geglu_fwd(const void* z, int64_t ldz, int64_t M, int32_t H, void* y, int64_t ldy, void* stream) {
+  MOS_CHECK_ARG(z && y && H % 80 == 0 && ldz % 8 == 0 && ldy % 8 == 0 && ldz >= 2 * H && ldy >= H,
+                "mos_geglu_fwd: bad arguments (H=%d must be a multiple of 80)", H);
+  MOS_CHECK_CUDA(launch_pdl(geglu_fwd_kernel, dim3(nblk(M * (H / 8), 256)), dim3(256), 0, STREAM(stream),
+                            reinterpret_cast<const __nv_bfloat16*>(z), (long long)ldz, (long long)M, (int)H,
+                            reinterpret_cast<__nv_bfloat16*>(y), (long long)ldy));
+  return MOS_OK;
+}
+
+extern "C" int mos_geglu_bwd(const void* z, int64_t ldz, const void* dy, int64_t lddy, int64_t M, int32_t H, void* dz,
+                             int64_t lddz, void* stream) {
+  MOS_CHECK_ARG(z && dy && dz && H % 80 == 0 && ldz % 8 == 0 && lddy % 8 == 0 && lddz % 8 == 0 && ldz >= 2 * H &&
+                    lddz >= 2 * H && lddy >= H, "mos_geglu_bwd: bad arguments (H=%d must be a multiple of 80)", H);
+  MOS_CHECK_CUDA(launch_pdl(geglu_bwd_kernel, dim3(nblk(M * (H / 8), 256)), dim3(256), 0, STREAM(stream),
+                            reinterpret_cast<const __nv_bfloat16*>(z), (long long)ldz,
+                            reinterpret_cast<const __nv_bfloat16*>(dy), (long long)lddy, (long long)M, (int)H,
+                            reinterpret_cast<__nv_bfloat16*>(dz), (long long)lddz));
+  return MOS_OK;
+}
+
+extern "C" int mos_upsample2x_bwd(const void* dy, int64_t lddy, int32_t B, int32_t H, int32_t W, int32_t C, void* dx,
+                                  int64_t lddx, void* stream) {
+  MOS_CHECK_ARG(dy && dx && C % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0, "mos_upsample2x_bwd: bad arguments");
+  MOS_CHECK_CUDA(launch_pdl(upsample2x_bwd_kernel, dim3(nblk((long long)B * H * W * (C / 8), 256)), dim3(256), 0,
+                            STREAM(stream), reinterpret_cast<const __nv_bfloat16*>(dy), (long long)lddy, (int)B, (int)H,
+                            (int)W, (int)C, reinterpret_cast<__nv_bfloat16*>(dx), (long long)lddx));
+  return MOS_OK;
+}
+
+extern "C" int mos_col2im_s2(const void* dcol, int32_t B, int32_t H, int32_t W, int32_t C, const void* add,
+                             int64_t ldadd, void* dx, int64_t lddx, void* stream) {
+  MOS_CHECK_ARG(dcol && dx && C % 8 == 0 && lddx % 8 == 0 && H % 2 == 0 && W % 2 == 0 && (!add || ldadd % 8 == 0),
+                "mos_col2im_s2: bad arguments");
+  MOS_CHECK_CUDA(launch_pdl(col2im_s2_kernel, dim3(nblk((long long)B * H * W * (C / 8), 256)), dim3(256), 0,
+                            STREAM(stream), reinterpret_cast<const __nv_bfloat16*>(dcol), (int)B, (int)H, (int)W, (int)C,
+                            reinterpret_cast<const __nv_bfloat16*>(add), (long long)ldadd,
+                            reinterpret_cast<__nv_bfloat16*>(dx), (long long)lddx));
+  return MOS_OK;
+}
+
+extern "C" int mos_conv_out_bwd(const float* dy, int32_t B, int32_t H, int32_t W, int32_t C, const float* w,
+                                int32_t Cout, void* dx, void* stream) {
+  MOS_CHECK_ARG(dy && w && dx && C % 8 == 0 && Cout >= 1 && Cout <= 4, "mos_conv_out_bwd: bad arguments");
+  MOS_CHECK_CUDA(launch_pdl(conv_out_bwd_kernel, dim3(nblk((long long)B * H * W * (C / 8), 256)), dim3(256), 0,
+                            STREAM(stream), dy, (int)B, (int)H, (int)W, (int)C, w, (int)Cout,
+                            reinterpret_cast<__nv_bfloat16*>(dx)));
+  return MOS_OK;
+}
+
+extern "C" int mos_masked_mse(const float* pred, const float* target, const float* mask, int32_t B, int32_t Cc,
+                              int32_t HW, float grad_scale, float* ws, float* loss, float* dpred, void* stream) {
+  MOS_CHECK_ARG(pred && target && mask && ws && loss && dpred && B > 0, "mos_masked_mse: bad arguments");
+  MOS_CHECK_CUDA(launch_pdl(mse_sums_kernel, dim3(B), dim3(256), 0, STREAM(stream), pred, target, mask, (int)Cc, (int)HW, ws));
+  MOS_CHECK_CUDA(launch_pdl(mse_grad_kernel, dim3(nblk((long long)B * Cc * HW, 256)), dim3(256), 0, STREAM(stream), pred,
+                            target, mask, (int)B, (int)Cc, (int)HW, (const float*)ws, grad_scale, dpred, loss));
+  return MOS_OK;
+}
+
+extern "C" int mos_add_noise(const float* x0, const float* noise, const int32_t* timesteps,
+                             const float* alphas_cumprod, int32_t B, int64_t per_sample, float* out, void* stream) {
+  MOS_CHECK_ARG(x0 && noise && timesteps && alphas_cumprod && out && B > 0, "mos_add_noise: bad arguments");
+  MOS_CHECK_CUDA(launch_pdl(add_noise_kernel, dim3(nblk(B * per_sample, 256)), dim3(256), 0, STREAM(stream), x0, noise,
+                            reinterpret_cast<const int*>(timesteps), alphas_cumprod, (long long)per_sample,
+                            (long long)B * per_sample, out));
+  return MOS_OK;
+}
+
+extern "C" int mos_heads_transpose(const void* src, int32_t BH, int32_t R, int32_t DP, int32_t DV, int32_t R8, void* dst,
+                                   void* stream) {
+  MOS_CHECK_ARG(src && dst && DV <= DP && R8 >= R && R8 % 8 == 0, "mos_heads_transpose: bad arguments");
+  dim3 grid(nblk(R, 32), nblk(DV, 32), BH);
+  MOS_CHECK_CUDA(launch_pdl(heads_transpose_kernel, grid, dim3(32, 8), 0, STREAM(stream),
+                            reinterpret_cast<const __nv_bfloat16*>(src), (int)R, (int)DP, (int)DV, (int)R8,
+                            reinterpret_cast<__nv_bfloat16*>(dst)));
+  return MOS_OK;
+}
+
+extern "C" int mos_attn_delta(const void* dO, int32_t DP, const void* O, int64_t ldo, int32_t batch, int32_t heads,
+                              int32_t head_dim, int32_t N, const float* pcols, const float* gcols, float* delta,
+                              void* stream) {
+  MOS_CHECK_ARG(dO && O && delta && head_dim % 8 == 0 && DP % 8 == 0 && ldo % 8 == 0 && (!pcols == !gcols),
+                "mos_attn_delta: bad arguments");
+  const long long total = (long long)batch * heads * N;
+  MOS_CHECK_CUDA(launch_pdl(attn_delta_kernel, dim3(nblk(total, 128)), dim3(128), 0, STREAM(stream),
+                            reinterpret_cast<const __nv_bfloat16*>(dO), (int)DP, reinterpret_cast<const __nv_bfloat16*>(O),
+                            (long long)ldo, (int)heads, (int)head_dim, (int)N, total, pcols, gcols, delta));
+  return MOS_OK;
+}
+
+extern "C" int mos_lora_grad(const void* x, int64_t ldx, const void* dy, int64_t lddy, int64_t M, int32_t K, int32_t N,
+                             const float* down, const float* up, float alpha, float* workspace,
+                             int64_t workspace_floats, int32_t accumulate, float* d_down, float* d_up, void* stream) {
+  MOS_CHECK_ARG(x && dy && down && up && workspace && d_down && d_up, "mos_lora_grad: NULL pointer");
+  MOS_CHECK_ARG(K % 8 == 0 && N % 8 == 0 && ldx % 8 == 0 && lddy % 8 == 0 && M > 0, "mos_lora_grad: bad shape");
+  const int nb = (int)ceil_div(M, LG_ROWS);
+  MOS_CHECK_ARG((long long)nb * 4 * (K + N) <= workspace_floats, "mos_lora_grad: workspace too small (need %lld floats)",
+                (long long)nb * 4 * (K + N));
+  float* pD = workspace;
+  float* pU = workspace + (long long)nb * 4 * K;
+  MOS_CHECK_CUDA(launch_pdl(lora_grad_partial_kernel, dim3(nb), dim3(256), 0, STREAM(stream),
+                            reinterpret_cast<const __nv_bfloat16*>(x), (long long)ldx,
+                            reinterpret_cast<const __nv_bfloat16*>(dy), (long long)lddy, (long long)M, (int)K, (int)N, down,
+                            up, pD, pU));
+  MOS_CHECK_CUDA(launch_pdl(lora_grad_reduce_kernel, dim3(nblk(4LL * K, 256)), dim3(256), 0, STREAM(stream),
+                            (const float*)pD, nb, 4LL * K, alpha, (int)accumulate, d_down));
+  MOS_CHECK_CUDA(launch_pdl(lora_grad_reduce_kernel, dim3(nblk(4LL * N, 256)), dim3(256), 0, STREAM(stream),
+                            (const float*)pU, nb, 4LL * N, alpha, (int)accumulate, d_up));
+  return MOS_OK;
+}

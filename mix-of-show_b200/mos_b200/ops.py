@@ -274,3 +274,117 @@ def flat_adamw_step(params, grads, exp_avg, exp_avg_sq, group_end, group_lr, *, 
         ctypes.c_float(beta1), ctypes.c_float(beta2), ctypes.c_float(eps), ctypes.c_float(weight_decay),
         ctypes.c_int64(step), ctypes.c_float(grad_scale), ctypes.c_int32(emb_rows), ctypes.c_int32(emb_dim),
         ptr(norm_mean_out), _s()), 'mos_flat_adamw_step')
+
+
+# ------------------------------------------------------------------------------------------------ training step
+def _i32(v):
+    return ctypes.c_int32(int(v))
+
+
+def _i64(v):
+    return ctypes.c_int64(int(v))
+
+
+def attention_train(Q, K, Vt, out, lse2, *, batch, heads, head_dim, nq, nk, scale=None, pcols=None, pos=None, ldo=None):
+    scale = head_dim ** -0.5 if scale is None else scale
+    check(_lib.lib().mos_attention_fwd_train(
+        ptr(Q), ptr(K), ptr(Vt), ptr(out), _i64(out.stride(-2) if ldo is None else ldo), ptr(lse2), ptr(pcols),
+        ptr(pos), _i32(batch), _i32(heads), _i32(head_dim), _i32(nq), _i32(nk), _i32(Vt.shape[-1]),
+        ctypes.c_float(scale), _s()), 'mos_attention_fwd_train')
+    return out
+
+
+def attention_bwd(Q, K, V, dO, Qt, Kt, dOt, lse2, delta, dq, dk, dv, *, batch, heads, head_dim, nq, nk, scale=None,
+                  gcols=None, pos=None, lddq=None, lddk=None, lddv=None):
+    scale = head_dim ** -0.5 if scale is None else scale
+    check(_lib.lib().mos_attention_bwd(
+        ptr(Q), ptr(K), ptr(V), ptr(dO), ptr(Qt), ptr(Kt), ptr(dOt), ptr(lse2), ptr(delta), ptr(gcols), ptr(pos),
+        ptr(dq), _i64(dq.stride(-2) if lddq is None else lddq), ptr(dk), _i64(dk.stride(-2) if lddk is None else lddk),
+        ptr(dv), _i64(dv.stride(-2) if lddv is None else lddv), _i32(batch), _i32(heads), _i32(head_dim), _i32(nq),
+        _i32(nk), _i32(Qt.shape[-1]), _i32(Kt.shape[-1]), ctypes.c_float(scale), _s()), 'mos_attention_bwd')
+
+
+def heads_transpose(src, dst):
+    BH, R, DP = src.shape
+    check(_lib.lib().mos_heads_transpose(ptr(src), _i32(BH), _i32(R), _i32(DP), _i32(dst.shape[1]), _i32(dst.shape[2]),
+                                         ptr(dst), _s()), 'mos_heads_transpose')
+    return dst
+
+
+def attn_delta(dO, O, delta, *, batch, heads, head_dim, N, ldo=None, pcols=None, gcols=None):
+    check(_lib.lib().mos_attn_delta(ptr(dO), _i32(dO.shape[-1]), ptr(O), _i64(O.stride(-2) if ldo is None else ldo),
+                                    _i32(batch), _i32(heads), _i32(head_dim), _i32(N), ptr(pcols), ptr(gcols),
+                                    ptr(delta), _s()), 'mos_attn_delta')
+    return delta
+
+
+def groupnorm_bwd(x, dy, gamma, beta, dx, workspace, *, B, HW, C, eps, silu, add=None, ldx=None, lddy=None, lddx=None,
+                  ldadd=None):
+    check(_lib.lib().mos_groupnorm_bwd(
+        ptr(x), _i64(x.stride(-2) if ldx is None else ldx), ptr(dy), _i64(dy.stride(-2) if lddy is None else lddy),
+        _i32(B), _i32(HW), _i32(C), ptr(gamma), ptr(beta), ctypes.c_float(eps), _i32(1 if silu else 0), ptr(workspace),
+        _i32(workspace.numel()), ptr(add), _i64(0 if add is None else (add.stride(-2) if ldadd is None else ldadd)),
+        ptr(dx), _i64(dx.stride(-2) if lddx is None else lddx), _s()), 'mos_groupnorm_bwd')
+    return dx
+
+
+def layernorm_bwd(x, dy, gamma, dx, *, M, C, eps=1e-5, add=None, ldx=None, lddy=None, lddx=None, ldadd=None):
+    check(_lib.lib().mos_layernorm_bwd(
+        ptr(x), _i64(x.stride(-2) if ldx is None else ldx), ptr(dy), _i64(dy.stride(-2) if lddy is None else lddy),
+        _i64(M), _i32(C), ptr(gamma), ctypes.c_float(eps), ptr(add),
+        _i64(0 if add is None else (add.stride(-2) if ldadd is None else ldadd)), ptr(dx),
+        _i64(dx.stride(-2) if lddx is None else lddx), _s()), 'mos_layernorm_bwd')
+    return dx
+
+
+def geglu_fwd(z, y, *, M, H):
+    check(_lib.lib().mos_geglu_fwd(ptr(z), _i64(z.stride(-2)), _i64(M), _i32(H), ptr(y), _i64(y.stride(-2)), _s()),
+          'mos_geglu_fwd')
+    return y
+
+
+def geglu_bwd(z, dy, dz, *, M, H):
+    check(_lib.lib().mos_geglu_bwd(ptr(z), _i64(z.stride(-2)), ptr(dy), _i64(dy.stride(-2)), _i64(M), _i32(H), ptr(dz),
+                                   _i64(dz.stride(-2)), _s()), 'mos_geglu_bwd')
+    return dz
+
+
+def upsample2x_bwd(dy, dx, *, B, H, W, C, lddy=None, lddx=None):
+    check(_lib.lib().mos_upsample2x_bwd(ptr(dy), _i64(C if lddy is None else lddy), _i32(B), _i32(H), _i32(W), _i32(C),
+                                        ptr(dx), _i64(C if lddx is None else lddx), _s()), 'mos_upsample2x_bwd')
+    return dx
+
+
+def col2im_s2(dcol, dx, *, B, H, W, C, add=None, ldadd=None, lddx=None):
+    check(_lib.lib().mos_col2im_s2(ptr(dcol), _i32(B), _i32(H), _i32(W), _i32(C), ptr(add),
+                                   _i64(0 if add is None else (C if ldadd is None else ldadd)), ptr(dx),
+                                   _i64(C if lddx is None else lddx), _s()), 'mos_col2im_s2')
+    return dx
+
+
+def conv_out_bwd(dy, w, dx, *, B, H, W, C):
+    check(_lib.lib().mos_conv_out_bwd(ptr(dy), _i32(B), _i32(H), _i32(W), _i32(C), ptr(w), _i32(dy.shape[1]), ptr(dx),
+                                      _s()), 'mos_conv_out_bwd')
+    return dx
+
+
+def masked_mse(pred, target, mask, ws, loss, dpred, *, grad_scale=1.0):
+    B, Cc = pred.shape[0], pred.shape[1]
+    HW = pred[0, 0].numel()
+    check(_lib.lib().mos_masked_mse(ptr(pred), ptr(target), ptr(mask), _i32(B), _i32(Cc), _i32(HW),
+                                    ctypes.c_float(grad_scale), ptr(ws), ptr(loss), ptr(dpred), _s()), 'mos_masked_mse')
+    return loss
+
+
+def add_noise(x0, noise, timesteps_i32, alphas_cumprod, out):
+    B = x0.shape[0]
+    check(_lib.lib().mos_add_noise(ptr(x0), ptr(noise), ptr(timesteps_i32), ptr(alphas_cumprod), _i32(B),
+                                   _i64(x0[0].numel()), ptr(out), _s()), 'mos_add_noise')
+    return out
+
+
+def lora_grad(x, dy, down, up, alpha, workspace, d_down, d_up, *, M, K, N, ldx=None, lddy=None, accumulate=False):
+    check(_lib.lib().mos_lora_grad(
+        ptr(x), _i64(x.stride(-2) if ldx is None else ldx), ptr(dy), _i64(dy.stride(-2) if lddy is None else lddy),
+        _i64(M), _i32(K), _i32(N), ptr(down), ptr(up), ctypes.c_float(alpha), ptr(workspace), _i64(workspace.numel()),
+        _i32(1 if accumulate else 0), ptr(d_down), ptr(d_up), _s()), 'mos_lora_grad')
