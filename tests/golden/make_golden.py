@@ -42,8 +42,56 @@ def pack16(obj):
     return obj
 
 
+from oracle.train_ref import attn_reg_inputs  # noqa: E402
+
+
+def golden_attn_reg():
+    """T2: EDLoRATrainer.cal_attn_reg (trainer_edlora.py:263-313) executed unbound, + autograd gradients."""
+    import types
+    tr = ref_shims.load_reference_module('mixofshow/pipelines/trainer_edlora.py')
+    out = {}
+    for full in (True, False):
+        maps, masks, ids, pos = attn_reg_inputs()
+        for lst in maps.values():
+            for m in lst:
+                m.requires_grad_(True)
+        me = types.SimpleNamespace(get_all_concept_token_ids=lambda: [49408 + i for i in range(32)],
+                                   reg_full_identity=full, attn_reg_weight=0.01)
+        loss = tr.EDLoRATrainer.cal_attn_reg(me, maps, masks, ids)
+        loss.backward()
+        grads = {}
+        for place, lst in maps.items():
+            for m in lst:
+                r = int(math.sqrt(m.shape[1]))
+                g = m.grad.view(2, 8, r * r, 77)
+                gc = torch.stack([g[i][:, :, pos[i]] for i in range(2)])            # [b, 8, N, 2]
+                assert torch.equal(gc[:, :1].expand_as(gc), gc)                     # identical over heads
+                other = m.grad.clone().view(2, 8, r * r, 77)
+                for i in range(2):
+                    other[i][:, :, pos[i]] = 0
+                assert other.abs().max().item() == 0                                # only the two concept columns
+                if r in grads:
+                    assert torch.equal(grads[r], gc[:, 0])                          # identical over a group's layers
+                grads[r] = gc[:, 0].clone()
+        out['full' if full else 'masked'] = dict(loss=loss.detach(), grads=grads)
+    out['pos'] = pos
+    # a mask without zeros at the coarsest resolution makes the reference return NaN (skipped by the caller, :257)
+    maps, masks, ids, pos = attn_reg_inputs()
+    masks[:] = 1.0
+    me = types.SimpleNamespace(get_all_concept_token_ids=lambda: [49408 + i for i in range(32)],
+                               reg_full_identity=True, attn_reg_weight=0.01)
+    out['nan_when_mask_full'] = bool(torch.isnan(tr.EDLoRATrainer.cal_attn_reg(me, maps, masks, ids)))
+    return out
+
+
 def main():
     assert ref_shims.reference_available(), 'needs /root/reference'
+    if '--only-attn-reg' in sys.argv:
+        G = torch.load(OUT, weights_only=False)
+        G['attn_reg'] = golden_attn_reg()
+        torch.save(G, OUT)
+        print('updated attn_reg in', OUT)
+        return
     ed = ref_shims.load_reference_module('mixofshow/models/edlora.py')
     reg = ref_shims.load_reference_module('mixofshow/pipelines/pipeline_regionally_t2iadapter.py')
     gf = ref_shims.load_reference_module('gradient_fusion.py')
@@ -213,6 +261,7 @@ def main():
                                  height=128, width=256, boxes=boxes, boxes_overlap=boxes_overlap, out=out_r,
                                  unet_seed=0)
 
+    G['attn_reg'] = golden_attn_reg()
     torch.save(pack16(G), OUT)
     print('wrote', OUT, os.path.getsize(OUT) / 1e6, 'MB')
 

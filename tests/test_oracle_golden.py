@@ -170,3 +170,31 @@ def test_schedulers_self_consistency():
     xt = d.add_noise(x0, n, t)
     ac = d.alphas_cumprod[t].view(2, 1, 1, 1)
     assert torch.allclose(xt, ac.sqrt() * x0 + (1 - ac).sqrt() * n)
+
+
+def test_attn_reg_restatement_vs_reference_golden(G):
+    """oracle.train_ref.cal_attn_reg / concept_token_positions vs the reference's EDLoRATrainer.cal_attn_reg
+    (trainer_edlora.py:263-313): loss, autograd gradients on the two concept columns, integer positions, NaN rule."""
+    import math
+    from oracle import train_ref as tr
+    g = G['attn_reg']
+    for tag, full in (('full', True), ('masked', False)):
+        maps, masks, ids, pos = tr.attn_reg_inputs()
+        got_pos = tr.concept_token_positions(ids, 2, [49408 + i for i in range(32)])
+        assert got_pos == g['pos'] == pos                                       # integer quantity: bit exact
+        for lst in maps.values():
+            for m in lst:
+                m.requires_grad_(True)
+        loss = tr.cal_attn_reg(maps, masks, got_pos, reg_full_identity=full, attn_reg_weight=0.01)
+        assert abs(loss.item() - g[tag]['loss'].item()) <= 1e-6 * abs(g[tag]['loss'].item())
+        loss.backward()
+        for lst in maps.values():
+            for m in lst:
+                r = int(math.sqrt(m.shape[1]))
+                gr = m.grad.view(2, 8, r * r, 77)
+                gc = torch.stack([gr[i][0][:, pos[i]] for i in range(2)])
+                ref = g[tag]['grads'][r].float()
+                assert (gc - ref).abs().max().item() <= 1e-6 * ref.abs().max().item()
+    maps, masks, ids, pos = tr.attn_reg_inputs()
+    masks[:] = 1.0
+    assert bool(torch.isnan(tr.cal_attn_reg(maps, masks, pos))) == g['nan_when_mask_full'] is True
