@@ -240,6 +240,27 @@ int mos_lora_grad(const void* x, int64_t ldx, const void* dy, int64_t lddy, int6
                   const float* down, const float* up, float alpha, float* workspace, int64_t workspace_floats,
                   int32_t accumulate, float* d_down, float* d_up, void* stream);
 
+/* Attention regulariser (cal_attn_reg, trainer_edlora.py:263-313) restricted to the two concept-token columns.
+ * One resolution group per call: pcols_host_ptrs = host array of L device pointers [B*heads, res*res, 2] (the
+ * mos_attention_fwd_train outputs of the group's layers); mask fp32 [B, 1, MH, MW]; cm [B, res*res, 2] and
+ * stats[8] = {max0, max1, argmax0, argmax1, n_zero, weighted loss, S0, S1} are outputs.  mos_attn_reg_grad turns them
+ * into gcols [B, res*res, 2] (the gradient on every layer/head's probabilities of the group; zero if any group of
+ * stats_all [ngroups][8] is NaN, the reference's skip rule :257); mos_attn_reg_total: out[0] = mse + valid attention
+ * loss, out[1] = attention loss (NaN when skipped). */
+int mos_attn_reg_group(const float* const* pcols_host_ptrs, int32_t L, int32_t B, int32_t heads, int32_t res,
+                       const float* mask, int32_t MH, int32_t MW, int32_t full_identity, float weight, float* cm,
+                       float* stats, void* stream);
+int mos_attn_reg_grad(const float* cm, const float* mask, int32_t B, int32_t res, int32_t MH, int32_t MW,
+                      int32_t full_identity, float weight, const float* stats_all, int32_t ngroups, int32_t group,
+                      int32_t L, int32_t heads, float grad_scale, float* gcols, void* stream);
+int mos_attn_reg_total(const float* mse, const float* stats_all, int32_t ngroups, float* out, void* stream);
+
+/* Re-pack all LoRA pairs of the flat training state into the forward / backward GEMM operand layouts after an
+ * optimiser step.  table_dev: int64 [n_modules, 8] = {D fp32 [4,K] ptr, U fp32 [N,4] ptr, K, N, forward down rows
+ * (bf16, 4 rows of pitch K), forward up rows (fp32 [N,4], scaled by alpha), backward "down" (bf16 [16,N], rows
+ * 0..3 = U^T; may be 0), backward "up" (fp32 [K,4] = alpha D^T; may be 0)}. */
+int mos_lora_pack(const int64_t* table_dev, int32_t n_modules, float alpha, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -379,6 +379,162 @@ __global__ void lora_grad_reduce_kernel(const float* __restrict__ partial, int n
   grad[i] = (accumulate ? grad[i] : 0.f) + alpha * a;
 }
 
+
+// ------------------------------------------------------------------------------------------------ attention regulariser
+// cal_attn_reg (trainer_edlora.py:281-313) on the two concept-token columns only.  Per resolution group:
+//   cm[b, n, c] = mean over (layers of the group x heads) of pcols_l[(b, h), n, c]
+//   y_c = cm_c / max(cm_c)  (max over the whole batch);  gt = nearest-resized mask
+//   loss = w * ( full ? mean((y_1 - gt)^2) : mean_{gt==0} y_1   +   mean_{gt==0} y_0 )
+// stats[8] per group = {max0, max1, argmax0, argmax1 (int bits), nzero, loss, S0, S1}, S_c = sum_i g_i x_i (g = dloss/dy)
+struct RegPtrs {
+  const float* p[8];
+};
+
+__global__ void attnreg_mean_kernel(RegPtrs tab, int L, int heads, int B, int N, float* __restrict__ cm) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * N * 2) return;
+  const int c = (int)(idx & 1);
+  const long long bn = idx >> 1;
+  const int n = (int)(bn % N), b = (int)(bn / N);
+  float acc = 0.f;
+  for (int l = 0; l < L; ++l)
+    for (int h = 0; h < heads; ++h) acc += tab.p[l][(((long long)b * heads + h) * N + n) * 2 + c];
+  cm[idx] = acc / (float)(L * heads);
+}
+
+__device__ __forceinline__ float reg_gt(const float* __restrict__ mask, int b, int n, int res, int MH, int MW) {
+  const int y = n / res, x = n - y * res;
+  const int sy = min((int)floorf((float)y * ((float)MH / (float)res)), MH - 1);
+  const int sx = min((int)floorf((float)x * ((float)MW / (float)res)), MW - 1);
+  return mask[((long long)b * MH + sy) * MW + sx];
+}
+
+__global__ void __launch_bounds__(1024)
+attnreg_reduce_kernel(const float* __restrict__ cm, const float* __restrict__ mask, int B, int res, int MH, int MW,
+                      int full_identity, float weight, float* __restrict__ stats) {
+  __shared__ float sv[4][32];
+  __shared__ int si[2][32];
+  __shared__ float bc[8];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int N = res * res, total = B * N;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  // ---- phase 1: max / argmax per column, number of zero mask pixels
+  float m0 = -INFINITY, m1 = -INFINITY, nz = 0.f;
+  int a0 = 0x7fffffff, a1 = 0x7fffffff;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const float x0 = cm[2 * i], x1 = cm[2 * i + 1];
+    if (x0 > m0) { m0 = x0; a0 = i; }
+    if (x1 > m1) { m1 = x1; a1 = i; }
+    nz += (reg_gt(mask, i / N, i % N, res, MH, MW) == 0.f) ? 1.f : 0.f;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const float o0 = __shfl_xor_sync(0xffffffffu, m0, d), o1 = __shfl_xor_sync(0xffffffffu, m1, d);
+    const int b0 = __shfl_xor_sync(0xffffffffu, a0, d), b1 = __shfl_xor_sync(0xffffffffu, a1, d);
+    if (o0 > m0 || (o0 == m0 && b0 < a0)) { m0 = o0; a0 = b0; }
+    if (o1 > m1 || (o1 == m1 && b1 < a1)) { m1 = o1; a1 = b1; }
+    nz += __shfl_xor_sync(0xffffffffu, nz, d);
+  }
+  if (lane == 0) {
+    sv[0][warp] = m0; sv[1][warp] = m1; sv[2][warp] = nz;
+    si[0][warp] = a0; si[1][warp] = a1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float M0 = -INFINITY, M1 = -INFINITY, Z = 0.f;
+    int A0 = 0x7fffffff, A1 = 0x7fffffff;
+    for (int w = 0; w < nw; ++w) {
+      if (sv[0][w] > M0 || (sv[0][w] == M0 && si[0][w] < A0)) { M0 = sv[0][w]; A0 = si[0][w]; }
+      if (sv[1][w] > M1 || (sv[1][w] == M1 && si[1][w] < A1)) { M1 = sv[1][w]; A1 = si[1][w]; }
+      Z += sv[2][w];
+    }
+    bc[0] = M0; bc[1] = M1; bc[2] = Z;
+    stats[0] = M0; stats[1] = M1;
+    stats[2] = __int_as_float(A0); stats[3] = __int_as_float(A1);
+    stats[4] = Z;
+  }
+  __syncthreads();
+  const float M0 = bc[0], M1 = bc[1], Z = bc[2];
+  // ---- phase 2: loss and S_c = sum_i g_i x_i
+  float ls = 0.f, s0 = 0.f, s1 = 0.f;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const float x0 = cm[2 * i], x1 = cm[2 * i + 1];
+    const float gt = reg_gt(mask, i / N, i % N, res, MH, MW);
+    const float y0 = x0 / M0, y1 = x1 / M1;
+    const float zero = (gt == 0.f) ? 1.f : 0.f;
+    float g1;
+    if (full_identity) {
+      ls += (y1 - gt) * (y1 - gt) / (float)total;
+      g1 = 2.0f * (y1 - gt) / (float)total;
+    } else {
+      ls += zero * y1 / Z;
+      g1 = zero / Z;
+    }
+    ls += zero * y0 / Z;
+    s0 += (zero / Z) * x0;
+    s1 += g1 * x1;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    ls += __shfl_xor_sync(0xffffffffu, ls, d);
+    s0 += __shfl_xor_sync(0xffffffffu, s0, d);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+  }
+  __syncthreads();
+  if (lane == 0) { sv[0][warp] = ls; sv[1][warp] = s0; sv[2][warp] = s1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f, c = 0.f;
+    for (int w = 0; w < nw; ++w) { a += sv[0][w]; b += sv[1][w]; c += sv[2][w]; }
+    stats[5] = weight * a;   // NaN when Z == 0, as the reference's mean over an empty selection
+    stats[6] = b;
+    stats[7] = c;
+  }
+}
+
+// gcols[b, n, c] = valid * w * (g_c / max_c - [i == argmax_c] S_c / max_c^2) / (heads * L)
+__global__ void attnreg_grad_kernel(const float* __restrict__ cm, const float* __restrict__ mask, int B, int res,
+                                    int MH, int MW, int full_identity, float weight, const float* __restrict__ stats_all,
+                                    int ngroups, int group, int L, int heads, float grad_scale,
+                                    float* __restrict__ gcols) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int N = res * res, total = B * N;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  bool valid = true;
+  for (int g = 0; g < ngroups; ++g) valid = valid && (stats_all[g * 8 + 4] > 0.f);
+  const float* st = stats_all + group * 8;
+  const float M0 = st[0], M1 = st[1], Z = st[4], S0 = st[6], S1 = st[7];
+  const int A0 = __float_as_int(st[2]), A1 = __float_as_int(st[3]);
+  const float gt = reg_gt(mask, i / N, i % N, res, MH, MW);
+  const float zero = (gt == 0.f) ? 1.f : 0.f;
+  const float x1 = cm[2 * i + 1];
+  const float g1 = full_identity ? 2.0f * (x1 / M1 - gt) / (float)total : zero / Z;
+  const float g0 = zero / Z;
+  const float k = valid ? grad_scale * weight / (float)(heads * L) : 0.f;
+  float d0 = g0 / M0 - (i == A0 ? S0 / (M0 * M0) : 0.f);
+  float d1 = g1 / M1 - (i == A1 ? S1 / (M1 * M1) : 0.f);
+  if (!valid) d0 = d1 = 0.f;   // avoid 0 * NaN
+  gcols[2 * i] = k * d0;
+  gcols[2 * i + 1] = k * d1;
+}
+
+// out[0] = mse + (valid ? sum_g loss_g : 0);  out[1] = sum_g loss_g (NaN when some resized mask has no zero, :257)
+__global__ void attnreg_total_kernel(const float* __restrict__ mse, const float* __restrict__ stats_all, int ngroups,
+                                     float* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float a = 0.f;
+  for (int g = 0; g < ngroups; ++g) a += stats_all[g * 8 + 5];
+  out[1] = a;
+  out[0] = mse[0] + (isnan(a) ? 0.f : a);
+}
+
 }  // namespace mos
 
 using namespace mos;
@@ -490,5 +646,38 @@ extern "C" int mos_lora_grad(const void* x, int64_t ldx, const void* dy, int64_t
                             (const float*)pD, nb, 4LL * K, alpha, (int)accumulate, d_down));
   MOS_CHECK_CUDA(launch_pdl(lora_grad_reduce_kernel, dim3(nblk(4LL * N, 256)), dim3(256), 0, STREAM(stream),
                             (const float*)pU, nb, 4LL * N, alpha, (int)accumulate, d_up));
+  return MOS_OK;
+}
+
+
+extern "C" int mos_attn_reg_group(const float* const* pcols_host_ptrs, int32_t L, int32_t B, int32_t heads, int32_t res,
+                                  const float* mask, int32_t MH, int32_t MW, int32_t full_identity, float weight,
+                                  float* cm, float* stats, void* stream) {
+  MOS_CHECK_ARG(pcols_host_ptrs && mask && cm && stats && L >= 1 && L <= 8 && B > 0 && res > 0,
+                "mos_attn_reg_group: bad arguments (1 <= layers per group <= 8)");
+  RegPtrs tab;
+  for (int l = 0; l < 8; ++l) tab.p[l] = l < L ? pcols_host_ptrs[l] : nullptr;
+  const int N = res * res;
+  MOS_CHECK_CUDA(launch_pdl(attnreg_mean_kernel, dim3(nblk((long long)B * N * 2, 256)), dim3(256), 0, STREAM(stream), tab,
+                            (int)L, (int)heads, (int)B, N, cm));
+  MOS_CHECK_CUDA(launch_pdl(attnreg_reduce_kernel, dim3(1), dim3(1024), 0, STREAM(stream), (const float*)cm, mask, (int)B,
+                            (int)res, (int)MH, (int)MW, (int)full_identity, weight, stats));
+  return MOS_OK;
+}
+
+extern "C" int mos_attn_reg_grad(const float* cm, const float* mask, int32_t B, int32_t res, int32_t MH, int32_t MW,
+                                 int32_t full_identity, float weight, const float* stats_all, int32_t ngroups,
+                                 int32_t group, int32_t L, int32_t heads, float grad_scale, float* gcols,
+                                 void* stream) {
+  MOS_CHECK_ARG(cm && mask && stats_all && gcols && group >= 0 && group < ngroups, "mos_attn_reg_grad: bad arguments");
+  MOS_CHECK_CUDA(launch_pdl(attnreg_grad_kernel, dim3(nblk((long long)B * res * res, 256)), dim3(256), 0, STREAM(stream),
+                            cm, mask, (int)B, (int)res, (int)MH, (int)MW, (int)full_identity, weight, stats_all,
+                            (int)ngroups, (int)group, (int)L, (int)heads, grad_scale, gcols));
+  return MOS_OK;
+}
+
+extern "C" int mos_attn_reg_total(const float* mse, const float* stats_all, int32_t ngroups, float* out, void* stream) {
+  MOS_CHECK_ARG(mse && stats_all && out && ngroups >= 1, "mos_attn_reg_total: bad arguments");
+  MOS_CHECK_CUDA(launch_pdl(attnreg_total_kernel, dim3(1), dim3(32), 0, STREAM(stream), mse, stats_all, (int)ngroups, out));
   return MOS_OK;
 }

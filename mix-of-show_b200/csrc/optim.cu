@@ -58,6 +58,37 @@ __global__ void row_norm_mean_kernel(const float* __restrict__ p, int rows, int 
   if (threadIdx.x == 0) norm_out[0] = total / (float)rows;
 }
 
+
+// Re-pack every LoRA pair of the flat training state into the operand layouts of the forward and backward GEMMs
+// (one launch per optimiser step).  table [n_mod][8] = {D fp32 [4,K], U fp32 [N,4], K, N,
+//   fwd down rows (bf16, 4 rows of pitch K inside the module group's [16,K] block),
+//   fwd up rows (fp32 [N,4], pre-scaled by alpha),
+//   bwd "down" (bf16 [16,N]: rows 0..3 = U^T), bwd "up" (fp32 [K,4] = alpha D^T)}.
+__global__ void lora_pack_kernel(const long long* __restrict__ table, float alpha) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long* e = table + (long long)blockIdx.y * 8;
+  const float* D = reinterpret_cast<const float*>(e[0]);
+  const float* U = reinterpret_cast<const float*>(e[1]);
+  const int K = (int)e[2], N = (int)e[3];
+  __nv_bfloat16* fdown = reinterpret_cast<__nv_bfloat16*>(e[4]);
+  float* fup = reinterpret_cast<float*>(e[5]);
+  __nv_bfloat16* bdown = reinterpret_cast<__nv_bfloat16*>(e[6]);
+  float* bup = reinterpret_cast<float*>(e[7]);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 4 * K; i += gridDim.x * blockDim.x) {
+    const int r = i / K, k = i - r * K;
+    const float v = D[i];
+    fdown[i] = __float2bfloat16(v);
+    if (bup) bup[k * 4 + r] = alpha * v;
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 4 * N; i += gridDim.x * blockDim.x) {
+    const int n = i >> 2, r = i & 3;
+    const float v = U[i];
+    fup[i] = alpha * v;
+    if (bdown) bdown[(long long)r * N + n] = __float2bfloat16(v);
+  }
+}
+
 }  // namespace mos
 
 using namespace mos;
@@ -88,5 +119,13 @@ extern "C" int mos_flat_adamw_step(float* params, const float* grads, float* exp
     row_norm_mean_kernel<<<1, 256, 0, stream>>>(params, emb_rows, emb_dim, norm_mean_out);
     MOS_CHECK_LAUNCH();
   }
+  return MOS_OK;
+}
+
+
+extern "C" int mos_lora_pack(const int64_t* table_dev, int32_t n_modules, float alpha, void* stream) {
+  MOS_CHECK_ARG(table_dev && n_modules > 0, "mos_lora_pack: bad arguments");
+  MOS_CHECK_CUDA(launch_pdl(lora_pack_kernel, dim3(8, (unsigned)n_modules), dim3(256), 0,
+                            reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const long long*>(table_dev), alpha));
   return MOS_OK;
 }

@@ -388,3 +388,26 @@ def lora_grad(x, dy, down, up, alpha, workspace, d_down, d_up, *, M, K, N, ldx=N
         ptr(x), _i64(x.stride(-2) if ldx is None else ldx), ptr(dy), _i64(dy.stride(-2) if lddy is None else lddy),
         _i64(M), _i32(K), _i32(N), ptr(down), ptr(up), ctypes.c_float(alpha), ptr(workspace), _i64(workspace.numel()),
         _i32(1 if accumulate else 0), ptr(d_down), ptr(d_up), _s()), 'mos_lora_grad')
+
+
+def attn_reg_group(pcols_list, mask, cm, stats, *, B, heads, res, full_identity, weight):
+    arr = (ctypes.c_void_p * len(pcols_list))(*[t.data_ptr() for t in pcols_list])
+    check(_lib.lib().mos_attn_reg_group(arr, _i32(len(pcols_list)), _i32(B), _i32(heads), _i32(res), ptr(mask),
+                                        _i32(mask.shape[-2]), _i32(mask.shape[-1]), _i32(1 if full_identity else 0),
+                                        ctypes.c_float(weight), ptr(cm), ptr(stats), _s()), 'mos_attn_reg_group')
+
+
+def attn_reg_grad(cm, mask, stats_all, gcols, *, B, res, full_identity, weight, group, L, heads, grad_scale=1.0):
+    check(_lib.lib().mos_attn_reg_grad(ptr(cm), ptr(mask), _i32(B), _i32(res), _i32(mask.shape[-2]),
+                                       _i32(mask.shape[-1]), _i32(1 if full_identity else 0), ctypes.c_float(weight),
+                                       ptr(stats_all), _i32(stats_all.shape[0]), _i32(group), _i32(L), _i32(heads),
+                                       ctypes.c_float(grad_scale), ptr(gcols), _s()), 'mos_attn_reg_grad')
+
+
+def attn_reg_total(mse, stats_all, out):
+    check(_lib.lib().mos_attn_reg_total(ptr(mse), ptr(stats_all), _i32(stats_all.shape[0]), ptr(out), _s()),
+          'mos_attn_reg_total')
+
+
+def lora_pack(table_dev, n_modules, alpha):
+    check(_lib.lib().mos_lora_pack(ptr(table_dev), _i32(n_modules), ctypes.c_float(alpha), _s()), 'mos_lora_pack')
