@@ -110,3 +110,67 @@ def test_optimizer_step_changes_forward(cuda):
         eng.optimizer_step()
     print('    loss over 6 steps on a fixed batch:', ' '.join(f'{l:.5f}' for l in losses))
     assert losses[-1] < losses[0]
+
+
+def test_train_step_full_sd15_topology(cuda):
+    """BASELINE config 2 shape (SD1.5 topology, 64x64 latents; batch 2 here): loss and flat LoRA gradient vs the fp32
+    oracle differentiated by autograd — the oracle runs on the GPU in true fp32 (TF32 off, conftest) to finish in
+    seconds.  All 16 cross-attention layers feed the attention regulariser (4 resolution groups, as the reference)."""
+    from mixofshow.utils.ptp_util import AttentionStore
+    from mos_b200.engine import ehs_to_layer_major
+    from mos_b200.train_engine import TrainEngine
+    from oracle import inject, train_ref
+    from oracle import unet as ou
+    from oracle.schedulers import DDPMScheduler
+    ref = ou.build_unet(0)
+    lora = inject.random_lora_state(ref, seed=10)
+    sd = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+    ref = ref.cuda()
+    leaves = {k: v.clone().cuda().requires_grad_(True) for k, v in lora.items()}
+    inject.inject_lora(ref, leaves, 1.0)
+    ctl = AttentionStore(training=True)
+    assert inject.install_control_processors(ref, ctl) == 16
+    g = torch.Generator().manual_seed(5)
+    B, H = 2, 64
+    x0, noise = torch.randn(B, 4, H, H, generator=g), torch.randn(B, 4, H, H, generator=g)
+    t = torch.tensor([77, 640])
+    ehs = torch.randn(B, 16, 77, 768, generator=g).to(torch.bfloat16).float()
+    masks = torch.zeros(B, 1, H, H)
+    masks[:, :, 12:50, 16:44] = 1.0
+    pos = [[4, 5], [2, 3]]
+    noisy = DDPMScheduler().add_noise(x0, noise, t)
+    loss, pred, attn = train_ref.train_loss(ref, ctl, noisy.cuda(), t.cuda(), ehs.cuda(), noise.cuda(), masks.cuda(),
+                                            masks.cuda(), pos, reg_full_identity=True, attn_reg_weight=0.01)
+    loss.backward()
+    ref_grads = {k: v.grad.detach().clone() for k, v in leaves.items()}
+    del ref, ctl, pred
+    torch.cuda.empty_cache()
+    eng = TrainEngine(sd, B, H, H, lora=lora, lora_alpha=1.0, attn_reg_weight=0.01, reg_full_identity=True)
+    out = eng.forward_backward(x0.cuda(), noise.cuda(), t.cuda(), ehs_to_layer_major(ehs.cuda()), masks.cuda(),
+                               token_pos=pos)
+    torch.cuda.synchronize()
+    print(f'full SD1.5 train step: loss {out[0].item():.6f} vs oracle {loss.item():.6f}; attn {out[1].item():.6f} vs '
+          f'{attn.item():.6f}')
+    assert abs(out[0].item() - loss.item()) < 2e-2 * abs(loss.item())
+    assert abs(out[1].item() - attn.item()) < 3e-2 * abs(attn.item())
+    fg, fr = [], []
+    for m, (gD, gU) in eng.lora_grad_dict().items():
+        fg += [gD.flatten(), gU.flatten()]
+        fr += [ref_grads[m + '.lora_down.weight'].flatten(), ref_grads[m + '.lora_up.weight'].flatten()]
+    fg, fr = torch.cat(fg), torch.cat(fr)
+    cos = torch.nn.functional.cosine_similarity(fg, fr, dim=0).item()
+    print(f'    flat LoRA gradient ({fg.numel()} params): rel-L2 {rel_l2(fg, fr):.3e}, cosine {cos:.5f}')
+    assert fg.numel() == 797184                      # SURVEY.md §8a: UNet `where: Attention` rank-4 parameter count
+    assert cos > 0.99 and rel_l2(fg, fr) < 0.12
+    # timing of the step (forward + loss + backward + AdamW), eager launches
+    import time
+    for _ in range(2):
+        eng.forward_backward(x0.cuda(), noise.cuda(), t.cuda(), ehs_to_layer_major(ehs.cuda()), masks.cuda())
+        eng.optimizer_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        eng.forward_backward(x0.cuda(), noise.cuda(), t.cuda(), ehs_to_layer_major(ehs.cuda()), masks.cuda())
+        eng.optimizer_step()
+    torch.cuda.synchronize()
+    print(f'    train step (B={B}, eager): {(time.perf_counter() - t0) / 5 * 1e3:.1f} ms, {eng.launches} forward launches')
