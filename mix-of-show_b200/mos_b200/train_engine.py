@@ -31,7 +31,10 @@ def _key(t):
 class TrainEngine(UNetEngine):
     def __init__(self, state_dict, batch, height, width, *, lora, lora_alpha=1.0, attn_reg_weight=0.01,
                  reg_full_identity=True, lr=1e-4, **kw):
-        kw.pop('use_graph', None)
+        self.use_train_graph = bool(kw.pop('use_graph', True))
+        self.tgraph = None
+        self._tgraphs = {}
+        self._accumulate = False
         super().__init__(state_dict, batch, height, width, lora=lora, lora_alpha=lora_alpha, use_graph=False, **kw)
         self.attn_reg_weight = attn_reg_weight
         self.reg_full_identity = reg_full_identity
@@ -49,6 +52,7 @@ class TrainEngine(UNetEngine):
         self.mse = torch.zeros(1, device=self.dev)
         self.loss_out = torch.zeros(2, device=self.dev)       # [total loss, attention loss (NaN when skipped)]
         self.mse_ws = torch.zeros(2 * B, device=self.dev)
+        self.x0 = torch.zeros(B, 4, H, W, device=self.dev)
 
     @staticmethod
     def _alphas_cumprod(n=1000, beta_start=0.00085, beta_end=0.012):
@@ -301,7 +305,8 @@ class TrainEngine(UNetEngine):
 
     def _lora_grad(self, m, x, dy, M, ldx=None, lddy=None):
         D, U, gD, gU, K, N = self.lora_views[m]
-        ops.lora_grad(x, dy, D, U, self.lora_alpha, self._lg_ws(M, K, N), gD, gU, M=M, K=K, N=N, ldx=ldx, lddy=lddy)
+        ops.lora_grad(x, dy, D, U, self.lora_alpha, self._lg_ws(M, K, N), gD, gU, M=M, K=K, N=N, ldx=ldx, lddy=lddy,
+                      accumulate=self._accumulate)
 
     def _attn_bwd(self, Q, K, V, ao, lse, dO, dq, dk, dv, N, nk, d, pcols=None, gcols=None):
         B, Hh = self.B, self.heads
@@ -554,7 +559,8 @@ class TrainEngine(UNetEngine):
         self._leftover = grads      # only the conv_in output gradient remains (the latents need no gradient)
 
     # ------------------------------------------------------------------------------------------ public API
-    def forward_backward(self, latents, noise, timesteps, ehs_layers, masks, loss_mask=None, token_pos=None):
+    def forward_backward(self, latents, noise, timesteps, ehs_layers, masks, loss_mask=None, token_pos=None,
+                         accumulate=False):
         """One forward + loss + backward.  latents (x0) / noise fp32 [B,4,H,W]; timesteps int [B]; ehs_layers bf16
         [16,B,77,768]; masks / loss_mask [B,1,H,W] (trainer_edlora.py:246-252); token_pos: B pairs of concept-token
         positions (:270-279).  Returns the device tensor [total loss, attention loss]."""
@@ -566,12 +572,37 @@ class TrainEngine(UNetEngine):
         self.loss_mask.copy_(masks if loss_mask is None else loss_mask)
         if token_pos is not None:
             self.pos.copy_(torch.as_tensor(token_pos, dtype=torch.int32))
-        ops.add_noise(latents.to(self.dev, F32).contiguous(), self.target, self.t_i32, self.alphas_cumprod,
-                      self.in_latents)
+        self.x0.copy_(latents)
+        self._accumulate = bool(accumulate)
+        if not self.use_train_graph:
+            self._step()
+            return self.loss_out
+        self.tgraph = self._tgraphs.get(self._accumulate)
+        if self.tgraph is None:
+            # warm-up (allocates every saved-activation / gradient buffer, sets kernel attributes), then capture the
+            # whole forward + loss + backward (~2500 launches) in one CUDA graph
+            saved = self.state.grads.clone() if self._accumulate else None   # the warm-up run must not count
+            torch.cuda.synchronize()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._step()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self.tgraph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.tgraph):
+                self._step()
+            self._tgraphs[self._accumulate] = self.tgraph
+            if saved is not None:
+                self.state.grads.copy_(saved)
+        self.tgraph.replay()
+        return self.loss_out
+
+    def _step(self):
+        ops.add_noise(self.x0, self.target, self.t_i32, self.alphas_cumprod, self.in_latents)
         self._run_train()
         self._loss()
         self._backward()
-        return self.loss_out
 
     def optimizer_step(self, grad_scale=1.0):
         from .dp import optimizer_step

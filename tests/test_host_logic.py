@@ -109,3 +109,21 @@ def test_product_bind_concept_prompt_and_boxes_match_reference_golden():
     for (H, W, ds, tag), idx in r['box_index_kat'].items():
         boxes = r['boxes'] if tag == 'abut' else r['boxes_overlap']
         assert [region_box_indices(b, H // ds, W // ds) for b in boxes] == [tuple(i) for i in idx]
+
+
+def test_train_loop_host_logic():
+    """train_edlora.py:73-75 total_iter and the linear schedule (diffusers get_scheduler('linear', warmup 0))."""
+    import pytest
+    import train_edlora as te
+    assert te.total_iterations(1000, 4, 1, 1) == 250.0
+    assert te.total_iterations(100, 8, 8, 1) == 100 / 64            # fractional, as the reference computes it
+    assert te.linear_lr(1e-4, 0, 250) == 1e-4
+    assert te.linear_lr(1e-4, 125, 250) == pytest.approx(5e-5)
+    assert te.linear_lr(1e-4, 250, 250) == 0.0 and te.linear_lr(1e-4, 300, 250) == 0.0
+    from mixofshow.pipelines.trainer_edlora import EDLoRATrainer
+    cfg = {'text_embedding': {'enable_tuning': True, 'lr': 1e-3}, 'text_encoder': {'enable_tuning': False},
+           'unet': {'enable_tuning': True, 'lr': 1e-4, 'lora_cfg': {'rank': 4, 'alpha': 1.0, 'where': 'Attention'}}}
+    with pytest.raises(NotImplementedError):
+        EDLoRATrainer({}, 2, finetune_cfg=cfg)
+    with pytest.raises(ValueError):
+        EDLoRATrainer({}, 2, finetune_cfg=None)
