@@ -47,6 +47,17 @@ def allreduce_flat(state, loss_value=0.0, norm_mean=0.0, group=None):
     return 1.0 / world, logs[0] / world, logs[1] / world
 
 
+def allreduce_flat_device(state, loss_dev=None, group=None):
+    """Same single collective without any host synchronisation: the loss rides on the wire as a device scalar and is
+    read later from state.grads[state.n] (divide by the world size).  Returns grad_scale = 1 / world."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if loss_dev is not None:
+        state.grads[state.n:state.n + 1].copy_(loss_dev.reshape(1))
+    if world > 1:
+        dist.all_reduce(state.grads, op=dist.ReduceOp.SUM, group=group)
+    return 1.0 / world
+
+
 def optimizer_step(state, grad_scale, norm_out=None):
     """AdamW on the flat state (CUDA only: there is no CPU fallback for the arithmetic)."""
     from . import ops
