@@ -76,6 +76,12 @@ int mos_gemm_bf16(const mos_gemm_args* args, void* stream);
  * prefetch done, accumulators ready, accumulators drained, tile written]. */
 int mos_debug_set_timeline(void* buf);
 
+/* Profiling aid for mos_attention_fwd: register a device buffer of 256 uint64 (or NULL to disable); CTA (0,0) of every
+ * subsequent launch stores clock64 stamps for its first 32 kv tiles: softmax warp 0 at [j*4 + k] (k: before s_full wait,
+ * S visible, softmax pass done, P published) and the MMA thread at [128 + j*4 + k] (k: K/V landed, S buffer free and
+ * S_j issued next, before p_full wait, P visible and PV_j issued next). */
+int mos_debug_set_attn_timeline(void* buf);
+
 /* Sum split-K partials and apply bias / bias_batch / residual -> bf16 [M, ldc]. */
 int mos_splitk_finalize(const float* partial, int32_t splits, int64_t M, int64_t N, const float* bias,
                         const float* bias_batch, int64_t rows_per_batch, int64_t bias_batch_ld,

@@ -286,97 +286,146 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, int DP, 
 // ------------------------------------------------------------------------------------------------ LoRA gradients
 // y = x W^T + alpha (x D^T) U^T  (edlora.py:244-246), dY given:
 //   dU[n, r] = alpha sum_m dY[m, n] t[m, r],  t = x D^T ;   dD[r, k] = alpha sum_m s[m, r] x[m, k],  s = dY U
-// One block = LG_ROWS rows; partial sums per block, reduced in a fixed order by lora_grad_reduce_kernel.
-constexpr int LG_ROWS = 64;
+// Both gradients are skinny reductions over the M rows.  One block owns a slab of R rows (R chosen on the host so that
+// at most 64 blocks exist):
+//   step 1  t, s of every slab row -> smem (one thread per row; D and U staged in smem, read as broadcasts)
+//   step 2  thread (row group g of 4, lane) owns an 8-column chunk of x (-> dD) or dY (-> dU): one 128-bit load and 32
+//           FMAs per row; the 4 row groups are summed in a fixed order through smem
+// and writes its partial [4K + 4N]; lora_grad_reduce_kernel sums the <= 64 partials in a fixed order (bitwise
+// reproducible).  (The first version spent 16.6 ms of a 49.7 ms training step here; profiles/README.md.)
+constexpr int LG_THREADS = 256;
+constexpr int LG_MAX_BLOCKS = 64;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(LG_THREADS)
 lora_grad_partial_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ dy,
                          long long lddy, long long M, int K, int N, const float* __restrict__ down,
-                         const float* __restrict__ up, float* __restrict__ pD, float* __restrict__ pU) {
-  __shared__ float ts[LG_ROWS][8];  // t[0..3], s[0..3]
+                         const float* __restrict__ up, int R, float* __restrict__ partial) {
+  extern __shared__ float lg_smem[];
+  float* sD = lg_smem;                 // [4][K]
+  float* sU = sD + 4 * K;              // [N][4]
+  float* ts = sU + 4 * N;              // [R][8]: t[0..3], s[0..3]
+  float* red = ts + (long long)R * 8;  // [4 groups][32 values][64 lanes]
   pdl_wait();
   pdl_launch_dependents();
-  const long long m0 = (long long)blockIdx.x * LG_ROWS;
-  const int rows = (int)min((long long)LG_ROWS, M - m0);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int r = warp; r < LG_ROWS; r += 8) {
-    float t[4] = {0.f, 0.f, 0.f, 0.f}, s[4] = {0.f, 0.f, 0.f, 0.f};
-    if (r < rows) {
-      const __nv_bfloat16* xr = x + (m0 + r) * ldx;
-      for (int k = lane * 8; k < K; k += 256) {
-        float v[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(xr + k)), v);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float* dp = down + (long long)q * K + k;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) t[q] += v[i] * __ldg(dp + i);
-        }
-      }
-      const __nv_bfloat16* dr = dy + (m0 + r) * lddy;
-      for (int n = lane * 8; n < N; n += 256) {
-        float v[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(dr + n)), v);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 u = __ldg(reinterpret_cast<const float4*>(up + (long long)(n + i) * 4));
-          s[0] += v[i] * u.x;
-          s[1] += v[i] * u.y;
-          s[2] += v[i] * u.z;
-          s[3] += v[i] * u.w;
-        }
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) {
-        t[q] += __shfl_xor_sync(0xffffffffu, t[q], d);
-        s[q] += __shfl_xor_sync(0xffffffffu, s[q], d);
-      }
-    }
-    if (lane == 0) {
+  const int tid = threadIdx.x;
+  const long long m0 = (long long)blockIdx.x * R;
+  const int rows = (int)min((long long)R, M - m0);
+  for (int i = tid * 4; i < 4 * K; i += LG_THREADS * 4)
+    *reinterpret_cast<float4*>(sD + i) = __ldg(reinterpret_cast<const float4*>(down + i));
+  for (int i = tid * 4; i < 4 * N; i += LG_THREADS * 4)
+    *reinterpret_cast<float4*>(sU + i) = __ldg(reinterpret_cast<const float4*>(up + i));
+  __syncthreads();
+  // ---- step 1: t = x D^T, s = dY U for every row of the slab
+  for (int r = tid; r < rows; r += LG_THREADS) {
+    float t[4] = {0.f, 0.f, 0.f, 0.f}, sv[4] = {0.f, 0.f, 0.f, 0.f};
+    const __nv_bfloat16* xr = x + (m0 + r) * ldx;
+#pragma unroll 4
+    for (int k = 0; k < K; k += 8) {
+      float v[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(xr + k)), v);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        ts[r][q] = t[q];
-        ts[r][4 + q] = s[q];
+        const float4 d0 = *reinterpret_cast<const float4*>(sD + q * K + k);
+        const float4 d1 = *reinterpret_cast<const float4*>(sD + q * K + k + 4);
+        t[q] += v[0] * d0.x + v[1] * d0.y + v[2] * d0.z + v[3] * d0.w + v[4] * d1.x + v[5] * d1.y + v[6] * d1.z +
+                v[7] * d1.w;
       }
     }
+    const __nv_bfloat16* dr = dy + (m0 + r) * lddy;
+#pragma unroll 4
+    for (int n = 0; n < N; n += 8) {
+      float v[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(dr + n)), v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 u = *reinterpret_cast<const float4*>(sU + (n + i) * 4);
+        sv[0] += v[i] * u.x;
+        sv[1] += v[i] * u.y;
+        sv[2] += v[i] * u.z;
+        sv[3] += v[i] * u.w;
+      }
+    }
+    *reinterpret_cast<float4*>(ts + r * 8) = make_float4(t[0], t[1], t[2], t[3]);
+    *reinterpret_cast<float4*>(ts + r * 8 + 4) = make_float4(sv[0], sv[1], sv[2], sv[3]);
   }
   __syncthreads();
-  float* pd = pD + (long long)blockIdx.x * 4 * K;
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    float a[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int r = 0; r < rows; ++r) {
-      const float xv = __bfloat162float(x[(m0 + r) * ldx + k]);
+  // ---- step 2: dD[q, k] = sum_r s[r, q] x[r, k];  dU[n, q] = sum_r t[r, q] dY[r, n]
+  const int g = tid >> 6, ln = tid & 63;
+  const int CK = K / 8, CH = CK + N / 8;
+  const int rpg = R / 4;
+  const int r_lo = g * rpg, r_hi = min(rows, (g + 1) * rpg);
+  float* pblk = partial + (long long)blockIdx.x * 4 * (K + N);
+  for (int c0 = 0; c0 < CH; c0 += 64) {
+    const int c = c0 + ln;
+    const bool active = c < CH;
+    float acc[4][8];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) a[q] += ts[r][4 + q] * xv;
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[q][i] = 0.f;
+    if (active) {
+      const bool isx = c < CK;
+      const __nv_bfloat16* base = isx ? x + m0 * ldx + c * 8 : dy + m0 * lddy + (c - CK) * 8;
+      const long long ld = isx ? ldx : lddy;
+      const float* w = ts + (isx ? 4 : 0);
+#pragma unroll 4
+      for (int r = r_lo; r < r_hi; ++r) {
+        float v[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(base + r * ld)), v);
+        const float4 wr = *reinterpret_cast<const float4*>(w + r * 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc[0][i] += wr.x * v[i];
+          acc[1][i] += wr.y * v[i];
+          acc[2][i] += wr.z * v[i];
+          acc[3][i] += wr.w * v[i];
+        }
+      }
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) pd[(long long)q * K + k] = a[q];
-  }
-  float* pu = pU + (long long)blockIdx.x * 4 * N;
-  for (int n = threadIdx.x; n < N; n += blockDim.x) {
-    float a[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int r = 0; r < rows; ++r) {
-      const float dv = __bfloat162float(dy[(m0 + r) * lddy + n]);
+    for (int q = 0; q < 4; ++q)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) a[q] += ts[r][q] * dv;
+      for (int i = 0; i < 8; ++i) red[(g * 32 + q * 8 + i) * 64 + ln] = acc[q][i];
+    __syncthreads();
+    if (g == 0 && active) {
+      float sum[4][8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int j = q * 8 + i;
+          sum[q][i] = ((red[j * 64 + ln] + red[(32 + j) * 64 + ln]) + red[(64 + j) * 64 + ln]) + red[(96 + j) * 64 + ln];
+        }
+      if (c < CK) {   // dD, layout [4][K]
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float* d = pblk + (long long)q * K + c * 8;
+          *reinterpret_cast<float4*>(d) = make_float4(sum[q][0], sum[q][1], sum[q][2], sum[q][3]);
+          *reinterpret_cast<float4*>(d + 4) = make_float4(sum[q][4], sum[q][5], sum[q][6], sum[q][7]);
+        }
+      } else {        // dU, layout [N][4]
+        float* d = pblk + 4LL * K + (long long)(c - CK) * 32;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<float4*>(d + i * 4) = make_float4(sum[0][i], sum[1][i], sum[2][i], sum[3][i]);
+      }
     }
-    *reinterpret_cast<float4*>(pu + (long long)n * 4) = make_float4(a[0], a[1], a[2], a[3]);
+    __syncthreads();
   }
 }
 
-// grad[i] (+)= alpha * sum_blk partial[blk][i]
-__global__ void lora_grad_reduce_kernel(const float* __restrict__ partial, int nblk_, long long n, float alpha,
-                                        int accumulate, float* __restrict__ grad) {
+// grad[i] (+)= alpha * sum_blk partial[blk][i];  i < n_down -> d_down, else d_up
+__global__ void lora_grad_reduce_kernel(const float* __restrict__ partial, int nblk_, long long n_down, long long n,
+                                        float alpha, int accumulate, float* __restrict__ d_down,
+                                        float* __restrict__ d_up) {
   pdl_wait();
   pdl_launch_dependents();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float a = 0.f;
   for (int b = 0; b < nblk_; ++b) a += partial[(long long)b * n + i];
-  grad[i] = (accumulate ? grad[i] : 0.f) + alpha * a;
+  float* g = i < n_down ? d_down + i : d_up + (i - n_down);
+  *g = (accumulate ? *g : 0.f) + alpha * a;
 }
 
 
@@ -633,19 +682,26 @@ extern "C" int mos_lora_grad(const void* x, int64_t ldx, const void* dy, int64_t
                              int64_t workspace_floats, int32_t accumulate, float* d_down, float* d_up, void* stream) {
   MOS_CHECK_ARG(x && dy && down && up && workspace && d_down && d_up, "mos_lora_grad: NULL pointer");
   MOS_CHECK_ARG(K % 8 == 0 && N % 8 == 0 && ldx % 8 == 0 && lddy % 8 == 0 && M > 0, "mos_lora_grad: bad shape");
-  const int nb = (int)ceil_div(M, LG_ROWS);
+  // slab height: a multiple of 64 rows such that at most LG_MAX_BLOCKS blocks exist
+  long long R = ceil_div(ceil_div(M, (long long)LG_MAX_BLOCKS), 64LL) * 64;
+  if (R > 1024) R = 1024;
+  const int nb = (int)ceil_div(M, R);
   MOS_CHECK_ARG((long long)nb * 4 * (K + N) <= workspace_floats, "mos_lora_grad: workspace too small (need %lld floats)",
                 (long long)nb * 4 * (K + N));
-  float* pD = workspace;
-  float* pU = workspace + (long long)nb * 4 * K;
-  MOS_CHECK_CUDA(launch_pdl(lora_grad_partial_kernel, dim3(nb), dim3(256), 0, STREAM(stream),
+  const size_t smem = (size_t)(4LL * K + 4LL * N + R * 8 + 4 * 32 * 64) * sizeof(float);
+  MOS_CHECK_ARG(smem <= 200 * 1024, "mos_lora_grad: K + N = %d too large for the shared-memory staging", K + N);
+  static bool configured = false;
+  if (!configured) {
+    MOS_CHECK_CUDA(cudaFuncSetAttribute(lora_grad_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  MOS_CHECK_CUDA(launch_pdl(lora_grad_partial_kernel, dim3(nb), dim3(LG_THREADS), smem, STREAM(stream),
                             reinterpret_cast<const __nv_bfloat16*>(x), (long long)ldx,
                             reinterpret_cast<const __nv_bfloat16*>(dy), (long long)lddy, (long long)M, (int)K, (int)N, down,
-                            up, pD, pU));
-  MOS_CHECK_CUDA(launch_pdl(lora_grad_reduce_kernel, dim3(nblk(4LL * K, 256)), dim3(256), 0, STREAM(stream),
-                            (const float*)pD, nb, 4LL * K, alpha, (int)accumulate, d_down));
-  MOS_CHECK_CUDA(launch_pdl(lora_grad_reduce_kernel, dim3(nblk(4LL * N, 256)), dim3(256), 0, STREAM(stream),
-                            (const float*)pU, nb, 4LL * N, alpha, (int)accumulate, d_up));
+                            up, (int)R, workspace));
+  const long long n = 4LL * (K + N);
+  MOS_CHECK_CUDA(launch_pdl(lora_grad_reduce_kernel, dim3(nblk(n, 256)), dim3(256), 0, STREAM(stream),
+                            (const float*)workspace, nb, 4LL * K, n, alpha, (int)accumulate, d_down, d_up));
   return MOS_OK;
 }
 

@@ -129,7 +129,8 @@ def test_conv_out_bwd_mse_noise(cuda):
     assert rel_l2(out, sch.add_noise(target, noise, t)) < 1e-6
 
 
-@pytest.mark.parametrize('M,K,N', [(8192, 320, 320), (154, 768, 640), (1000, 1280, 1280)])
+@pytest.mark.parametrize('M,K,N', [(8192, 320, 320), (154, 768, 640), (1000, 1280, 1280), (20001, 640, 320),
+                                   (70000, 320, 320)])
 def test_lora_grad(cuda, M, K, N):
     from mos_b200 import ops
     x, dy = mk((M, K), cuda, 1.0, 1), mk((M, N), cuda, 1.0, 2)

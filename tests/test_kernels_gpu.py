@@ -53,6 +53,28 @@ def test_attention(cuda, d, nq, nk):
     assert rel_l2(out, ref) < 8e-3
 
 
+@pytest.mark.parametrize('d,nq,nk,amp', [(40, 256, 1024, 4.0), (40, 256, 1024, 16.0), (40, 384, 1000, 60.0),
+                                         (80, 256, 1024, 16.0), (80, 128, 600, 60.0), (160, 128, 512, 16.0),
+                                         (160, 128, 500, 60.0)])
+def test_attention_growing_logits(cuda, d, nq, nk, amp):
+    """Later key tiles carry ever larger logits, so the kernel's lazy reference maximum has to move (jump > 8 in log2
+    units: O rescale in TMEM) and, for the large amplitudes, a tile has to be redone against its own maximum (jump > 32).
+    Same tolerance as test_attention: the result must not depend on which path a tile took."""
+    from mos_b200 import ops
+    B, H = 1, 8
+    q, k, v = mk((B, H, nq, d), cuda, seed=4), mk((B, H, nk, d), cuda, seed=5), mk((B, H, nk, d), cuda, seed=6)
+    ramp = (0.1 + torch.arange(nk, device=cuda).float() / nk).view(1, 1, nk, 1)
+    k = (k.float() * ramp * amp).to(torch.bfloat16)
+    Q, K, Vt = pack_heads(q, k, v, d)
+    out = torch.full((B, nq, H * d), float('nan'), device=cuda, dtype=torch.bfloat16)
+    ops.attention(Q, K, Vt, out, batch=B, heads=H, head_dim=d, nq=nq, nk=nk)
+    torch.cuda.synchronize()
+    ref = F.scaled_dot_product_attention(q.float(), k.float(), v.float())
+    ref = ref.permute(0, 2, 1, 3).reshape(B, nq, H * d)
+    assert torch.isfinite(out.float()).all()
+    assert rel_l2(out, ref) < 8e-3
+
+
 @pytest.mark.parametrize('d,nq', [(40, 4096), (80, 1024), (160, 256), (160, 64)])
 def test_attention_probs(cuda, d, nq):
     """probability maps for the attention controller (edlora.py:81-82): [B*heads, N, 77], rows sum to 1."""
