@@ -6,11 +6,21 @@
 // mixofshow/models/edlora.py:77-83,151-156 and pipeline_regionally_t2iadapter.py:111-116.
 //
 // One CTA = one 128-query tile of one (batch, head).  192 threads:
-//   warps 0..3  softmax: tcgen05.ld S from TMEM, online softmax (exp2, warp-free: one thread owns one row),
-//               P -> bf16 -> 128B-swizzled smem; O accumulated in registers from the per-tile P.V product
+//   warps 0..3  softmax: one thread owns one query row.  tcgen05.ld S from TMEM ONCE per tile, p = 2^(s*c - m_ref)
+//               against a lazily updated reference maximum, P -> bf16 -> 128B-swizzled smem
 //   warp 4      TMA producer (Q once, K / V^T ring)
-//   warp 5      TMEM allocator + tcgen05.mma issuer: S_j = Q K_j^T (TMEM, double buffered), PV_j = P_j V_j
-// S_{j+1} is issued before PV_j so the tensor pipe overlaps the softmax of the next tile.
+//   warp 5      TMEM allocator + tcgen05.mma issuer: S_j = Q K_j^T (TMEM), O += P_j V_j (one TMEM accumulator)
+// Design notes (measurements in profiles/README.md):
+//   * lazy reference maximum: tile j is exponentiated against the running maximum of tiles < j (exact: softmax is shift
+//     invariant; p <= 2^32 is harmless in fp32 / bf16).  Only tile 0 takes a row-max pre-pass; a tile whose maximum
+//     exceeds the reference by more than 2^32 is redone against its own maximum (warp-uniform slow path).  The reference
+//     only moves when a tile maximum exceeds it by more than 8 (log2 units), so rescales are rare.
+//   * PV_j accumulates into ONE TMEM accumulator (tcgen05.mma accumulate flag); when the reference moved, the owning
+//     thread rescales its O row in TMEM (tcgen05.ld / tcgen05.st) before it publishes P_j.  O is read once, at the end.
+//   * d = 40 self-attention: 64-key tiles with S and P double buffered, a 3-stage K/V ring, 256 TMEM columns and 91 KB of
+//     smem, so that two CTAs share an SM and neither waits for S_{j+1} or for the P buffer.
+//   * full tiles run a straight-line pass (no per-chunk branches: instruction-fetch bubbles after branches were 11 % of
+//     the issue-stall samples), 4 independent max / sum accumulators, TMEM loads one 16-column chunk ahead.
 // Layouts (written by the QKV GEMM epilogue): Q,K [B*H, rows, DP] (DP = d padded to 64, pad = 0),
 // V^T [B*H, DV, nk8] (keys contiguous), so every MMA operand is K-major SWIZZLE_128B.
 #include <stdlib.h>
@@ -19,34 +29,6 @@
 #include "tc.cuh"
 
 namespace mos {
-
-// WIDE: d = 160 cross-attention variant (nk <= 128): one 128-key tile, single-buffered, so that the probability maps of
-// the controller path come from a single kv tile at every head size.
-template <int D, bool WIDE = false>
-struct AttnCfg {
-  static constexpr int KSTEPS = (D + 15) / 16;
-  static constexpr int DP = ((D + 63) / 64) * 64;
-  static constexpr int QCH = DP / 64;
-  static constexpr int DV = ((D + 15) / 16) * 16;
-  static constexpr int BKV = (D <= 80 || WIDE) ? 128 : 64;
-  static constexpr int KVCH = BKV / 64;
-  static constexpr int STAGES = WIDE ? 1 : 2;
-  // d = 40: single S / P buffers and 256 TMEM columns so that TWO CTAs share an SM (the softmax of one hides the
-  // MMA / TMEM latency of the other); larger head sizes keep double buffering and one CTA per SM.
-  static constexpr int SB = (D <= 40 || WIDE) ? 1 : 2;
-  static constexpr int PB = (D <= 40 || WIDE) ? 1 : 2;
-  static constexpr int MINB = D <= 40 ? 2 : 1;
-  static constexpr int Q_BYTES = QCH * 128 * 128;
-  static constexpr int K_BYTES = QCH * BKV * 128;
-  static constexpr int V_BYTES = KVCH * DV * 128;
-  static constexpr int P_BYTES = KVCH * 128 * 128;
-  static constexpr int O_STRIDE = ((DV + 63) / 64) * 64;
-  static constexpr int S_COL0 = 0;
-  static constexpr int O_COL0 = SB * BKV;
-  static constexpr int TMEM_COLS = (O_COL0 + 2 * O_STRIDE <= 256) ? 256 : 512;
-  static constexpr int SMEM_BYTES = Q_BYTES + STAGES * (K_BYTES + V_BYTES) + PB * P_BYTES + 1024;
-  static_assert(O_COL0 + 2 * O_STRIDE <= TMEM_COLS, "TMEM budget");
-};
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -63,312 +45,22 @@ struct AttnDev {
   float* lse2;   // optional [B*H, nq]: log2-domain log-sum-exp of scale*S (saved for the backward kernels)
   float* pcols;  // optional [B*H, nq, 2]: probabilities at key columns pos[b][0..1] (single kv tile only)
   const int* pos;
-  int dbg;       // MOS_ATTN_DBG experiment bits (profiling only): 1 = skip p_empty wait, 2 = back-off in spin loops
-  unsigned long long* tl;   // optional timeline buffer (mos_debug_set_attn_timeline)
+  unsigned long long* tl;   // timeline buffer of the TL instantiation (mos_debug_set_attn_timeline)
 };
 
-template <int D, bool WIDE>
-__global__ void __launch_bounds__(192, AttnCfg<D, WIDE>::MINB)
-attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-            const __grid_constant__ CUtensorMap tmV, const AttnDev p) {
-  using C = AttnCfg<D, WIDE>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sKV = sQ + C::Q_BYTES;
-  uint8_t* sP = sKV + C::STAGES * (C::K_BYTES + C::V_BYTES);
-
-  __shared__ uint64_t q_full, kv_full[C::STAGES], kv_empty[C::STAGES];
-  __shared__ uint64_t s_full[2], s_empty[2], p_full[2], p_empty[2], o_full[2], o_empty[2];
-  __shared__ uint32_t tmem_holder;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128;
-  const int bh = blockIdx.y;
-  const int T = (p.nk + C::BKV - 1) / C::BKV;
-
-  if (warp == 4 && lane == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-    mbar_init(&q_full, 1);
-    for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], 128);
-      mbar_init(&p_full[s], 128);
-      mbar_init(&p_empty[s], 1);
-      mbar_init(&o_full[s], 1);
-      mbar_init(&o_empty[s], 128);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 5) tmem_alloc(&tmem_holder, C::TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = tmem_holder;
-  pdl_wait();               // Q / K / V^T come from the previous kernel in the stream
-  pdl_launch_dependents();
-
-  if (warp == 4) {
-    // ================================================================= TMA producer
-    if (lane == 0) {
-      mbar_expect_tx(&q_full, C::Q_BYTES);
-#pragma unroll
-      for (int c = 0; c < C::QCH; ++c) tma_load_3d(sQ + c * 16384, &tmQ, &q_full, c * 64, q0, bh);
-      for (int j = 0; j < T; ++j) {
-        const int st = j % C::STAGES;
-        mbar_wait(&kv_empty[st], ((j / C::STAGES) & 1) ^ 1);
-        uint8_t* sK = sKV + st * (C::K_BYTES + C::V_BYTES);
-        uint8_t* sV = sK + C::K_BYTES;
-        mbar_expect_tx(&kv_full[st], C::K_BYTES + C::V_BYTES);
-#pragma unroll
-        for (int c = 0; c < C::QCH; ++c)
-          tma_load_3d(sK + c * (C::BKV * 128), &tmK, &kv_full[st], c * 64, j * C::BKV, bh);
-#pragma unroll
-        for (int c = 0; c < C::KVCH; ++c)
-          tma_load_3d(sV + c * (C::DV * 128), &tmV, &kv_full[st], j * C::BKV + c * 64, 0, bh);
-      }
-    }
-  } else if (warp == 5) {
-    // ================================================================= MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc_s = make_idesc(128, C::BKV, 1);
-      const uint32_t idesc_o = make_idesc(128, C::DV, 1);
-      mbar_wait(&q_full, 0);
-      for (int j = 0; j <= T; ++j) {
-        if (j < T) {
-          const int st = j % C::STAGES, sb = j % C::SB;
-          mbar_wait(&kv_full[st], (j / C::STAGES) & 1);
-          mbar_wait(&s_empty[sb], ((j / C::SB) & 1) ^ 1);
-          tc_fence_after();
-          uint8_t* sK = sKV + st * (C::K_BYTES + C::V_BYTES);
-#pragma unroll
-          for (int kk = 0; kk < C::KSTEPS; ++kk) {
-            uint64_t ad = make_desc_sw128(smem_u32(sQ + (kk >> 2) * 16384)) + 2 * (kk & 3);
-            uint64_t bd = make_desc_sw128(smem_u32(sK + (kk >> 2) * (C::BKV * 128))) + 2 * (kk & 3);
-            umma_bf16(tmem + C::S_COL0 + sb * C::BKV, ad, bd, idesc_s, kk > 0 ? 1u : 0u);
-          }
-          umma_commit(&s_full[sb]);
-        }
-        if (j >= 1) {
-          const int jj = j - 1, pb = jj % C::PB, ob = jj & 1, st = jj % C::STAGES;
-          mbar_wait(&p_full[pb], (jj / C::PB) & 1);
-          mbar_wait(&o_empty[ob], ((jj >> 1) & 1) ^ 1);
-          tc_fence_after();
-          uint8_t* sV = sKV + st * (C::K_BYTES + C::V_BYTES) + C::K_BYTES;
-          uint8_t* sPb = sP + pb * C::P_BYTES;
-          const int kv_valid = min(C::BKV, p.nk - jj * C::BKV);
-          const int ksteps = (kv_valid + 15) >> 4;
-          for (int kk = 0; kk < ksteps; ++kk) {
-            uint64_t ad = make_desc_sw128(smem_u32(sPb + (kk >> 2) * 16384)) + 2 * (kk & 3);
-            uint64_t bd = make_desc_sw128(smem_u32(sV + (kk >> 2) * (C::DV * 128))) + 2 * (kk & 3);
-            umma_bf16(tmem + C::O_COL0 + ob * C::O_STRIDE, ad, bd, idesc_o, kk > 0 ? 1u : 0u);
-          }
-          umma_commit(&o_full[ob]);
-          umma_commit(&p_empty[pb]);
-          umma_commit(&kv_empty[st]);
-        }
-      }
-    }
-  } else {
-    // ================================================================= softmax / accumulate (warps 0..3)
-    const int r = warp * 32 + lane;  // query row in tile == TMEM lane
-    const uint32_t trow = tmem + (uint32_t(warp * 32) << 16);
-    const int q_idx = q0 + r;
-    float acc[C::DV];
-#pragma unroll
-    for (int i = 0; i < C::DV; ++i) acc[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
-
-    auto accumulate = [&](int jj, float a) {
-      const int ob = jj & 1;
-      if (lane == 0) mbar_wait(&o_full[ob], (jj >> 1) & 1);   // one polling lane per warp
-      __syncwarp();
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < C::DV / 16; ++c) {
-        uint32_t v[16];
-        tmem_ld16(trow + C::O_COL0 + ob * C::O_STRIDE + c * 16, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) acc[c * 16 + i] = acc[c * 16 + i] * a + __uint_as_float(v[i]);
-      }
-      tc_fence_before();
-      mbar_arrive(&o_empty[ob]);
-    };
-
-    for (int j = 0; j < T; ++j) {
-      const int sb = j % C::SB, pbuf = j % C::PB;
-      const int kv_valid = min(C::BKV, p.nk - j * C::BKV);
-      if (lane == 0) mbar_wait(&s_full[sb], (j / C::SB) & 1);
-      __syncwarp();
-      tc_fence_after();
-      const uint32_t ts = trow + C::S_COL0 + sb * C::BKV;
-      // pass 1: row max   (full tiles take the mask-free path: this kernel is issue-bound, ncu: 69 % issue active)
-      const bool full = kv_valid == C::BKV;
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < C::BKV / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(ts + c * 32, v);
-        tmem_ld_wait();
-        if (full) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
-        }
-      }
-      const float m_new = fmaxf(m_run, mx * p.scale_log2);
-      const float alpha = ex2_approx(m_run - m_new);
-      // pass 2: probabilities -> bf16 -> swizzled smem
-      if (lane == 0) mbar_wait(&p_empty[pbuf], ((j / C::PB) & 1) ^ 1);
-      __syncwarp();
-      uint8_t* sPb = sP + pbuf * C::P_BYTES;
-      float rs = 0.f;
-      float pc0 = 0.f, pc1 = 0.f;
-      int pos0 = -1, pos1 = -1;
-      if (p.pcols != nullptr) {
-        const int bb = bh / p.heads;
-        pos0 = __ldg(p.pos + bb * 2) - j * C::BKV;
-        pos1 = __ldg(p.pos + bb * 2 + 1) - j * C::BKV;
-      }
-#pragma unroll 1
-      for (int c = 0; c < C::BKV / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(ts + c * 32, v);
-        tmem_ld_wait();
-        float pv[32];
-        if (full) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            pv[i] = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
-            rs += pv[i];
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float e = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
-            pv[i] = (c * 32 + i < kv_valid) ? e : 0.f;
-            rs += pv[i];
-          }
-        }
-        if (p.pcols != nullptr) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            pc0 = (c * 32 + i == pos0) ? pv[i] : pc0;
-            pc1 = (c * 32 + i == pos1) ? pv[i] : pc1;
-          }
-        }
-        uint8_t* rowp = sPb + (c >> 1) * 16384 + r * 128;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 u;
-          u.x = pack_bf16x2(pv[g * 8 + 0], pv[g * 8 + 1]);
-          u.y = pack_bf16x2(pv[g * 8 + 2], pv[g * 8 + 3]);
-          u.z = pack_bf16x2(pv[g * 8 + 4], pv[g * 8 + 5]);
-          u.w = pack_bf16x2(pv[g * 8 + 6], pv[g * 8 + 7]);
-          const int c16 = (c & 1) * 4 + g;  // 16-byte chunk inside the 128-byte row
-          *reinterpret_cast<uint4*>(rowp + ((c16 ^ (r & 7)) << 4)) = u;
-        }
-      }
-      if (p.pcols != nullptr && T == 1 && q_idx < p.nq) {
-        const float inv = 1.0f / rs;
-        *reinterpret_cast<float2*>(p.pcols + ((long long)bh * p.nq + q_idx) * 2) = make_float2(pc0 * inv, pc1 * inv);
-      }
-      if (p.probs != nullptr && T == 1) {
-        // normalised probabilities for the attention controller (edlora.py:81-82): single kv tile, so l = rs
-        const float inv = 1.0f / rs;
-        float* prow = p.probs + ((long long)bh * p.nq + q_idx) * p.nk;
-#pragma unroll 1
-        for (int c = 0; c < C::BKV / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld32(ts + c * 32, v);
-          tmem_ld_wait();
-          if (q_idx < p.nq) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i < kv_valid) prow[c * 32 + i] = exp2f(__uint_as_float(v[i]) * p.scale_log2 - m_new) * inv;
-          }
-          __syncwarp();
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(&s_empty[sb]);
-      fence_proxy_async_smem();
-      mbar_arrive(&p_full[pbuf]);
-      l_run = l_run * alpha + rs;
-      m_run = m_new;
-      if (j >= 1) accumulate(j - 1, alpha_prev);
-      alpha_prev = alpha;
-    }
-    accumulate(T - 1, alpha_prev);
-
-    if (q_idx < p.nq) {
-      const float inv = 1.0f / l_run;
-      const int b = bh / p.heads, h = bh - b * p.heads;
-      if (p.lse2 != nullptr) p.lse2[(long long)bh * p.nq + q_idx] = m_run + log2f(l_run);
-      __nv_bfloat16* orow = p.out + ((long long)b * p.nq + q_idx) * p.ldo + h * D;
-#pragma unroll
-      for (int c = 0; c < D / 8; ++c) {
-        uint4 u;
-        u.x = pack_bf16x2(acc[c * 8 + 0] * inv, acc[c * 8 + 1] * inv);
-        u.y = pack_bf16x2(acc[c * 8 + 2] * inv, acc[c * 8 + 3] * inv);
-        u.z = pack_bf16x2(acc[c * 8 + 4] * inv, acc[c * 8 + 5] * inv);
-        u.w = pack_bf16x2(acc[c * 8 + 6] * inv, acc[c * 8 + 7] * inv);
-        *reinterpret_cast<uint4*>(orow + c * 8) = u;
-      }
-    }
-    tc_fence_before();
-  }
-
-  __syncthreads();
-  if (warp == 5) {
-    tc_fence_after();
-    tmem_dealloc(tmem, C::TMEM_COLS);
-  }
-}
-
-
-// =====================================================================================================================
-// v2 kernel (default): single TMEM read of S per tile, O accumulated in TMEM.
-//
-// Measured on B200 the v1 kernel above spends ~3400 SM-cycles per 128x128 tile at d = 40 against a MUFU bound of 1024
-// (16 ex2 / clk / SM): TMEM reads run at 64 B/clk, and v1 reads every S tile twice (row max, then exp) and the PV product
-// once, through single-accumulator dependency chains.  v2:
-//   * lazy reference maximum: tile j is exponentiated against the running maximum of tiles < j (exact: softmax is shift
-//     invariant; p <= 2^32 is harmless in fp32 / bf16).  Only tile 0 takes a row-max pre-pass; a tile whose maximum
-//     exceeds the reference by more than 2^32 is redone against its own maximum (warp-uniform slow path).
-//   * the reference only moves when a tile maximum exceeds it by more than 8 (log2 units), so rescales are rare;
-//   * PV_j accumulates into ONE TMEM accumulator (tcgen05.mma accumulate flag); when the reference moved, the owning
-//     thread rescales its O row in TMEM (tcgen05.ld / tcgen05.st) before it publishes P_j.  O is read once, at the end.
-//   * 4-way independent max / sum accumulators, TMEM loads issued one chunk ahead of the arithmetic.
-// optional in-kernel timeline (profiling aid, mos_debug_set_attn_timeline): CTA (0,0) records clock64 stamps of its
-// softmax warp 0 (role 0) and of the MMA thread (role 1) for the first 32 kv tiles, 4 stamps per tile and role.  The
-// buffer pointer travels as a kernel parameter (constant bank): a disabled timeline costs one predicated branch.
-#define astamp(role, j, k)                                                                             \
-  do {                                                                                                 \
-    if (p.tl != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (j) < 32) p.tl[(role) * 128 + (j) * 4 + (k)] = clock64(); \
-  } while (0)
-
-template <int D, bool WIDE = false>
-struct AttnCfg2 {
+// ONE: single-tile variant for cross-attention (nk <= 128): one 128-key tile, nothing double buffered, so that the
+// probability maps / concept-token columns of the controller and regulariser paths come from a single kv tile.
+template <int D, bool ONE = false>
+struct AttnCfg {
   static constexpr int KSTEPS = (D + 15) / 16;
   static constexpr int DP = ((D + 63) / 64) * 64;
   static constexpr int QCH = DP / 64;
   static constexpr int DV = ((D + 15) / 16) * 16;
-  static constexpr int BKV = (D <= 80 || WIDE) ? 128 : 64;
+  static constexpr int BKV = ONE ? 128 : (D <= 40 ? 64 : (D <= 80 ? 128 : 64));
   static constexpr int KVCH = BKV / 64;
-  static constexpr int STAGES = WIDE ? 1 : 2;
-  static constexpr int SB = (D <= 40 || WIDE) ? 1 : 2;      // d = 40: 256 TMEM columns -> two CTAs per SM
-  static constexpr int PB = (D <= 40 || WIDE) ? 1 : 2;
+  static constexpr int STAGES = ONE ? 1 : (D <= 40 ? 3 : 2);
+  static constexpr int SB = ONE ? 1 : 2;
+  static constexpr int PB = ONE ? 1 : 2;
   static constexpr int MINB = D <= 40 ? 2 : 1;
   static constexpr int Q_BYTES = QCH * 128 * 128;
   static constexpr int K_BYTES = QCH * BKV * 128;
@@ -378,31 +70,8 @@ struct AttnCfg2 {
   static constexpr int TMEM_COLS = (O_COL0 + DV <= 256) ? 256 : 512;
   static constexpr int SMEM_BYTES = Q_BYTES + STAGES * (K_BYTES + V_BYTES) + PB * P_BYTES + 1024;
   static_assert(O_COL0 + DV <= TMEM_COLS, "TMEM budget");
+  static_assert(MINB * SMEM_BYTES <= 227 * 1024, "smem budget");
 };
-
-// row maximum of one S tile (raw logits), masked to the first kv_valid columns
-template <int BKV>
-__device__ __forceinline__ float s_row_max(uint32_t ts, int kv_valid) {
-  constexpr int NCH = BKV / 16;
-  uint32_t v[2][16];
-  float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-  tmem_ld16(ts, v[0]);
-#pragma unroll
-  for (int ch = 0; ch < NCH; ++ch) {
-    if (ch * 16 >= kv_valid) break;
-    tmem_ld_wait();
-    if (ch + 1 < NCH && (ch + 1) * 16 < kv_valid) tmem_ld16(ts + (ch + 1) * 16, v[(ch + 1) & 1]);
-    if ((ch + 1) * 16 <= kv_valid) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[ch & 1][i]));
-    } else {
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (ch * 16 + i < kv_valid) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[ch & 1][i]));
-    }
-  }
-  return fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-}
 
 // 16 logits of one row -> probabilities (fp32 sums, running raw maxima, packed bf16 pairs)
 template <bool WHOLE, bool PC>
@@ -439,12 +108,79 @@ __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, u
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// One pass over an S tile: p = 2^(s * c - m_ref) -> bf16 -> swizzled smem; returns the row sum, the raw row maximum
-// and (PC) the probabilities at the two concept-token columns.  TMEM loads run one 16-column chunk ahead.
+// row maximum of one S tile (raw logits), masked to the first kv_valid columns
+template <int BKV>
+__device__ __forceinline__ float s_row_max(uint32_t ts, int kv_valid) {
+  constexpr int NCH = BKV / 16;
+  uint32_t v[2][16];
+  float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  tmem_ld16(ts, v[0]);
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    if (ch * 16 >= kv_valid) break;
+    tmem_ld_wait();
+    if (ch + 1 < NCH && (ch + 1) * 16 < kv_valid) tmem_ld16(ts + (ch + 1) * 16, v[(ch + 1) & 1]);
+    if ((ch + 1) * 16 <= kv_valid) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[ch & 1][i]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (ch * 16 + i < kv_valid) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[ch & 1][i]));
+    }
+  }
+  return fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+}
+
+// the P buffer is free once PV_{j-PB} has retired; one lane polls
+__device__ __forceinline__ void wait_p_empty(uint64_t* bar, uint32_t parity, int lane) {
+  if (lane == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
+
+// Straight-line pass over a FULL S tile: p = 2^(s * c - m_ref) -> bf16 -> swizzled smem; row sum and raw row maximum.
+// TMEM loads are 32 columns wide and run one load ahead (a tcgen05.ld takes ~300 cycles to return while the tensor pipe
+// is busy, about the time the arithmetic of 32 columns needs); no branches besides the (normally already satisfied)
+// P-buffer wait.
+template <int BKV>
+__device__ __forceinline__ void s_softmax_pass_full(uint32_t ts, float c, float m_ref, uint32_t sPb, int r,
+                                                    uint64_t* p_empty_bar, uint32_t pe_parity, int lane, float& rs,
+                                                    float& mx) {
+  constexpr int NCH = BKV / 32;
+  uint32_t v[2][32];
+  float s4[4] = {0.f, 0.f, 0.f, 0.f};
+  float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  const float nm = -m_ref;
+  float unused0 = 0.f, unused1 = 0.f;
+  tmem_ld32(ts, v[0]);
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    tmem_ld_wait();
+    if (ch + 1 < NCH) tmem_ld32(ts + (ch + 1) * 32, v[(ch + 1) & 1]);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t pk[8];
+      const uint32_t(&vh)[16] = *reinterpret_cast<const uint32_t(*)[16]>(&v[ch & 1][h * 16]);
+      s_chunk<true, false>(vh, ch * 32 + h * 16, BKV, c, nm, s4, m4, pk, -1, -1, unused0, unused1);
+      if (ch == 0 && h == 0) wait_p_empty(p_empty_bar, pe_parity, lane);
+      const int c16b = ch * 2 + h;        // 16-column chunk index inside the tile
+      const uint32_t rowp = sPb + (c16b >> 2) * 16384 + r * 128;
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const int c16 = (c16b & 3) * 2 + g;  // 16-byte chunk inside the 128-byte row
+        sts128(rowp + ((c16 ^ (r & 7)) << 4), pk[g * 4 + 0], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+      }
+    }
+  }
+  rs = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+  mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+}
+
+// General pass (partial tiles, concept-token columns, redo path): masks the columns >= kv_valid.
 template <int BKV, bool PC>
-__device__ __forceinline__ void s_softmax_pass(uint32_t ts, float c, float m_ref, int kv_valid, uint32_t sPb, int r,
-                                               uint64_t* p_empty_bar, uint32_t pe_parity, bool wait_pe, int lane,
-                                               float& rs, float& mx, int pos0, int pos1, float& pc0, float& pc1) {
+__device__ __noinline__ void s_softmax_pass(uint32_t ts, float c, float m_ref, int kv_valid, uint32_t sPb, int r,
+                                            uint64_t* p_empty_bar, uint32_t pe_parity, bool wait_pe, int lane,
+                                            float& rs, float& mx, int pos0, int pos1, float& pc0, float& pc1) {
   constexpr int NCH = BKV / 16;
   uint32_t v[2][16];
   float s4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -457,18 +193,12 @@ __device__ __forceinline__ void s_softmax_pass(uint32_t ts, float c, float m_ref
     tmem_ld_wait();
     if (ch + 1 < NCH && (ch + 1) * 16 < kv_valid) tmem_ld16(ts + (ch + 1) * 16, v[(ch + 1) & 1]);
     uint32_t pk[8];
-    if ((ch + 1) * 16 <= kv_valid)
-      s_chunk<true, PC>(v[ch & 1], ch * 16, kv_valid, c, nm, s4, m4, pk, pos0, pos1, pc0, pc1);
-    else
-      s_chunk<false, PC>(v[ch & 1], ch * 16, kv_valid, c, nm, s4, m4, pk, pos0, pos1, pc0, pc1);
-    if (ch == 0 && wait_pe) {             // the P buffer is free once PV_{j-1} has retired
-      if (lane == 0) mbar_wait(p_empty_bar, pe_parity);
-      __syncwarp();
-    }
+    s_chunk<false, PC>(v[ch & 1], ch * 16, kv_valid, c, nm, s4, m4, pk, pos0, pos1, pc0, pc1);
+    if (ch == 0 && wait_pe) wait_p_empty(p_empty_bar, pe_parity, lane);
     const uint32_t rowp = sPb + (ch >> 2) * 16384 + r * 128;
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
-      const int c16 = (ch & 3) * 2 + g;  // 16-byte chunk inside the 128-byte row
+      const int c16 = (ch & 3) * 2 + g;
       sts128(rowp + ((c16 ^ (r & 7)) << 4), pk[g * 4 + 0], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
     }
   }
@@ -476,11 +206,18 @@ __device__ __forceinline__ void s_softmax_pass(uint32_t ts, float c, float m_ref
   mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
 }
 
-template <int D, bool WIDE>
-__global__ void __launch_bounds__(192, AttnCfg2<D, WIDE>::MINB)
-attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-             const __grid_constant__ CUtensorMap tmV, const AttnDev p) {
-  using C = AttnCfg2<D, WIDE>;
+// optional in-kernel timeline (TL instantiation only, mos_debug_set_attn_timeline): CTA (0,0) records clock64 stamps of
+// its softmax warp 0 (role 0) and of the MMA thread (role 1) for the first 32 kv tiles, 4 stamps per tile and role.
+#define astamp(role, j, k)                                                                                     \
+  do {                                                                                                         \
+    if (TL && blockIdx.x == 0 && blockIdx.y == 0 && (j) < 32) p.tl[(role) * 128 + (j) * 4 + (k)] = clock64();  \
+  } while (0)
+
+template <int D, bool ONE, bool TL>
+__global__ void __launch_bounds__(192, AttnCfg<D, ONE>::MINB)
+attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+            const __grid_constant__ CUtensorMap tmV, const AttnDev p) {
+  using C = AttnCfg<D, ONE>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -488,7 +225,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   uint8_t* sP = sKV + C::STAGES * (C::K_BYTES + C::V_BYTES);
 
   __shared__ uint64_t q_full, kv_full[C::STAGES], kv_empty[C::STAGES];
-  __shared__ uint64_t s_full[2], s_empty[2], p_full[2], p_empty[2], o_full;
+  __shared__ uint64_t s_full[2], s_empty[2], p_full[2], p_empty[2], o_full, o_done;
   __shared__ uint32_t tmem_holder;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -507,11 +244,12 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], 128);
-      mbar_init(&p_full[s], 128);
+      mbar_init(&s_empty[s], 4);     // one arrival per softmax warp (lane 0, after __syncwarp)
+      mbar_init(&p_full[s], 4);
       mbar_init(&p_empty[s], 1);
     }
     mbar_init(&o_full, 1);
+    mbar_init(&o_done, 1);
     fence_barrier_init();
   }
   if (warp == 5) tmem_alloc(&tmem_holder, C::TMEM_COLS);
@@ -528,10 +266,10 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       mbar_expect_tx(&q_full, C::Q_BYTES);
 #pragma unroll
       for (int c = 0; c < C::QCH; ++c) tma_load_3d(sQ + c * 16384, &tmQ, &q_full, c * 64, q0, bh);
+      int st = 0;
+      uint32_t ph = 0;
       for (int j = 0; j < T; ++j) {
-        const int st = j % C::STAGES;
-        if (p.dbg & 2) mbar_wait_sleep(&kv_empty[st], ((j / C::STAGES) & 1) ^ 1);
-        else mbar_wait(&kv_empty[st], ((j / C::STAGES) & 1) ^ 1);
+        mbar_wait_hint(&kv_empty[st], ph ^ 1);     // long waits: park instead of polling next to the softmax warps
         uint8_t* sK = sKV + st * (C::K_BYTES + C::V_BYTES);
         uint8_t* sV = sK + C::K_BYTES;
         mbar_expect_tx(&kv_full[st], C::K_BYTES + C::V_BYTES);
@@ -541,6 +279,10 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
 #pragma unroll
         for (int c = 0; c < C::KVCH; ++c)
           tma_load_3d(sV + c * (C::DV * 128), &tmV, &kv_full[st], j * C::BKV + c * 64, 0, bh);
+        if (++st == C::STAGES) {
+          st = 0;
+          ph ^= 1;
+        }
       }
     }
   } else if (warp == 5) {
@@ -549,17 +291,17 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       const uint32_t idesc_s = make_idesc(128, C::BKV, 1);
       const uint32_t idesc_o = make_idesc(128, C::DV, 1);
       mbar_wait(&q_full, 0);
+      int st_s = 0, st_p = 0;          // K/V ring slot of the next S product / of the next PV product
+      uint32_t ph_s = 0;
       for (int j = 0; j <= T; ++j) {
         if (j < T) {
-          const int st = j % C::STAGES, sb = j % C::SB;
-          if (p.dbg & 2) mbar_wait_sleep(&kv_full[st], (j / C::STAGES) & 1);
-          else mbar_wait(&kv_full[st], (j / C::STAGES) & 1);
+          const int sb = j % C::SB;
+          mbar_wait(&kv_full[st_s], ph_s);
           astamp(1, j, 0);
-          if (p.dbg & 2) mbar_wait_sleep(&s_empty[sb], ((j / C::SB) & 1) ^ 1);
-          else mbar_wait(&s_empty[sb], ((j / C::SB) & 1) ^ 1);
+          mbar_wait(&s_empty[sb], ((j / C::SB) & 1) ^ 1);
           tc_fence_after();
           astamp(1, j, 1);
-          uint8_t* sK = sKV + st * (C::K_BYTES + C::V_BYTES);
+          uint8_t* sK = sKV + st_s * (C::K_BYTES + C::V_BYTES);
 #pragma unroll
           for (int kk = 0; kk < C::KSTEPS; ++kk) {
             uint64_t ad = make_desc_sw128(smem_u32(sQ + (kk >> 2) * 16384)) + 2 * (kk & 3);
@@ -567,15 +309,18 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
             umma_bf16(tmem + sb * C::BKV, ad, bd, idesc_s, kk > 0 ? 1u : 0u);
           }
           umma_commit(&s_full[sb]);
+          if (++st_s == C::STAGES) {
+            st_s = 0;
+            ph_s ^= 1;
+          }
         }
         if (j >= 1) {
-          const int jj = j - 1, pb = jj % C::PB, st = jj % C::STAGES;
+          const int jj = j - 1, pb = jj % C::PB;
           astamp(1, jj, 2);
-          if (p.dbg & 2) mbar_wait_sleep(&p_full[pb], (jj / C::PB) & 1);
-          else mbar_wait(&p_full[pb], (jj / C::PB) & 1);     // P_jj in smem, O rescaled if the reference moved
+          mbar_wait(&p_full[pb], (jj / C::PB) & 1);     // P_jj in smem, O rescaled if the reference moved
           tc_fence_after();
           astamp(1, jj, 3);
-          uint8_t* sV = sKV + st * (C::K_BYTES + C::V_BYTES) + C::K_BYTES;
+          uint8_t* sV = sKV + st_p * (C::K_BYTES + C::V_BYTES) + C::K_BYTES;
           uint8_t* sPb = sP + pb * C::P_BYTES;
           const int kv_valid = min(C::BKV, p.nk - jj * C::BKV);
           const int ksteps = (kv_valid + 15) >> 4;
@@ -586,9 +331,11 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
           }
           umma_commit(&o_full);
           umma_commit(&p_empty[pb]);
-          umma_commit(&kv_empty[st]);
+          umma_commit(&kv_empty[st_p]);
+          if (++st_p == C::STAGES) st_p = 0;
         }
       }
+      umma_commit(&o_done);   // every PV product has retired
     }
   } else {
     // ================================================================= softmax (warps 0..3), one thread per query row
@@ -615,28 +362,33 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       if (threadIdx.x == 0) astamp(0, j, 1);
       const uint32_t ts = trow + sb * C::BKV;
       const uint32_t sPb = smem_u32(sP + pbuf * C::P_BYTES);
+      const uint32_t pe_parity = ((j / C::PB) & 1) ^ 1;
       float m_use = m;
       if (j == 0) m_use = s_row_max<C::BKV>(ts, kv_valid) * c;    // the only two-pass tile
       float rs, mx, mt, pc0 = 0.f, pc1 = 0.f;
-      const uint32_t pe_parity = ((j / C::PB) & 1) ^ 1;
-      bool redone = false;
-#pragma unroll 1
-      for (;;) {
-        if (want_pc)
-          s_softmax_pass<C::BKV, true>(ts, c, m_use, kv_valid, sPb, r, &p_empty[pbuf], pe_parity, !redone, lane, rs,
-                                       mx, pos0 - j * C::BKV, pos1 - j * C::BKV, pc0, pc1);
-        else
-          s_softmax_pass<C::BKV, false>(ts, c, m_use, kv_valid, sPb, r, &p_empty[pbuf], pe_parity,
-                                        !redone && !(p.dbg & 1), lane, rs, mx, -1, -1, pc0, pc1);
-        mt = mx * c;
-        if (j == 0 || redone || !__any_sync(0xffffffffu, mt > m_use + 32.f)) break;
+      const bool fast = kv_valid == C::BKV && !want_pc;
+      if (fast) s_softmax_pass_full<C::BKV>(ts, c, m_use, sPb, r, &p_empty[pbuf], pe_parity, lane, rs, mx);
+      else if (want_pc)
+        s_softmax_pass<C::BKV, true>(ts, c, m_use, kv_valid, sPb, r, &p_empty[pbuf], pe_parity, true, lane, rs, mx,
+                                     pos0 - j * C::BKV, pos1 - j * C::BKV, pc0, pc1);
+      else
+        s_softmax_pass<C::BKV, false>(ts, c, m_use, kv_valid, sPb, r, &p_empty[pbuf], pe_parity, true, lane, rs, mx, -1,
+                                      -1, pc0, pc1);
+      mt = mx * c;
+      if (j > 0 && __any_sync(0xffffffffu, mt > m_use + 32.f)) {
         // slow path: a logit far above everything seen so far -- redo this tile against its own maximum
         const float m_new = fmaxf(m_use, mt);
         const float a = ex2_approx(m - m_new);
         l *= a;
         a_pend *= a;
         m_use = m_new;
-        redone = true;
+        if (want_pc)
+          s_softmax_pass<C::BKV, true>(ts, c, m_use, kv_valid, sPb, r, &p_empty[pbuf], pe_parity, false, lane, rs, mx,
+                                       pos0 - j * C::BKV, pos1 - j * C::BKV, pc0, pc1);
+        else
+          s_softmax_pass<C::BKV, false>(ts, c, m_use, kv_valid, sPb, r, &p_empty[pbuf], pe_parity, false, lane, rs,
+                                        mx, -1, -1, pc0, pc1);
+        mt = mx * c;
       }
       l += rs;
       m = m_use;
@@ -679,10 +431,13 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
           __syncwarp();
         }
       }
-      tc_fence_before();
-      mbar_arrive(&s_empty[sb]);
-      fence_proxy_async_smem();
-      mbar_arrive(&p_full[pbuf]);
+      tc_fence_before();              // this thread's TMEM reads of S_j (and O rescale) are ordered before ...
+      fence_proxy_async_smem();       // ... and its P_j stores are visible to the tensor core's async proxy
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&s_empty[sb]);
+        mbar_arrive(&p_full[pbuf]);
+      }
       if (threadIdx.x == 0) astamp(0, j, 3);
       // lazy reference update for the following tiles (applied to O -- including PV_j -- before P_{j+1} is published)
       if (mt > m + 8.f) {
@@ -693,7 +448,9 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       }
     }
     // all PV products retired -> normalise and write the row
-    if (lane == 0) mbar_wait(&o_full, (T - 1) & 1);
+    // (o_full cannot be used here: with two P buffers PV_{T-2} may still be in flight, and a parity wait cannot tell
+    // "T - 2 completions" from "T completions")
+    if (lane == 0) mbar_wait(&o_done, 0);
     __syncwarp();
     tc_fence_after();
     const float inv = a_pend / l;
@@ -731,20 +488,11 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
 
 static unsigned long long* g_attn_tl_host = nullptr;
 
-static int attn_version() {   // MOS_ATTN_V1=1 selects the first-generation kernel (A/B measurements only)
-  static int v = 0;
-  if (v == 0) {
-    const char* e = getenv("MOS_ATTN_V1");
-    v = (e && e[0] == '1') ? 1 : 2;
-  }
-  return v;
-}
-
-template <int D, bool WIDE>
+template <int D, bool ONE>
 static int launch_attn(const void* Q, const void* K, const void* Vt, void* out, int64_t ldo, float* probs, int BH,
                        int heads, int nq, int nk, int nk8, float scale, cudaStream_t stream, float* lse2 = nullptr,
                        float* pcols = nullptr, const int* pos = nullptr) {
-  using C = AttnCfg<D, WIDE>;
+  using C = AttnCfg<D, ONE>;
   CUtensorMap tmQ, tmK, tmV;
   {
     uint64_t dims[3] = {(uint64_t)C::DP, (uint64_t)nq, (uint64_t)BH};
@@ -778,28 +526,18 @@ static int launch_attn(const void* Q, const void* K, const void* Vt, void* out, 
   p.lse2 = lse2;
   p.pcols = pcols;
   p.pos = pos;
-  static int dbg = -1;
-  if (dbg < 0) {
-    const char* e = getenv("MOS_ATTN_DBG");
-    dbg = e ? atoi(e) : 0;
-  }
-  p.dbg = dbg;
   p.tl = g_attn_tl_host;
   static bool configured = false;
   if (!configured) {
-    MOS_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel<D, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    MOS_CHECK_CUDA(cudaFuncSetAttribute(attn2_kernel<D, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        AttnCfg2<D, WIDE>::SMEM_BYTES));
+    MOS_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel<D, ONE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    MOS_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel<D, ONE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
   }
   dim3 grid((unsigned)ceil_div(nq, 128), (unsigned)BH);
-  if (attn_version() == 1) {
-    MOS_CHECK_CUDA(launch_pdl(attn_kernel<D, WIDE>, grid, dim3(192), (size_t)C::SMEM_BYTES, stream, tmQ, tmK, tmV, p));
-  } else {
-    const size_t smem = (dbg & 4) ? (size_t)(120 * 1024) : (size_t)AttnCfg2<D, WIDE>::SMEM_BYTES;
-    if (dbg & 4) MOS_CHECK_CUDA(cudaFuncSetAttribute(attn2_kernel<D, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
-    MOS_CHECK_CUDA(launch_pdl(attn2_kernel<D, WIDE>, grid, dim3(192), smem, stream, tmQ, tmK, tmV, p));
-  }
+  if (p.tl != nullptr)
+    MOS_CHECK_CUDA(launch_pdl(attn_kernel<D, ONE, true>, grid, dim3(192), (size_t)C::SMEM_BYTES, stream, tmQ, tmK, tmV, p));
+  else
+    MOS_CHECK_CUDA(launch_pdl(attn_kernel<D, ONE, false>, grid, dim3(192), (size_t)C::SMEM_BYTES, stream, tmQ, tmK, tmV, p));
   return MOS_OK;
 }
 
@@ -818,7 +556,9 @@ extern "C" int mos_attention_fwd(const void* Q, const void* K, const void* Vt, v
   const int BH = batch * heads;
   if (probs) MOS_CHECK_ARG(nk <= 128, "mos_attention_fwd: probs output needs a single kv tile (nk <= 128)");
   switch (head_dim) {
-    case 40: return launch_attn<40, false>(Q, K, Vt, out, ldo, probs, BH, heads, nq, nk, nk8, scale, stream);
+    case 40:
+      if (nk <= 128) return launch_attn<40, true>(Q, K, Vt, out, ldo, probs, BH, heads, nq, nk, nk8, scale, stream);
+      return launch_attn<40, false>(Q, K, Vt, out, ldo, probs, BH, heads, nq, nk, nk8, scale, stream);
     case 80: return launch_attn<80, false>(Q, K, Vt, out, ldo, probs, BH, heads, nq, nk, nk8, scale, stream);
     case 160:
       if (nk <= 128) return launch_attn<160, true>(Q, K, Vt, out, ldo, probs, BH, heads, nq, nk, nk8, scale, stream);
@@ -845,7 +585,10 @@ extern "C" int mos_attention_fwd_train(const void* Q, const void* K, const void*
   const int BH = batch * heads;
   const int* ip = reinterpret_cast<const int*>(pos);
   switch (head_dim) {
-    case 40: return launch_attn<40, false>(Q, K, Vt, out, ldo, nullptr, BH, heads, nq, nk, nk8, scale, stream, lse2, pcols, ip);
+    case 40:
+      if (nk <= 128)
+        return launch_attn<40, true>(Q, K, Vt, out, ldo, nullptr, BH, heads, nq, nk, nk8, scale, stream, lse2, pcols, ip);
+      return launch_attn<40, false>(Q, K, Vt, out, ldo, nullptr, BH, heads, nq, nk, nk8, scale, stream, lse2, pcols, ip);
     case 80: return launch_attn<80, false>(Q, K, Vt, out, ldo, nullptr, BH, heads, nq, nk, nk8, scale, stream, lse2, pcols, ip);
     case 160:
       if (nk <= 128)

@@ -33,7 +33,10 @@ struct BwdCfg {
   static constexpr int DV = ((D + 15) / 16) * 16;
   static constexpr int OSTR = ((DV + 63) / 64) * 64;
   // ---- dQ kernel: inner tile = keys
-  static constexpr int BTA = D <= 80 ? 128 : 64;
+  // d = 40: 64-wide inner tiles, 256 TMEM columns and <= 113 KB smem, so that TWO CTAs share an SM: every tile is a
+  // serial chain (S, dP on the tensor pipe -> dS by the row threads -> dQ), and the second CTA fills the bubbles.
+  static constexpr int BTA = D <= 40 ? 64 : (D <= 80 ? 128 : 64);
+  static constexpr int MINB = D <= 40 ? 2 : 1;
   static constexpr int KCHA = BTA / 64;
   static constexpr int A_Q_BYTES = QCH * 128 * 128;           // Q or dO tile [128, DP]
   static constexpr int A_K_BYTES = QCH * BTA * 128;           // K or V tile [BTA, DP]
@@ -41,9 +44,10 @@ struct BwdCfg {
   static constexpr int A_DS_BYTES = KCHA * 128 * 128;         // dS [128, BTA]
   static constexpr int A_SMEM = 2 * A_Q_BYTES + 2 * A_K_BYTES + A_KT_BYTES + A_DS_BYTES + 1024;
   static constexpr int A_DQ_COL = 2 * BTA;
-  static_assert(A_DQ_COL + OSTR <= 512, "TMEM budget (dq)");
+  static constexpr int A_TMEM = (A_DQ_COL + OSTR <= 256) ? 256 : 512;
+  static_assert(A_DQ_COL + OSTR <= A_TMEM, "TMEM budget (dq)");
   // ---- dK/dV kernel: inner tile = queries
-  static constexpr int BTB = D <= 40 ? 128 : 64;
+  static constexpr int BTB = 64;
   static constexpr int KCHB = BTB / 64;
   static constexpr int B_K_BYTES = QCH * 128 * 128;           // K or V tile [128, DP]
   static constexpr int B_Q_BYTES = QCH * BTB * 128;           // Q or dO tile [BTB, DP]
@@ -52,7 +56,8 @@ struct BwdCfg {
   static constexpr int B_SMEM = 2 * B_K_BYTES + 2 * B_Q_BYTES + 2 * B_QT_BYTES + 2 * B_P_BYTES + 1024;
   static constexpr int B_DK_COL = 2 * BTB;
   static constexpr int B_DV_COL = 2 * BTB + OSTR;
-  static_assert(B_DV_COL + OSTR <= 512, "TMEM budget (dkv)");
+  static constexpr int B_TMEM = (B_DV_COL + OSTR <= 256) ? 256 : 512;
+  static_assert(B_DV_COL + OSTR <= B_TMEM, "TMEM budget (dkv)");
   static_assert(A_SMEM <= 227 * 1024 - 2048 && B_SMEM <= 227 * 1024 - 2048, "smem budget");
 };
 
@@ -88,7 +93,7 @@ __device__ __forceinline__ void store_row32_sw128(uint8_t* tile, int r, int c /*
 
 // =================================================================================================== dQ
 template <int D>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, BwdCfg<D>::MINB)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    const __grid_constant__ CUtensorMap tmKt, const BwdDev p) {
@@ -127,7 +132,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(&dq_full, 1);
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(&tmem_holder, 512);
+  if (warp == 5) tmem_alloc(&tmem_holder, C::A_TMEM);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -269,13 +274,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   if (warp == 5) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    tmem_dealloc(tmem, C::A_TMEM);
   }
 }
 
 // =================================================================================================== dK, dV
 template <int D>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, BwdCfg<D>::MINB)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                     const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                     const __grid_constant__ CUtensorMap tmQt, const __grid_constant__ CUtensorMap tmdOt,
@@ -319,7 +324,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     mbar_init(&out_full, 1);
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(&tmem_holder, 512);
+  if (warp == 5) tmem_alloc(&tmem_holder, C::B_TMEM);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -483,7 +488,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   __syncthreads();
   if (warp == 5) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    tmem_dealloc(tmem, C::B_TMEM);
   }
 }
 

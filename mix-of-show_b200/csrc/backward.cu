@@ -287,14 +287,14 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, int DP, 
 // y = x W^T + alpha (x D^T) U^T  (edlora.py:244-246), dY given:
 //   dU[n, r] = alpha sum_m dY[m, n] t[m, r],  t = x D^T ;   dD[r, k] = alpha sum_m s[m, r] x[m, k],  s = dY U
 // Both gradients are skinny reductions over the M rows.  One block owns a slab of R rows (R chosen on the host so that
-// at most 64 blocks exist):
-//   step 1  t, s of every slab row -> smem (one thread per row; D and U staged in smem, read as broadcasts)
+// at most 128 blocks exist):
+//   step 1  t, s of every slab row -> smem (thread = (row, column part); D and U staged in smem, read as broadcasts)
 //   step 2  thread (row group g of 4, lane) owns an 8-column chunk of x (-> dD) or dY (-> dU): one 128-bit load and 32
 //           FMAs per row; the 4 row groups are summed in a fixed order through smem
-// and writes its partial [4K + 4N]; lora_grad_reduce_kernel sums the <= 64 partials in a fixed order (bitwise
+// and writes its partial [4K + 4N]; lora_grad_reduce_kernel sums the <= 128 partials in a fixed order (bitwise
 // reproducible).  (The first version spent 16.6 ms of a 49.7 ms training step here; profiles/README.md.)
 constexpr int LG_THREADS = 256;
-constexpr int LG_MAX_BLOCKS = 64;
+constexpr int LG_MAX_BLOCKS = 128;
 
 __global__ void __launch_bounds__(LG_THREADS)
 lora_grad_partial_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ dy,
@@ -315,40 +315,55 @@ lora_grad_partial_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, con
   for (int i = tid * 4; i < 4 * N; i += LG_THREADS * 4)
     *reinterpret_cast<float4*>(sU + i) = __ldg(reinterpret_cast<const float4*>(up + i));
   __syncthreads();
-  // ---- step 1: t = x D^T, s = dY U for every row of the slab
-  for (int r = tid; r < rows; r += LG_THREADS) {
+  // ---- step 1: t = x D^T, s = dY U for every row of the slab.  Thread = (row, part): with R <= 128 rows the 256 threads
+  // split every row's columns P = 256 / R ways (chunk c goes to part c mod P); partial dots are summed in a fixed order.
+  const int P = R >= LG_THREADS ? 1 : LG_THREADS / R;
+  float* tsp = P > 1 ? red : ts;       // [P][R][8] partial dots (aliases the step-2 reduction buffer; P * R * 8 <= 2048)
+  for (int idx = tid; idx < R * P; idx += LG_THREADS) {
+    const int r = idx % R, part = idx / R;
     float t[4] = {0.f, 0.f, 0.f, 0.f}, sv[4] = {0.f, 0.f, 0.f, 0.f};
-    const __nv_bfloat16* xr = x + (m0 + r) * ldx;
-#pragma unroll 4
-    for (int k = 0; k < K; k += 8) {
-      float v[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(xr + k)), v);
+    if (r < rows) {
+      const __nv_bfloat16* xr = x + (m0 + r) * ldx;
+#pragma unroll 8
+      for (int k = part * 8; k < K; k += P * 8) {
+        float v[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(xr + k)), v);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 d0 = *reinterpret_cast<const float4*>(sD + q * K + k);
-        const float4 d1 = *reinterpret_cast<const float4*>(sD + q * K + k + 4);
-        t[q] += v[0] * d0.x + v[1] * d0.y + v[2] * d0.z + v[3] * d0.w + v[4] * d1.x + v[5] * d1.y + v[6] * d1.z +
-                v[7] * d1.w;
+        for (int q = 0; q < 4; ++q) {
+          const float4 d0 = *reinterpret_cast<const float4*>(sD + q * K + k);
+          const float4 d1 = *reinterpret_cast<const float4*>(sD + q * K + k + 4);
+          t[q] += v[0] * d0.x + v[1] * d0.y + v[2] * d0.z + v[3] * d0.w + v[4] * d1.x + v[5] * d1.y + v[6] * d1.z +
+                  v[7] * d1.w;
+        }
+      }
+      const __nv_bfloat16* dr = dy + (m0 + r) * lddy;
+#pragma unroll 8
+      for (int n = part * 8; n < N; n += P * 8) {
+        float v[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dr + n)), v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 u = *reinterpret_cast<const float4*>(sU + (n + i) * 4);
+          sv[0] += v[i] * u.x;
+          sv[1] += v[i] * u.y;
+          sv[2] += v[i] * u.z;
+          sv[3] += v[i] * u.w;
+        }
       }
     }
-    const __nv_bfloat16* dr = dy + (m0 + r) * lddy;
-#pragma unroll 4
-    for (int n = 0; n < N; n += 8) {
-      float v[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(dr + n)), v);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 u = *reinterpret_cast<const float4*>(sU + (n + i) * 4);
-        sv[0] += v[i] * u.x;
-        sv[1] += v[i] * u.y;
-        sv[2] += v[i] * u.z;
-        sv[3] += v[i] * u.w;
-      }
-    }
-    *reinterpret_cast<float4*>(ts + r * 8) = make_float4(t[0], t[1], t[2], t[3]);
-    *reinterpret_cast<float4*>(ts + r * 8 + 4) = make_float4(sv[0], sv[1], sv[2], sv[3]);
+    float* o = tsp + ((long long)part * R + r) * 8;
+    *reinterpret_cast<float4*>(o) = make_float4(t[0], t[1], t[2], t[3]);
+    *reinterpret_cast<float4*>(o + 4) = make_float4(sv[0], sv[1], sv[2], sv[3]);
   }
   __syncthreads();
+  if (P > 1) {
+    for (int i = tid; i < R * 8; i += LG_THREADS) {
+      float a = 0.f;
+      for (int part = 0; part < P; ++part) a += tsp[(long long)part * R * 8 + i];
+      ts[i] = a;
+    }
+    __syncthreads();
+  }
   // ---- step 2: dD[q, k] = sum_r s[r, q] x[r, k];  dU[n, q] = sum_r t[r, q] dY[r, n]
   const int g = tid >> 6, ln = tid & 63;
   const int CK = K / 8, CH = CK + N / 8;
@@ -368,7 +383,7 @@ lora_grad_partial_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, con
       const __nv_bfloat16* base = isx ? x + m0 * ldx + c * 8 : dy + m0 * lddy + (c - CK) * 8;
       const long long ld = isx ? ldx : lddy;
       const float* w = ts + (isx ? 4 : 0);
-#pragma unroll 4
+#pragma unroll 8
       for (int r = r_lo; r < r_hi; ++r) {
         float v[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(base + r * ld)), v);
@@ -683,8 +698,9 @@ extern "C" int mos_lora_grad(const void* x, int64_t ldx, const void* dy, int64_t
   MOS_CHECK_ARG(x && dy && down && up && workspace && d_down && d_up, "mos_lora_grad: NULL pointer");
   MOS_CHECK_ARG(K % 8 == 0 && N % 8 == 0 && ldx % 8 == 0 && lddy % 8 == 0 && M > 0, "mos_lora_grad: bad shape");
   // slab height: a multiple of 64 rows such that at most LG_MAX_BLOCKS blocks exist
-  long long R = ceil_div(ceil_div(M, (long long)LG_MAX_BLOCKS), 64LL) * 64;
+  long long R = ceil_div(ceil_div(M, (long long)LG_MAX_BLOCKS), 16LL) * 16;   // 16 | R, and R | 256 or 256 | R below
   if (R > 1024) R = 1024;
+  if (R < 256) { long long p2 = 16; while (p2 < R) p2 *= 2; R = p2; } else R = ceil_div(R, 256LL) * 256;
   const int nb = (int)ceil_div(M, R);
   MOS_CHECK_ARG((long long)nb * 4 * (K + N) <= workspace_floats, "mos_lora_grad: workspace too small (need %lld floats)",
                 (long long)nb * 4 * (K + N));

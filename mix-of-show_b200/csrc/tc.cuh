@@ -74,6 +74,38 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// try_wait with a suspend-time hint: the hardware may park the thread (no issue slots used) until the phase completes
+// or `ns` nanoseconds pass.  A plain try_wait returns after ~50 cycles on B200, so a polling single-thread role
+// (TMA producer, MMA issuer) otherwise burns ~15 % of its scheduler's issue slots next to the busy softmax warps
+// (ncu source view of the attention kernel: profiles/README.md).
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait built on it; the clock is only consulted every 1024 polls.
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns = 2000) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = 0;
+  uint32_t n = 0;
+  while (!mbar_try_wait_hint(bar, parity, ns)) {
+    if ((++n & 1023u) == 0) {
+      const long long t = clock64();
+      if (t0 == 0) t0 = t;
+      if (t - t0 > 4000000000LL) {
+        printf("mos: mbarrier timeout block(%d,%d,%d) thread %d\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+        __trap();
+      }
+    }
+  }
+}
+
 // Same with a nanosleep back-off between polls: for single-thread roles that wait long and share a scheduler with
 // busy warps.
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {

@@ -178,7 +178,7 @@ class TrainEngine(UNetEngine):
         return self.buf('T.' + tag, shape, dtype, zero)
 
     def _lg_ws(self, M, K, N):
-        need = ((M + 63) // 64) * 4 * (K + N)
+        need = 128 * 4 * (K + N)            # mos_lora_grad: at most 128 row slabs, one partial [4K + 4N] each
         cur = getattr(self, '_lg_buf', None)
         if cur is None or cur.numel() < need:
             self._lg_buf = torch.empty(max(need, 1 << 20), device=self.dev)

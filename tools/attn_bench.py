@@ -1,5 +1,5 @@
 """Device time of the flash-attention kernel at the shapes of one SD1.5 denoise step (CFG batch 2, 8 heads).
-  python tools/attn_bench.py [--batch 2]        (MOS_ATTN_V1=1 selects the first-generation kernel for A/B)
+  python tools/attn_bench.py [--batch 2]
 Algorithmic FLOPs = 4 * nq * nk * d per (batch, head); time = CUDA events over 20 back-to-back launches."""
 import argparse
 import os
@@ -16,7 +16,7 @@ ap.add_argument('--batch', type=int, default=2)
 ap.add_argument('--reps', type=int, default=20)
 a = ap.parse_args()
 B, H = a.batch, 8
-print(f'kernel version: {"v1" if os.environ.get("MOS_ATTN_V1") == "1" else "v2"}  batch {B}')
+print(f'batch {B}')
 for d, nq, nk in [(40, 4096, 4096), (80, 1024, 1024), (160, 256, 256), (160, 64, 64), (40, 4096, 77), (80, 1024, 77),
                   (160, 256, 77), (40, 18432, 18432)]:
     if nq > 8192 and B > 2:
@@ -41,6 +41,6 @@ for d, nq, nk in [(40, 4096, 4096), (80, 1024, 1024), (160, 256, 256), (160, 64,
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / a.reps * 1e3
     fl = 4.0 * nq * nk * d * B * H
-    tiles = B * H * -(-nq // 128) * -(-nk // (128 if d <= 80 or nk <= 128 else 64))
+    tiles = B * H * -(-nq // 128) * -(-nk // 128)
     print(f'd={d:3d} nq={nq:5d} nk={nk:5d}: {us:9.1f} us  {fl / us / 1e6:7.1f} TFLOP/s (algorithmic)  '
-          f'{us * 1e-6 * 1.965e9 * 148 / tiles:7.0f} SM-cycles per kv tile')
+          f'{us * 1e-6 * 1.965e9 * 148 / tiles:7.0f} SM-cycles per 128x128 block')
