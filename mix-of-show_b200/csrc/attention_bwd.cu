@@ -108,7 +108,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* sKt = sV + C::A_K_BYTES;
   uint8_t* sdS = sKt + C::A_KT_BYTES;
 
-  __shared__ uint64_t qdo_full, kv_full, kv_empty, sdp_full, sdp_empty, ds_full, ds_empty, dq_full;
+  __shared__ uint64_t qdo_full, kv_full, kv_empty, kt_full, kt_empty, sdp_full, sdp_empty, ds_full, ds_empty, dq_full;
   __shared__ uint32_t tmem_holder;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -125,6 +125,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(&qdo_full, 1);
     mbar_init(&kv_full, 1);
     mbar_init(&kv_empty, 1);
+    mbar_init(&kt_full, 1);
+    mbar_init(&kt_empty, 1);
     mbar_init(&sdp_full, 1);
     mbar_init(&sdp_empty, 128);
     mbar_init(&ds_full, 128);
@@ -148,17 +150,21 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tma_load_3d(sQ + c * 16384, &tmQ, &qdo_full, c * 64, q0, bh);
         tma_load_3d(sdO + c * 16384, &tmdO, &qdo_full, c * 64, q0, bh);
       }
+      // K / V row tiles are only read by the S and dP products and K^T only by the dQ product: each buffer is released
+      // as soon as its last reader has retired, so the next tile's loads fly while the row threads compute dS.
       for (int j = 0; j < T; ++j) {
         mbar_wait(&kv_empty, (j & 1) ^ 1);
-        mbar_expect_tx(&kv_full, 2 * C::A_K_BYTES + C::A_KT_BYTES);
+        mbar_expect_tx(&kv_full, 2 * C::A_K_BYTES);
 #pragma unroll
         for (int c = 0; c < C::QCH; ++c) {
           tma_load_3d(sK + c * (BT * 128), &tmK, &kv_full, c * 64, j * BT, bh);
           tma_load_3d(sV + c * (BT * 128), &tmV, &kv_full, c * 64, j * BT, bh);
         }
+        mbar_wait(&kt_empty, (j & 1) ^ 1);
+        mbar_expect_tx(&kt_full, C::A_KT_BYTES);
 #pragma unroll
         for (int c = 0; c < C::KCHA; ++c)
-          tma_load_3d(sKt + c * (C::DV * 128), &tmKt, &kv_full, j * BT + c * 64, 0, bh);
+          tma_load_3d(sKt + c * (C::DV * 128), &tmKt, &kt_full, j * BT + c * 64, 0, bh);
       }
     }
   } else if (warp == 5) {
@@ -183,7 +189,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           umma_bf16(tmem + BT, ad, bv, idesc_s, kk > 0 ? 1u : 0u);
         }
         umma_commit(&sdp_full);
+        umma_commit(&kv_empty);          // K / V row tiles are free once S and dP have retired
         mbar_wait(&ds_full, j & 1);
+        mbar_wait(&kt_full, j & 1);
         tc_fence_after();
         const int kv_valid = min(BT, p.nk - j * BT);
         const int ksteps = (kv_valid + 15) >> 4;
@@ -193,7 +201,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           umma_bf16(tmem + C::A_DQ_COL, as, bt, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
         }
         umma_commit(&ds_empty);
-        umma_commit(&kv_empty);
+        umma_commit(&kt_empty);
       }
       umma_commit(&dq_full);
     }
@@ -298,7 +306,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   uint8_t* sPt = sdOt + C::B_QT_BYTES;
   uint8_t* sdSt = sPt + C::B_P_BYTES;
 
-  __shared__ uint64_t kv_full, q_full, q_empty, stp_full, stp_empty, pds_full, pds_empty, out_full;
+  __shared__ uint64_t kv_full, q_full, q_empty, qt_full, qt_empty, stp_full, stp_empty, pds_full, pds_empty, out_full;
   __shared__ uint32_t tmem_holder;
   __shared__ float sL[2][BT], sDl[2][BT], sG0[2][BT], sG1[2][BT];
 
@@ -317,6 +325,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     mbar_init(&kv_full, 1);
     mbar_init(&q_full, 1);
     mbar_init(&q_empty, 1);
+    mbar_init(&qt_full, 1);
+    mbar_init(&qt_empty, 1);
     mbar_init(&stp_full, 1);
     mbar_init(&stp_empty, 128);
     mbar_init(&pds_full, 128);
@@ -340,18 +350,22 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         tma_load_3d(sK + c * 16384, &tmK, &kv_full, c * 64, k0, bh);
         tma_load_3d(sV + c * 16384, &tmV, &kv_full, c * 64, k0, bh);
       }
+      // Q / dO row tiles are only read by the S^T and dP^T products, Q^T / dO^T only by the dK / dV products: early
+      // release as in the dQ kernel.
       for (int i = 0; i < T; ++i) {
         mbar_wait(&q_empty, (i & 1) ^ 1);
-        mbar_expect_tx(&q_full, 2 * C::B_Q_BYTES + 2 * C::B_QT_BYTES);
+        mbar_expect_tx(&q_full, 2 * C::B_Q_BYTES);
 #pragma unroll
         for (int c = 0; c < C::QCH; ++c) {
           tma_load_3d(sQ + c * (BT * 128), &tmQ, &q_full, c * 64, i * BT, bh);
           tma_load_3d(sdO + c * (BT * 128), &tmdO, &q_full, c * 64, i * BT, bh);
         }
+        mbar_wait(&qt_empty, (i & 1) ^ 1);
+        mbar_expect_tx(&qt_full, 2 * C::B_QT_BYTES);
 #pragma unroll
         for (int c = 0; c < C::KCHB; ++c) {
-          tma_load_3d(sQt + c * (C::DV * 128), &tmQt, &q_full, i * BT + c * 64, 0, bh);
-          tma_load_3d(sdOt + c * (C::DV * 128), &tmdOt, &q_full, i * BT + c * 64, 0, bh);
+          tma_load_3d(sQt + c * (C::DV * 128), &tmQt, &qt_full, i * BT + c * 64, 0, bh);
+          tma_load_3d(sdOt + c * (C::DV * 128), &tmdOt, &qt_full, i * BT + c * 64, 0, bh);
         }
       }
     }
@@ -377,7 +391,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
           umma_bf16(tmem + BT, av, bd, idesc_s, kk > 0 ? 1u : 0u);
         }
         umma_commit(&stp_full);
+        umma_commit(&q_empty);           // Q / dO row tiles are free once S^T and dP^T have retired
         mbar_wait(&pds_full, i & 1);
+        mbar_wait(&qt_full, i & 1);
         tc_fence_after();
         const int q_valid = min(BT, p.nq - i * BT);
         const int ksteps = (q_valid + 15) >> 4;
@@ -392,7 +408,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
           umma_bf16(tmem + C::B_DK_COL, as, bq, idesc_o, (i > 0 || kk > 0) ? 1u : 0u);
         }
         umma_commit(&pds_empty);
-        umma_commit(&q_empty);
+        umma_commit(&qt_empty);
       }
       umma_commit(&out_full);
     }

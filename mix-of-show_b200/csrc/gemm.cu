@@ -70,6 +70,7 @@ struct GemmDev {
   int heads, head_dim, dpad, dv_pad;
   long long tokens_per_batch;
   int accum;           // MOS_OUT_F32: out += result (Gram accumulation)
+  unsigned long long* tl;   // optional timeline buffer (mos_debug_set_timeline)
 };
 
 __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v) {
@@ -92,16 +93,17 @@ __device__ __forceinline__ void cp_async_wait_all() {
 }
 
 // ---- optional in-kernel timeline (profiling aid): when a buffer is registered through mos_debug_set_timeline, the
-// first 8 CTAs of every gemm launch record %globaltimer stamps (ns) at their phase boundaries.
-__device__ unsigned long long* g_timeline = nullptr;
-__device__ __forceinline__ void stamp(int slot) {
-  unsigned long long* tl = g_timeline;
-  if (tl != nullptr && blockIdx.x < 8) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    tl[blockIdx.x * 8 + slot] = t;
-  }
-}
+// first 8 CTAs of every gemm launch record %globaltimer stamps (ns) at their phase boundaries.  The pointer travels in
+// the kernel parameters (constant bank): a __device__ global would cost an L2 round trip at every stamp site, on the
+// critical path of the TMA / MMA threads.
+#define stamp(slot)                                                       \
+  do {                                                                    \
+    if (p.tl != nullptr && blockIdx.x < 8) {                              \
+      unsigned long long t_;                                              \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));              \
+      p.tl[blockIdx.x * 8 + (slot)] = t_;                                 \
+    }                                                                     \
+  } while (0)
 
 struct TileCoord {
   int n0, m0, cb0, ch0, cw0, split;
@@ -568,6 +570,7 @@ __global__ void splitk_finalize_kernel(const float* __restrict__ partial, int sp
   *reinterpret_cast<uint2*>(out + m * ldc + n) = o;
 }
 
+static unsigned long long* g_timeline_host = nullptr;
 static bool is_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 static int ilog2(int v) {
   int l = 0;
@@ -740,6 +743,7 @@ extern "C" int mos_gemm_bf16(const mos_gemm_args* a, void* stream_) {
   p.dv_pad = a->dv_pad;
   p.tokens_per_batch = a->tokens_per_batch > 0 ? a->tokens_per_batch : 1;
   p.accum = a->accumulate;
+  p.tl = g_timeline_host;
   if (a->bias_batch && !a->conv)
     MOS_CHECK_ARG(p.rows_per_batch >= 32, "mos_gemm_bf16: bias_batch needs rows_per_batch >= 32 in plain mode");
   p.total_super = (p.n_tiles / p.cx) * (m_tiles / p.cm) * splits;
@@ -806,8 +810,7 @@ extern "C" int mos_gemm_bf16(const mos_gemm_args* a, void* stream_) {
 }
 
 extern "C" int mos_debug_set_timeline(void* buf) {
-  unsigned long long* p = reinterpret_cast<unsigned long long*>(buf);
-  MOS_CHECK_CUDA(cudaMemcpyToSymbol(mos::g_timeline, &p, sizeof(p)));
+  mos::g_timeline_host = reinterpret_cast<unsigned long long*>(buf);
   return MOS_OK;
 }
 
