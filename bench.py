@@ -328,10 +328,11 @@ def main():
     if roof is not None:
         frac = roof['achieved'] / peaks['tflops']
         out['roofline'] = {'bound': 'tensor', 'achieved': roof['achieved'], 'peak': peaks['tflops'], 'unit': 'TFLOP/s',
-                           'frac': frac, 'traffic': 8.0e6,
-                           'traffic_note': 'mean dram__bytes_read+write per launch over the 12 launches of '
-                                           'profiles/r1_gemm_full_v2.ncu-rep (2-27 MB read, ~0 written: outputs stay '
-                                           'in the 126 MB L2); algorithmic operand bytes per launch are 2-40 MB',
+                           'frac': frac, 'traffic': 15.9e6,
+                           'traffic_note': 'mean dram__bytes_read+write per launch over the first 40 gemm launches of one '
+                                           'step (profiles/r1_gemm_full_v4_summary.csv, ncu --set full): 1.3-170 MB, e.g. '
+                                           '7.2-12.4 MB for the res-64 3x3 conv whose algorithmic operand bytes are 7.0 MB '
+                                           '(DRAM traffic ~ algorithmic; the re-reads are L2->SM: 212 MB for that launch)',
                            'method': 'T(graph step) - T(graph step without gemm launches), CUDA events',
                            'peak_source': peaks['src'] + ' (bf16_tflops_sustained)',
                            'kernel': 'mos::gemm_kernel (tcgen05 GEMM + implicit-GEMM conv3x3)',

@@ -67,6 +67,9 @@ typedef struct mos_gemm_args {
   int32_t heads, head_dim, dpad, dv_pad;
   int64_t tokens_per_batch;
   int32_t accumulate;     /* MOS_OUT_F32 only: out += result (Gram accumulation, gradient fusion) */
+  int32_t w_static;       /* 1: W is not written by the kernels just ahead in the stream (model weights): its first tiles
+                           * are requested before griddepcontrol.wait, overlapping the predecessor's tail.  0 = W may be
+                           * an activation (Gram products): every load waits for the dependency. */
 } mos_gemm_args;
 
 int mos_gemm_bf16(const mos_gemm_args* args, void* stream);

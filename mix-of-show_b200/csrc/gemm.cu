@@ -71,6 +71,7 @@ struct GemmDev {
   long long tokens_per_batch;
   int accum;           // MOS_OUT_F32: out += result (Gram accumulation)
   unsigned long long* tl;   // optional timeline buffer (mos_debug_set_timeline)
+  int w_static;        // W tiles may be requested before griddepcontrol.wait
 };
 
 __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v) {
@@ -225,9 +226,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   // Everything above touched no global memory written by the previous kernel in the stream.
   if (threadIdx.x == 0) stamp(1);
-  pdl_wait();
+  const bool is_producer = warp == 0 && lane == 0;
+  if (!is_producer) pdl_wait();
   pdl_launch_dependents();
-  if (threadIdx.x == 0) stamp(2);
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -238,17 +239,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (int j = 0; j < p.cm; ++j) mask_b |= (uint16_t)(1u << (j * p.cx + nx));
       const int a_rows = BM / p.cx;           // rows of A this CTA fetches
       const int b_rows = BN / p.cm;           // rows of W this CTA fetches
+      // The weights are static: request the W tiles of the first ring pass BEFORE waiting for the previous kernel, so
+      // that their HBM round trip overlaps the predecessor's tail (the 1.72 GB of weights stream from HBM every step;
+      // the activations behind the dependency come from L2).  A (and the LoRA rows, which the training step rewrites)
+      // follow after griddepcontrol.wait and complete the same mbarrier transaction.
+      int pre = 0;
+      if (p.w_static && csize == 1 && cluster_id < p.total_super) {
+        const TileCoord t0 = item_coord(p, cluster_id, nx, my);
+        const int kb0 = t0.split * p.kb_per_split;
+        pre = min(p.stages, min(p.kb_total, kb0 + p.kb_per_split) - kb0);
+        for (int i = 0; i < pre; ++i) {
+          mbar_expect_tx(&full_bar[i], (uint32_t)stage_bytes);
+          tma_load_2d(smem + i * stage_bytes + A_STAGE_BYTES, &tmB, &full_bar[i], (kb0 + i) * BK, t0.n0);
+        }
+      }
+      pdl_wait();
+      stamp(2);
       int stage = 0;
       uint32_t phase = 0;
+      int issued = 0;
       for (int ws = cluster_id; ws < p.total_super; ws += num_clusters) {
         const TileCoord t = item_coord(p, ws, nx, my);
         const int kb_begin = t.split * p.kb_per_split;
         const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);   // every CTA of the cluster has released this slot
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++issued) {
+          const bool w_requested = issued < pre;     // W tile already in flight, transaction bytes already expected
           uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + A_STAGE_BYTES;
-          mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+          if (!w_requested) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);   // every CTA of the cluster has released this slot
+            mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+          }
           uint8_t* sa_dst = sa + nx * a_rows * 128;
           if (p.conv) {
             const int tap = kb / p.kc_per_tap;
@@ -268,7 +289,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           if (p.cm > 1)
             tma_load_2d_mc(sb + my * b_rows * 128, &tmB, &full_bar[stage], kb * BK, t.n0 + my * b_rows, mask_b);
-          else
+          else if (!w_requested)
             tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, t.n0);
           if (p.lora) tma_load_2d(sb + B_STAGE_BYTES, &tmL, &full_bar[stage], kb * BK, 0);
           if (++stage == p.stages) {
@@ -744,6 +765,7 @@ extern "C" int mos_gemm_bf16(const mos_gemm_args* a, void* stream_) {
   p.tokens_per_batch = a->tokens_per_batch > 0 ? a->tokens_per_batch : 1;
   p.accum = a->accumulate;
   p.tl = g_timeline_host;
+  p.w_static = a->w_static;
   if (a->bias_batch && !a->conv)
     MOS_CHECK_ARG(p.rows_per_batch >= 32, "mos_gemm_bf16: bias_batch needs rows_per_batch >= 32 in plain mode");
   p.total_super = (p.n_tiles / p.cx) * (m_tiles / p.cm) * splits;

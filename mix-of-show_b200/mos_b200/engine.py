@@ -11,6 +11,7 @@ of the up-block concat buffer that will consume them, so `torch.cat([h, skip])` 
 There is no CPU / PyTorch fallback: every arithmetic op below is a C-ABI call into the CUDA library.
 """
 import math
+import os
 
 import torch
 
@@ -18,6 +19,9 @@ from . import ops
 from ._lib import MOS_SEG_ROWS, MOS_SEG_TRANSPOSED
 
 BF16 = torch.bfloat16
+# Experiment (opt-in, MOS_GEMM_PREFETCH_W=1): request the first weight tiles of every GEMM before griddepcontrol.wait.
+# Measured on B200 in round 1: no gain for the batch-2 denoise step (6.41 -> 6.55 ms together with a cheaper erf), so off.
+PREFETCH_W = os.environ.get('MOS_GEMM_PREFETCH_W') == '1'
 SKIP_CH = [320, 320, 320, 320, 640, 640, 640, 1280, 1280, 1280, 1280, 1280]
 
 
@@ -272,7 +276,7 @@ class UNetEngine:
         if splits > 1:
             partial = self.buf('splitk', (16 * 1024 * 1280,), torch.float32)
             assert splits * M * ent['N'] <= partial.numel()
-            ops.gemm(A, ent['W'], None, M=M, splits=splits, partial=partial, conv=conv, lda=lda)
+            ops.gemm(A, ent['W'], None, M=M, splits=splits, partial=partial, conv=conv, lda=lda, w_static=PREFETCH_W)
             if 'splitk' not in self.skip:
               ops.splitk_finalize(partial, splits, M, ent['N'], out, bias=ent['bias'], bias_batch=bias_batch,
                                   rows_per_batch=rows_per_batch, residual=residual,
@@ -282,7 +286,8 @@ class UNetEngine:
         if lora:
             kw.update(lora_down=ent['lora_down'], lora_up=ent['lora_up'], lora_seg=ent['lora_seg'])
         ops.gemm(A, ent['W'], out, M=M, residual=residual, bias_batch=bias_batch, rows_per_batch=rows_per_batch,
-                 bias_batch_ld=self.temb_total if bias_batch is not None else 0, geglu=geglu, heads=heads, **kw)
+                 bias_batch_ld=self.temb_total if bias_batch is not None else 0, geglu=geglu, heads=heads, w_static=PREFETCH_W,
+                 **kw)
         self.launches += 1
         return out
 

@@ -32,8 +32,31 @@ eng.in_t.fill_(981.0)
 for _ in range(args.runs):          # warm-up runs (allocate scratch, set attributes)
     eng._run()
 torch.cuda.synchronize()
+# log the shape of every tcgen05 GEMM launch of the profiled step, in launch order (-> gpurun_out/gemm_shapes.csv), so
+# that the per-launch times of the ncu list can be attributed to layer shapes
+from mos_b200 import ops  # noqa: E402
+
+shapes = []
+_orig = ops.gemm
+
+
+def _logging_gemm(A, W, out=None, **kw):
+    conv = kw.get('conv')
+    M = conv[0] * conv[1] * conv[2] if conv is not None else (kw.get('M') or A.shape[0])
+    shapes.append((M, W.shape[0], W.shape[1], int(conv is not None), int(kw.get('lora_down') is not None),
+                   int(bool(kw.get('geglu'))), int(kw.get('heads') is not None), kw.get('splits') or 1))
+    return _orig(A, W, out, **kw)
+
+
+ops.gemm = _logging_gemm
 torch.cuda.profiler.start()         # use with: ncu --profile-from-start off
 eng._run()
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
+ops.gemm = _orig
 print('launches per step:', eng.launches)
+os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+with open(os.path.join(ROOT, 'gpurun_out', 'gemm_shapes.csv'), 'w') as f:
+    f.write('M,N,K,conv,lora,geglu,heads,splits\n')
+    for sh in shapes:
+        f.write(','.join(str(v) for v in sh) + '\n')
