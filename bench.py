@@ -91,7 +91,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- workload
-def build_workload(tiny=False):
+def build_workload(tiny=False, images=1):
     """Oracle-side construction of the synthetic model (weights + LoRA + inputs). The oracle module is used here
     only as the weight initialiser / CPU baseline, never on the measured GPU path."""
     import torch
@@ -103,8 +103,8 @@ def build_workload(tiny=False):
     lora = inject.random_lora_state(unet, seed=10)
     sd = {k: v.clone() for k, v in unet.state_dict().items()}
     H = W = 64
-    lat = torch.randn(1, 4, H, W, generator=torch.Generator().manual_seed(1))
-    ehs = torch.randn(2, 16, 77, 768, generator=torch.Generator().manual_seed(2))
+    lat = torch.randn(images, 4, H, W, generator=torch.Generator().manual_seed(1))
+    ehs = torch.randn(2 * images, 16, 77, 768, generator=torch.Generator().manual_seed(2))   # [uncond x n | cond x n]
     return unet, sd, lora, lat, ehs, cfg
 
 
@@ -175,6 +175,9 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--tiny', action='store_true', help='debug: 2-level UNet')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--images', type=int, default=1,
+                    help='images denoised together per step (default 1 = the BASELINE workload; > 1 is a separate, '
+                         'labelled throughput mode: value counts image-steps)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -209,9 +212,10 @@ def main():
     from mos_b200.engine import UNetEngine, ehs_to_layer_major
     from mos_b200.scheduler import DPMSolverPP2M
 
-    unet, sd, lora, lat, ehs, cfg = build_workload(args.tiny)
+    unet, sd, lora, lat, ehs, cfg = build_workload(args.tiny, args.images)
     kw = dict(block_out=cfg['block_out_channels'], layers=cfg['layers_per_block']) if cfg else {}
-    B, H, W = 2, lat.shape[2], lat.shape[3]
+    n_img = args.images
+    B, H, W = 2 * n_img, lat.shape[2], lat.shape[3]
     eng = UNetEngine(sd, B, H, W, lora=lora, lora_alpha=1.0, device=dev, **kw)
     nx = len(eng.xattn_names)
     sched = DPMSolverPP2M()
@@ -256,7 +260,6 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
     launches = (eng.launches + 1) * args.steps
     final_lat = latents.clone()
 
@@ -270,8 +273,8 @@ def main():
     def e2e_step(i):
         h_t.fill_(ts[i])
         latents.copy_(h_lat, non_blocking=True)
-        eng.in_latents[0].copy_(h_lat[0], non_blocking=True)
-        eng.in_latents[1].copy_(h_lat[0], non_blocking=True)
+        eng.in_latents[:n_img].copy_(h_lat, non_blocking=True)
+        eng.in_latents[n_img:].copy_(h_lat, non_blocking=True)
         eng.in_t.copy_(h_t, non_blocking=True)
         eng.in_ehs.copy_(h_ehs, non_blocking=True)
         eng.run()
@@ -291,6 +294,7 @@ def main():
     g1.record()
     barrier()
     e2e_ms = max(g0.elapsed_time(g1), 1e3 * (time.perf_counter() - t0))
+    clocks = sampler.stop() if rank == 0 else None      # sampled over both timed regions (device-resident and e2e)
     h2d = h_lat.numel() * 4 * 2 + h_t.numel() * 4 + h_ehs.numel() * 2
     d2h = h_out.numel() * 4
 
@@ -310,20 +314,20 @@ def main():
         return
 
     peaks = load_peaks()
-    value = world * args.steps / (ms / 1e3)
-    e2e_value = world * args.steps / (e2e_ms / 1e3)
+    value = world * n_img * args.steps / (ms / 1e3)
+    e2e_value = world * n_img * args.steps / (e2e_ms / 1e3)
     out = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'bf16', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'parallelism': f'replicas x{world} (independent images per GPU, no data-path '
                    'collective; SURVEY.md 8e)', 'l2': 'inputs larger than L2: 1.72 GB of bf16 weights streamed per '
-                   'step vs 126 MB L2, no explicit flush', 'cuda_graph': bool(used_graph)},
+                   'step vs 126 MB L2, no explicit flush', 'cuda_graph': bool(used_graph), 'images_per_step': n_img},
         'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': e2e_ms / args.steps},
         'gpu_launches': launches,
-        'step_tflops': FLOPS_PER_STEP * value / world / 1e12 if not args.tiny else None,
+        'step_tflops': FLOPS_PER_STEP * value / world / 1e12 if not args.tiny else None,   # per GPU, all images
     }
     if roof is not None:
         frac = roof['achieved'] / peaks['tflops']
@@ -338,7 +342,7 @@ def main():
                            'kernel': 'mos::gemm_kernel (tcgen05 GEMM + implicit-GEMM conv3x3)',
                            'launches_per_step': roof['launches'], 'kernel_ms_per_step': roof['ms'],
                            'algorithmic_gflop_per_step': roof['gflop']}
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and n_img == 1:
         t0 = time.perf_counter()
         done, secs = cpu_reference_steps(unet, lora, lat, ehs, 2, 1, budget_s=60.0)
         out['cpu_baseline'] = {'value': done / secs, 'unit': UNIT, 'cores': CPU_THREADS, 'host_cpus': os.cpu_count(),
