@@ -106,20 +106,6 @@ __device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, u
   }
 }
 
-// Same with a nanosleep back-off between polls: for single-thread roles that wait long and share a scheduler with
-// busy warps.
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(40);
-    if (clock64() - t0 > 4000000000LL) {
-      printf("mos: mbarrier timeout block(%d,%d,%d) thread %d\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
-      __trap();
-    }
-  }
-}
-
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
