@@ -138,6 +138,18 @@ int mos_im2col_s2(const void* x, int64_t ldx, int32_t B, int32_t H, int32_t W, i
 /* x[m, :C] += r[m, :C] (T2I-Adapter residuals, pipeline_regionally_t2iadapter.py:565). */
 int mos_add_rows(void* x, int64_t ldx, const void* r, int64_t ldr, int64_t M, int32_t C, void* stream);
 
+/* ---- CLIP text encoder (transformers CLIPTextModel called at pipeline_edlora.py:133-145,
+ * trainer_edlora.py:220-234, gradient_fusion.py:182-199).  The linears and LayerNorms reuse mos_gemm_bf16 / mos_layernorm_fwd. */
+/* x[m, :C] = token_embedding[ids[m]] + position_embedding[m % T] -> bf16 [M, ld]; columns C..ld-1 are zeroed. */
+int mos_clip_embed(const int32_t* ids, const float* token_embedding, const float* position_embedding, int64_t M, int32_t T,
+                   int32_t C, int32_t vocab, void* x, int64_t ld, void* stream);
+/* x[m, :C] <- x * sigmoid(1.702 x) in place (quick-GELU of the CLIP MLP). */
+int mos_quick_gelu(void* x, int64_t ld, int64_t M, int32_t C, void* stream);
+/* Causal self-attention over one key tile (n <= 128): layouts as mos_attention_fwd; head_dim 80 only (CLIP's 64-dim heads
+ * run zero-padded to 80 with scale = 64^-0.5). */
+int mos_attention_fwd_causal(const void* Q, const void* K, const void* Vt, void* out, int64_t ldo, int32_t batch,
+                             int32_t heads, int32_t head_dim, int32_t n, int32_t n8, float scale, void* stream);
+
 /* One fused kernel for mixofshow/pipelines/pipeline_edlora.py:273-290: classifier-free-guidance combine,
  * DPM-Solver++(2M) data-prediction update and re-duplication of the latents for the next UNet call.
  * noise_pred fp32 [2n] (uncond | cond) when cfg else [n]; coefficients from the host-side schedule.

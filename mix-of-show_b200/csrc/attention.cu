@@ -110,7 +110,7 @@ __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, u
 
 // row maximum of one S tile (raw logits), masked to the first kv_valid columns
 template <int BKV>
-__device__ __forceinline__ float s_row_max(uint32_t ts, int kv_valid) {
+__device__ __forceinline__ float s_row_max(uint32_t ts, int kv_valid, int row_lim) {
   constexpr int NCH = BKV / 16;
   uint32_t v[2][16];
   float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -120,13 +120,15 @@ __device__ __forceinline__ float s_row_max(uint32_t ts, int kv_valid) {
     if (ch * 16 >= kv_valid) break;
     tmem_ld_wait();
     if (ch + 1 < NCH && (ch + 1) * 16 < kv_valid) tmem_ld16(ts + (ch + 1) * 16, v[(ch + 1) & 1]);
-    if ((ch + 1) * 16 <= kv_valid) {
+    // row_lim <= kv_valid: columns this row may attend to (== kv_valid unless the launch is causal); the branch is
+    // taken per lane, the loads above are warp-uniform
+    if ((ch + 1) * 16 <= row_lim) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[ch & 1][i]));
     } else {
 #pragma unroll
       for (int i = 0; i < 16; ++i)
-        if (ch * 16 + i < kv_valid) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[ch & 1][i]));
+        if (ch * 16 + i < row_lim) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[ch & 1][i]));
     }
   }
   return fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
@@ -176,9 +178,10 @@ __device__ __forceinline__ void s_softmax_pass_full(uint32_t ts, float c, float 
   mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
 }
 
-// General pass (partial tiles, concept-token columns, redo path): masks the columns >= kv_valid.
+// General pass (partial tiles, concept-token columns, causal rows, redo path): masks the columns >= row_lim
+// (row_lim == kv_valid unless the launch is causal; chunks >= kv_valid are skipped by the whole warp).
 template <int BKV, bool PC>
-__device__ __noinline__ void s_softmax_pass(uint32_t ts, float c, float m_ref, int kv_valid, uint32_t sPb, int r,
+__device__ __noinline__ void s_softmax_pass(uint32_t ts, float c, float m_ref, int kv_valid, int row_lim, uint32_t sPb, int r,
                                             uint64_t* p_empty_bar, uint32_t pe_parity, bool wait_pe, int lane,
                                             float& rs, float& mx, int pos0, int pos1, float& pc0, float& pc1) {
   constexpr int NCH = BKV / 16;
@@ -193,7 +196,7 @@ __device__ __noinline__ void s_softmax_pass(uint32_t ts, float c, float m_ref, i
     tmem_ld_wait();
     if (ch + 1 < NCH && (ch + 1) * 16 < kv_valid) tmem_ld16(ts + (ch + 1) * 16, v[(ch + 1) & 1]);
     uint32_t pk[8];
-    s_chunk<false, PC>(v[ch & 1], ch * 16, kv_valid, c, nm, s4, m4, pk, pos0, pos1, pc0, pc1);
+    s_chunk<false, PC>(v[ch & 1], ch * 16, row_lim, c, nm, s4, m4, pk, pos0, pos1, pc0, pc1);
     if (ch == 0 && wait_pe) wait_p_empty(p_empty_bar, pe_parity, lane);
     const uint32_t rowp = sPb + (ch >> 2) * 16384 + r * 128;
 #pragma unroll
@@ -213,7 +216,7 @@ __device__ __noinline__ void s_softmax_pass(uint32_t ts, float c, float m_ref, i
     if (TL && blockIdx.x == 0 && blockIdx.y == 0 && (j) < 32) p.tl[(role) * 128 + (j) * 4 + (k)] = clock64();  \
   } while (0)
 
-template <int D, bool ONE, bool TL>
+template <int D, bool ONE, bool TL, bool CAUSAL = false>
 __global__ void __launch_bounds__(192, AttnCfg<D, ONE>::MINB)
 attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
             const __grid_constant__ CUtensorMap tmV, const AttnDev p) {
@@ -363,16 +366,18 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       const uint32_t ts = trow + sb * C::BKV;
       const uint32_t sPb = smem_u32(sP + pbuf * C::P_BYTES);
       const uint32_t pe_parity = ((j / C::PB) & 1) ^ 1;
+      // causal (CLIP text encoder, self-attention): row q attends to keys <= q
+      const int row_lim = CAUSAL ? max(0, min(kv_valid, q_idx - j * C::BKV + 1)) : kv_valid;
       float m_use = m;
-      if (j == 0) m_use = s_row_max<C::BKV>(ts, kv_valid) * c;    // the only two-pass tile
+      if (j == 0) m_use = s_row_max<C::BKV>(ts, kv_valid, row_lim) * c;    // the only two-pass tile
       float rs, mx, mt, pc0 = 0.f, pc1 = 0.f;
-      const bool fast = kv_valid == C::BKV && !want_pc;
+      const bool fast = !CAUSAL && kv_valid == C::BKV && !want_pc;
       if (fast) s_softmax_pass_full<C::BKV>(ts, c, m_use, sPb, r, &p_empty[pbuf], pe_parity, lane, rs, mx);
       else if (want_pc)
-        s_softmax_pass<C::BKV, true>(ts, c, m_use, kv_valid, sPb, r, &p_empty[pbuf], pe_parity, true, lane, rs, mx,
+        s_softmax_pass<C::BKV, true>(ts, c, m_use, kv_valid, row_lim, sPb, r, &p_empty[pbuf], pe_parity, true, lane, rs, mx,
                                      pos0 - j * C::BKV, pos1 - j * C::BKV, pc0, pc1);
       else
-        s_softmax_pass<C::BKV, false>(ts, c, m_use, kv_valid, sPb, r, &p_empty[pbuf], pe_parity, true, lane, rs, mx, -1,
+        s_softmax_pass<C::BKV, false>(ts, c, m_use, kv_valid, row_lim, sPb, r, &p_empty[pbuf], pe_parity, true, lane, rs, mx, -1,
                                       -1, pc0, pc1);
       mt = mx * c;
       if (j > 0 && __any_sync(0xffffffffu, mt > m_use + 32.f)) {
@@ -383,10 +388,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         a_pend *= a;
         m_use = m_new;
         if (want_pc)
-          s_softmax_pass<C::BKV, true>(ts, c, m_use, kv_valid, sPb, r, &p_empty[pbuf], pe_parity, false, lane, rs, mx,
+          s_softmax_pass<C::BKV, true>(ts, c, m_use, kv_valid, row_lim, sPb, r, &p_empty[pbuf], pe_parity, false, lane, rs, mx,
                                        pos0 - j * C::BKV, pos1 - j * C::BKV, pc0, pc1);
         else
-          s_softmax_pass<C::BKV, false>(ts, c, m_use, kv_valid, sPb, r, &p_empty[pbuf], pe_parity, false, lane, rs,
+          s_softmax_pass<C::BKV, false>(ts, c, m_use, kv_valid, row_lim, sPb, r, &p_empty[pbuf], pe_parity, false, lane, rs,
                                         mx, -1, -1, pc0, pc1);
         mt = mx * c;
       }
@@ -488,7 +493,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 
 static unsigned long long* g_attn_tl_host = nullptr;
 
-template <int D, bool ONE>
+template <int D, bool ONE, bool CAUSAL = false>
 static int launch_attn(const void* Q, const void* K, const void* Vt, void* out, int64_t ldo, float* probs, int BH,
                        int heads, int nq, int nk, int nk8, float scale, cudaStream_t stream, float* lse2 = nullptr,
                        float* pcols = nullptr, const int* pos = nullptr) {
@@ -529,15 +534,16 @@ static int launch_attn(const void* Q, const void* K, const void* Vt, void* out, 
   p.tl = g_attn_tl_host;
   static bool configured = false;
   if (!configured) {
-    MOS_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel<D, ONE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    MOS_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel<D, ONE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    MOS_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel<D, ONE, false, CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    if (!CAUSAL)
+      MOS_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel<D, ONE, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
   }
   dim3 grid((unsigned)ceil_div(nq, 128), (unsigned)BH);
-  if (p.tl != nullptr)
-    MOS_CHECK_CUDA(launch_pdl(attn_kernel<D, ONE, true>, grid, dim3(192), (size_t)C::SMEM_BYTES, stream, tmQ, tmK, tmV, p));
+  if (!CAUSAL && p.tl != nullptr)
+    MOS_CHECK_CUDA(launch_pdl(attn_kernel<D, ONE, true, false>, grid, dim3(192), (size_t)C::SMEM_BYTES, stream, tmQ, tmK, tmV, p));
   else
-    MOS_CHECK_CUDA(launch_pdl(attn_kernel<D, ONE, false>, grid, dim3(192), (size_t)C::SMEM_BYTES, stream, tmQ, tmK, tmV, p));
+    MOS_CHECK_CUDA(launch_pdl(attn_kernel<D, ONE, false, CAUSAL>, grid, dim3(192), (size_t)C::SMEM_BYTES, stream, tmQ, tmK, tmV, p));
   return MOS_OK;
 }
 
@@ -596,6 +602,21 @@ extern "C" int mos_attention_fwd_train(const void* Q, const void* K, const void*
       return launch_attn<160, false>(Q, K, Vt, out, ldo, nullptr, BH, heads, nq, nk, nk8, scale, stream, lse2, pcols, ip);
     default: return set_err(MOS_EUNSUPPORTED, "mos_attention_fwd_train: head_dim %d not in {40, 80, 160}", head_dim);
   }
+}
+
+// Causal self-attention over one key tile (nq == nk <= 128): the CLIP text encoder's attention (77 tokens; 12 heads of 64
+// dims run as head_dim 80 with zero-padded columns and scale = 64^-0.5).  Reference: transformers CLIPTextModel as called
+// at mixofshow/pipelines/pipeline_edlora.py:133-145 and trainer_edlora.py:220-234.
+extern "C" int mos_attention_fwd_causal(const void* Q, const void* K, const void* Vt, void* out, int64_t ldo, int32_t batch,
+                                        int32_t heads, int32_t head_dim, int32_t n, int32_t n8, float scale,
+                                        void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MOS_CHECK_ARG(Q && K && Vt && out, "mos_attention_fwd_causal: NULL pointer");
+  MOS_CHECK_ARG(batch > 0 && heads > 0 && n > 0 && n <= 128, "mos_attention_fwd_causal: needs 0 < n <= 128 (one key tile)");
+  MOS_CHECK_ARG(n8 >= n && n8 % 8 == 0, "mos_attention_fwd_causal: n8 must be >= n and a multiple of 8");
+  MOS_CHECK_ARG(ldo >= (int64_t)heads * head_dim && ldo % 8 == 0, "mos_attention_fwd_causal: bad ldo");
+  if (head_dim != 80) return set_err(MOS_EUNSUPPORTED, "mos_attention_fwd_causal: head_dim %d (only 80 is built)", head_dim);
+  return launch_attn<80, true, true>(Q, K, Vt, out, ldo, nullptr, batch * heads, heads, n, n, n8, scale, stream);
 }
 
 extern "C" int mos_debug_set_attn_timeline(void* buf) {

@@ -225,6 +225,50 @@ __global__ void add_rows_kernel(__nv_bfloat16* __restrict__ x, long long ldx, co
   *reinterpret_cast<uint4*>(x + m * ldx + o * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
 }
 
+// ---------------------------------------------------------------------------------- CLIP text encoder glue
+// x[m, :C] = token_embedding[ids[m]] + position_embedding[m % T]   (fp32 tables -> bf16 rows; transformers
+// CLIPTextEmbeddings as called through text_encoder(...) at pipeline_edlora.py:133-145); columns C..ld-1 are zeroed
+// (the hidden state lives in a buffer padded to the GEMM's 160-column tile).
+__global__ void clip_embed_kernel(const int* __restrict__ ids, const float* __restrict__ tok, const float* __restrict__ pos,
+                                  long long M, int T, int C, int vocab, __nv_bfloat16* __restrict__ x, long long ld) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int oct = (int)(ld / 8);
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * oct) return;
+  const int o = (int)(idx % oct);
+  const long long m = idx / oct;
+  uint32_t w[4] = {0u, 0u, 0u, 0u};
+  if (o * 8 < C) {
+    int id = ids[m];
+    id = min(max(id, 0), vocab - 1);
+    const float* tr = tok + (long long)id * C + o * 8;
+    const float* pr = pos + (long long)(m % T) * C + o * 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[i] = pack_bf16x2(__ldg(tr + 2 * i) + __ldg(pr + 2 * i), __ldg(tr + 2 * i + 1) + __ldg(pr + 2 * i + 1));
+  }
+  *reinterpret_cast<uint4*>(x + m * ld + o * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// quick-GELU in place: x <- x * sigmoid(1.702 x)   (CLIP MLP activation, transformers QuickGELUActivation)
+__global__ void quick_gelu_kernel(__nv_bfloat16* __restrict__ x, long long ld, long long M, int C) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int oct = C / 8;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * oct) return;
+  const int o = (int)(idx % oct);
+  const long long m = idx / oct;
+  uint4 a = *reinterpret_cast<const uint4*>(x + m * ld + o * 8);
+  uint32_t aw[4] = {a.x, a.y, a.z, a.w}, ow[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = unpack_bf16x2(aw[i]);
+    ow[i] = pack_bf16x2(f.x / (1.0f + __expf(-1.702f * f.x)), f.y / (1.0f + __expf(-1.702f * f.y)));
+  }
+  *reinterpret_cast<uint4*>(x + m * ld + o * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+}
+
 // ---------------------------------------------------------------------------------- CFG + DPM-Solver++(2M)
 // eps = cfg ? u + g (c - u) : e ;  x0 = (x - sigma_s eps) / alpha_s ;  x <- c_x x + c_m0 x0 + c_m1 x0_prev ;
 // x0_prev <- x0 ; unet_in (both CFG halves) <- x
@@ -377,6 +421,25 @@ extern "C" int mos_add_rows(void* x, int64_t ldx, const void* r, int64_t ldr, in
   MOS_CHECK_CUDA(launch_pdl(add_rows_kernel, dim3(nblk(M * (C / 8), 256)), dim3(256), 0, STREAM(stream),
                             reinterpret_cast<__nv_bfloat16*>(x), (long long)ldx,
                             reinterpret_cast<const __nv_bfloat16*>(r), (long long)ldr, (long long)M, (int)C));
+  return MOS_OK;
+}
+
+extern "C" int mos_clip_embed(const int32_t* ids, const float* token_embedding, const float* position_embedding, int64_t M,
+                              int32_t T, int32_t C, int32_t vocab, void* x, int64_t ld, void* stream) {
+  MOS_CHECK_ARG(ids && token_embedding && position_embedding && x && M > 0 && T > 0 && vocab > 0,
+                "mos_clip_embed: bad arguments");
+  MOS_CHECK_ARG(C % 8 == 0 && ld % 8 == 0 && ld >= C, "mos_clip_embed: C=%d ld=%lld must be multiples of 8, ld >= C", C,
+                (long long)ld);
+  MOS_CHECK_CUDA(launch_pdl(clip_embed_kernel, dim3(nblk(M * (ld / 8), 256)), dim3(256), 0, STREAM(stream),
+                            reinterpret_cast<const int*>(ids), token_embedding, position_embedding, (long long)M, (int)T,
+                            (int)C, (int)vocab, reinterpret_cast<__nv_bfloat16*>(x), (long long)ld));
+  return MOS_OK;
+}
+
+extern "C" int mos_quick_gelu(void* x, int64_t ld, int64_t M, int32_t C, void* stream) {
+  MOS_CHECK_ARG(x && M > 0 && C % 8 == 0 && ld % 8 == 0 && ld >= C, "mos_quick_gelu: bad arguments");
+  MOS_CHECK_CUDA(launch_pdl(quick_gelu_kernel, dim3(nblk(M * (C / 8), 256)), dim3(256), 0, STREAM(stream),
+                            reinterpret_cast<__nv_bfloat16*>(x), (long long)ld, (long long)M, (int)C));
   return MOS_OK;
 }
 

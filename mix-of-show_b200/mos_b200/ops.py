@@ -413,3 +413,26 @@ def attn_reg_total(mse, stats_all, out):
 
 def lora_pack(table_dev, n_modules, alpha):
     check(_lib.lib().mos_lora_pack(ptr(table_dev), _i32(n_modules), ctypes.c_float(alpha), _s()), 'mos_lora_pack')
+
+
+# ----------------------------------------------------------------------------------------------- CLIP text encoder
+def attention_causal(Q, K, Vt, out, *, batch, heads, head_dim, n, scale, ldo=None):
+    """Causal self-attention over one key tile (n <= 128); layouts as `attention`."""
+    check(_lib.lib().mos_attention_fwd_causal(
+        ptr(Q), ptr(K), ptr(Vt), ptr(out), _i64(out.stride(-2) if ldo is None else ldo), _i32(batch), _i32(heads),
+        _i32(head_dim), _i32(n), _i32(Vt.shape[-1]), ctypes.c_float(scale), _s()), 'mos_attention_fwd_causal')
+    return out
+
+
+def clip_embed(ids, token_embedding, position_embedding, x, *, T, C):
+    """x[m, :C] = token_embedding[ids[m]] + position_embedding[m % T] (bf16 rows of pitch x.stride(0), pad columns zeroed)."""
+    assert ids.dtype == torch.int32 and token_embedding.dtype == torch.float32 and position_embedding.dtype == torch.float32
+    check(_lib.lib().mos_clip_embed(ptr(ids), ptr(token_embedding), ptr(position_embedding), _i64(ids.numel()), _i32(T),
+                                    _i32(C), _i32(token_embedding.shape[0]), ptr(x), _i64(x.stride(0)), _s()),
+          'mos_clip_embed')
+    return x
+
+
+def quick_gelu(x, *, M, C):
+    check(_lib.lib().mos_quick_gelu(ptr(x), _i64(x.stride(0)), _i64(M), _i32(C), _s()), 'mos_quick_gelu')
+    return x

@@ -127,3 +127,43 @@ def test_train_loop_host_logic():
         EDLoRATrainer({}, 2, finetune_cfg=cfg)
     with pytest.raises(ValueError):
         EDLoRATrainer({}, 2, finetune_cfg=None)
+
+
+def test_clip_engine_packing_on_cpu():
+    """CLIPTextEngine pads 64-dim heads to 80 and 768 / 3072 columns to 800 / 3200 without changing the arithmetic."""
+    from transformers import CLIPTextConfig, CLIPTextModel
+    from mos_b200.clip_engine import CLIPTextEngine
+    cfg = CLIPTextConfig(vocab_size=300, hidden_size=768, intermediate_size=3072, num_hidden_layers=1,
+                         num_attention_heads=12, max_position_embeddings=77)
+    torch.manual_seed(0)
+    m = CLIPTextModel(cfg).eval()
+    sd = m.state_dict()
+    lora = inject.random_lora_state(m, seed=3, where='CLIPAttention')
+    assert len(lora) == 8                                   # q, k, v, out_proj x (down, up)
+    eng = CLIPTextEngine(sd, 2, lora=lora, lora_alpha=0.5, device='cpu')
+    e = eng.w[0]
+    assert e['qkv']['W'].shape == (2880, 768) and e['out']['W'].shape == (800, 960)
+    assert e['fc1']['W'].shape == (3200, 768) and e['fc2']['W'].shape == (800, 3200)
+    L = 'text_model.encoder.layers.0.'
+    x = torch.randn(6, 768)
+    for s, pj in enumerate(('q_proj', 'k_proj', 'v_proj')):
+        W, b = sd[L + f'self_attn.{pj}.weight'], sd[L + f'self_attn.{pj}.bias']
+        ref = x @ W.T + b + 0.5 * (x @ lora[L + f'self_attn.{pj}.lora_down.weight'].T) @ lora[L + f'self_attn.{pj}.lora_up.weight'].T
+        Wp = e['qkv']['W'][960 * s:960 * (s + 1)].float()
+        t = x @ e['qkv']['lora_down'][4 * s:4 * s + 4].float().T
+        got = (x @ Wp.T + e['qkv']['bias'][960 * s:960 * (s + 1)] + t @ e['qkv']['lora_up'][960 * s:960 * (s + 1)].T)
+        got = got.view(6, 12, 80)
+        assert got[:, :, 64:].abs().max().item() == 0.0     # head pads carry exact zeros
+        assert torch.allclose(got[:, :, :64].reshape(6, 768), ref, atol=0.05, rtol=0.05)
+    # out_proj reads the padded head layout: zero weight columns at the pads, zero rows 768..799
+    a = torch.zeros(6, 12, 80)
+    a[:, :, :64] = torch.randn(6, 12, 64)
+    ref = a[:, :, :64].reshape(6, 768) @ sd[L + 'self_attn.out_proj.weight'].T + sd[L + 'self_attn.out_proj.bias']
+    got = a.reshape(6, 960) @ e['out']['W'].float().T + e['out']['bias']
+    assert got[:, 768:].abs().max().item() == 0.0
+    assert torch.allclose(got[:, :768], ref, atol=0.05, rtol=0.05)
+    # merged mode folds alpha * up @ down into the weight (gradient_fusion.py:99-143)
+    em = CLIPTextEngine(sd, 2, lora=lora, lora_alpha=0.5, merge_lora=True, device='cpu').w[0]
+    assert 'lora_down' not in em['qkv']
+    Wq = sd[L + 'self_attn.q_proj.weight'] + 0.5 * lora[L + 'self_attn.q_proj.lora_up.weight'] @ lora[L + 'self_attn.q_proj.lora_down.weight']
+    assert torch.equal(em['qkv']['W'][:960].view(12, 80, 768)[:, :64].reshape(768, 768).float(), Wq.to(torch.bfloat16).float())
