@@ -12,8 +12,8 @@ Gram matrices on the fly (tcgen05 GEMM, fp32 accumulate), and a closure is one [
 The optimiser is the same algorithm the reference calls (torch.optim.LBFGS: history 25, lr 1, strong-Wolfe line
 search, tolerance 1e-16, ONE .step of max_iter iterations, best iterate over all closure evaluations), restated here
 over CUDA vector primitives (mos_vec_*), working on the correction D = W - W0 so that the quadratic is evaluated
-without the cancellation of the raw Gram form.  The text-encoder half (merge_text_encoder, merge_new_concepts_) is a
-CLIP-side component: SURVEY.md §8f "next".
+without the cancellation of the raw Gram form.  The text-encoder half (merge_text_encoder) runs on the B200 CLIP engine
+(mos_b200/clip_engine.py); merge_new_concepts_ (tokenizer / embedding-table bookkeeping) stays with the caller.
 """
 import math
 
@@ -302,6 +302,77 @@ def merge_kv_in_cross_attention(unet_state_dict, cross_kv_layer_names, text_feat
         for c, tuned in enumerate(unet_crosskv_list):
             X = text_features[c][layer_idx].to(device, F32).contiguous()
             Wc = _merged(W0, tuned[dn_name], tuned[dn_name.replace('lora_down', 'lora_up')], alphas[c], device)  # :403-409
+            Gc = torch.empty(d_in, d_in, device=device)
+            ops.gram_small(X, Gc)
+            WG = torch.empty_like(Cm)
+            ops.sgemm_nn(Wc.contiguous(), Gc, WG)
+            ops.vec_axpby(G.view(-1), Gc.view(-1), 1.0, 1.0)
+            ops.vec_axpby(Cm.view(-1), WG.view(-1), 1.0, 1.0)
+            vv += float((Wc.double() * WG.double()).sum())
+            n += X.shape[0]
+        new_w[name] = solve_from_gram(G, Cm, vv, n, W0, optimize_iters).cpu()
+    return new_w
+
+
+class _RowRecorder:
+    """CLIPTextEngine hook for the text-encoder fusion: keeps the rows of the valid (un-padded) token positions of
+    every recorded GEMM input as fp32 (a few hundred rows of 768: no tensor-core Gram needed)."""
+
+    def __init__(self, rows, heads, d, dh):
+        self.rows, self.heads, self.d, self.dh = rows, heads, d, dh
+        self.X = {}
+
+    def __call__(self, key, A, M, C):
+        X = A[self.rows].float()
+        if C == self.heads * self.dh and self.dh != self.d:       # attention output in the padded head layout
+            X = X.view(-1, self.heads, self.dh)[:, :, :self.d].reshape(-1, self.heads * self.d)
+        self.X[key] = X.contiguous()
+
+
+TEXT_KEYS = {'q_proj': 'self_attn.in', 'k_proj': 'self_attn.in', 'v_proj': 'self_attn.in', 'out_proj': 'self_attn.out_proj'}
+
+
+def merge_text_encoder(text_state_dict, text_encoder_list, alphas, prompt_ids, optimize_iters, device='cuda',
+                       pad_id=49407):
+    """Text-encoder fusion (gradient_fusion.py:460-565).  text_encoder_list[c]: concept c's CLIP LoRA
+    ({'text_model.encoder.layers.{i}.self_attn.{q,k,v,out}_proj.lora_{down,up}.weight'}); prompt_ids[c]: the un-padded
+    token-id sequences of concept c's 32 layer-bound prompts ('photo of a <c>' and '<c>' x 16, :515-520; the tokenizer
+    runs upstream).  For every concept its LoRA is merged (:505-512), the prompts run through the B200 CLIP engine and
+    the inputs of the LoRA'd linears at ALL valid token positions are recorded (the reference's forward hooks, :146-167,
+    :525-541); every layer is then solved from the accumulated Gram matrices as in merge_kv_in_cross_attention.
+    Causal attention makes the features of a valid position independent of the padding behind it, so the sequences are
+    padded to 77 for the engine and only the valid rows are kept."""
+    from mos_b200.clip_engine import CLIPTextEngine
+    names = sorted({k.replace('.lora_down', '').replace('.lora_up', '') for t in text_encoder_list for k in t})
+    feats = []
+    for c, tuned in enumerate(text_encoder_list):
+        seqs = [torch.as_tensor(p_).reshape(-1) for p_ in prompt_ids[c]]
+        n_seq = len(seqs)
+        eng = CLIPTextEngine(text_state_dict, n_seq, lora=tuned, lora_alpha=alphas[c], merge_lora=True, device=device)
+        ids = torch.full((n_seq, eng.T), pad_id, dtype=torch.long)
+        rows = []
+        for s_, q in enumerate(seqs):
+            assert 0 < q.numel() <= eng.T
+            ids[s_, :q.numel()] = q
+            rows += [s_ * eng.T + t for t in range(q.numel())]
+        rec = _RowRecorder(torch.tensor(rows, device=device), eng.heads, eng.d, eng.dh)
+        eng.gram_rec = rec
+        eng(ids)
+        feats.append(rec.X)
+    new_w = {}
+    for name in names:                                       # e.g. 'text_model.encoder.layers.0.self_attn.q_proj.weight'
+        mod = name[:-len('.weight')]
+        layer, leaf = mod.rsplit('.self_attn.', 1)
+        rec_key = layer + '.' + TEXT_KEYS[leaf]
+        W0 = text_state_dict[name].to(device, F32)
+        d_in = W0.shape[1]
+        G = torch.zeros(d_in, d_in, device=device)
+        Cm = torch.zeros(W0.shape[0], d_in, device=device)
+        vv, n = 0.0, 0
+        for c, tuned in enumerate(text_encoder_list):
+            X = feats[c][rec_key]
+            Wc = _merged(W0, tuned[mod + '.lora_down.weight'], tuned[mod + '.lora_up.weight'], alphas[c], device) \
+                if (mod + '.lora_down.weight') in tuned else W0
             Gc = torch.empty(d_in, d_in, device=device)
             ops.gram_small(X, Gc)
             WG = torch.empty_like(Cm)
