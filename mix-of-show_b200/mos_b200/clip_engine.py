@@ -63,6 +63,11 @@ class CLIPTextEngine:
         for i in range(self.n_layers):
             self._pack_layer(i, f32)
 
+    def set_token_embedding(self, table):
+        """Re-upload the token-embedding table (new concept rows written by the caller, trainer_edlora.py:77-82 /
+        convert_edlora_to_diffusers.py:17-20); the row count may have grown (resize_token_embeddings)."""
+        self.tok = table.detach().to(self.dev, torch.float32).contiguous()
+
     # ------------------------------------------------------------------------------------------ packing
     def _lora_pair(self, module):
         src = self._merge if self._merge is not None else self.lora
