@@ -91,21 +91,52 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- workload
+TINY = dict(block_out_channels=(320, 640), layers_per_block=1)       # --tiny debug topology (2-level UNet)
+
+
 def build_workload(tiny=False, images=1):
-    """Oracle-side construction of the synthetic model (weights + LoRA + inputs). The oracle module is used here
-    only as the weight initialiser / CPU baseline, never on the measured GPU path."""
+    """Synthetic model + inputs for both arms WITHOUT touching oracle/: SD1.5-topology weights from this package's own
+    `UNet2DConditionModel` container (PyTorch default inits under manual_seed(0), diffusers parameter names), a rank-4
+    ED-LoRA on every attention projection (down ~ kaiming-uniform(a=sqrt(5)) as edlora.py:238, up ~ N(0, 0.02^2) so the
+    low-rank path is exercised) and random latents / layer-wise text embeddings."""
+    import math
+
     import torch
-    from oracle import inject
-    from oracle import unet as ou
-    cfg = ou.TINY if tiny else None
-    unet = ou.build_unet(0, cfg)
-    inject.install_edlora_processors(unet)
-    lora = inject.random_lora_state(unet, seed=10)
-    sd = {k: v.clone() for k, v in unet.state_dict().items()}
+    from mixofshow.models.unet_b200 import UNet2DConditionModel
+    from mos_b200.engine import cross_attention_names
+    cfg = TINY if tiny else None
+    torch.manual_seed(0)
+    model = UNet2DConditionModel(**(cfg or {}))
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    del model
+    g = torch.Generator().manual_seed(10)
+    names = cross_attention_names(cfg['block_out_channels'], cfg['layers_per_block']) if cfg else cross_attention_names()
+    lora = {}
+    for an in names:
+        tb = an[:-len('.attn2')]
+        for a in ('attn1', 'attn2'):
+            for pj in ('to_q', 'to_k', 'to_v', 'to_out.0'):
+                m = f'{tb}.{a}.{pj}'
+                cout, cin = sd[m + '.weight'].shape
+                lora[m + '.lora_down.weight'] = (torch.rand(4, cin, generator=g) * 2 - 1) / math.sqrt(cin)
+                lora[m + '.lora_up.weight'] = torch.randn(cout, 4, generator=g) * 0.02
     H = W = 64
     lat = torch.randn(images, 4, H, W, generator=torch.Generator().manual_seed(1))
     ehs = torch.randn(2 * images, 16, 77, 768, generator=torch.Generator().manual_seed(2))   # [uncond x n | cond x n]
-    return unet, sd, lora, lat, ehs, cfg
+    return sd, lora, lat, ehs, cfg
+
+
+def build_cpu_reference(sd, lora, cfg):
+    """CPU arm only: the fp32 oracle port of the reference path (oracle/ is test / baseline infrastructure), loaded with
+    the SAME synthetic weights as the GPU arm."""
+    from oracle import inject
+    from oracle import unet as ou
+    with __import__('torch').no_grad():
+        unet = ou.UNet2DConditionModel(ou.TINY if cfg else None)
+        unet.load_state_dict(sd)
+    unet.eval()
+    inject.install_edlora_processors(unet)
+    return unet
 
 
 def pick_cpu_threads():
@@ -187,7 +218,8 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return
-        unet, sd, lora, lat, ehs, cfg = build_workload(args.tiny)
+        sd, lora, lat, ehs, cfg = build_workload(args.tiny)
+        unet = build_cpu_reference(sd, lora, cfg)
         done, secs = cpu_reference_steps(unet, lora, lat, ehs, args.steps, min(args.warmup, 1), budget_s=240.0)
         v = done / secs
         print(json.dumps({
@@ -212,7 +244,7 @@ def main():
     from mos_b200.engine import UNetEngine, ehs_to_layer_major
     from mos_b200.scheduler import DPMSolverPP2M
 
-    unet, sd, lora, lat, ehs, cfg = build_workload(args.tiny, args.images)
+    sd, lora, lat, ehs, cfg = build_workload(args.tiny, args.images)
     kw = dict(block_out=cfg['block_out_channels'], layers=cfg['layers_per_block']) if cfg else {}
     n_img = args.images
     B, H, W = 2 * n_img, lat.shape[2], lat.shape[3]
@@ -343,7 +375,7 @@ def main():
                            'launches_per_step': roof['launches'], 'kernel_ms_per_step': roof['ms'],
                            'algorithmic_gflop_per_step': roof['gflop']}
     if world == 1 and not args.no_cpu_baseline and n_img == 1:
-        t0 = time.perf_counter()
+        unet = build_cpu_reference(sd, lora, cfg)
         done, secs = cpu_reference_steps(unet, lora, lat, ehs, 2, 1, budget_s=60.0)
         out['cpu_baseline'] = {'value': done / secs, 'unit': UNIT, 'cores': CPU_THREADS, 'host_cpus': os.cpu_count(),
                                'kind': 'port',
