@@ -44,3 +44,22 @@ def test_product_arm_fails_loudly_without_cuda():
         pytest.skip('a GPU is present')
     r = _run(['--tiny', '--steps', '1', '--warmup', '1'])
     assert r.returncode != 0 and 'needs a GPU' in (r.stderr + r.stdout)
+
+
+def test_product_code_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package may import it, and bench.py may do so only inside the
+    two CPU-baseline functions."""
+    import re
+    pkg = os.path.join(ROOT, 'mix-of-show_b200')
+    pat = re.compile(r'^\s*(from\s+oracle\b|import\s+oracle\b)', re.M)
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith('.py'):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not pat.search(src), f'{os.path.join(dirpath, f)} imports oracle'
+    src = open(os.path.join(ROOT, 'bench.py')).read()
+    allowed = ('def build_cpu_reference', 'def cpu_reference_steps')
+    for m in pat.finditer(src):
+        head = src[:m.start()]
+        last_def = head.rfind('\ndef ')
+        assert src[last_def + 1:].startswith(allowed), 'bench.py imports oracle outside the CPU-baseline functions'
