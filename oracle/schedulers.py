@@ -7,7 +7,9 @@
 
 Third-party (diffusers, un-vendored, recommended ==0.19.3): restated from the published algorithm
 (DPM-Solver++ 2M, midpoint, lower_order_final, epsilon prediction, scaled_linear betas 0.00085..0.012).
-Parity unpinned against diffusers itself (not installable here); pinned by closed-form self-checks in tests.
+Parity unpinned against diffusers itself (not installable here); pinned instead against mathematics in
+tests/test_oracle_golden.py: closed-form coefficients == step(), and convergence of the sampler to the analytic
+probability-flow solution for Gaussian data at better than first order (a first-order update fails that test).
 """
 import numpy as np
 import torch
