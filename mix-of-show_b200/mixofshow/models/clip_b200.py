@@ -27,6 +27,17 @@ class CLIPTextModel:
                                       max_position_embeddings=self._sd['text_model.embeddings.position_embedding.weight'].shape[0],
                                       vocab_size=self._sd[TOKEN_KEY].shape[0])
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder='text_encoder', **kw):
+        """transformers call shape (`CLIPTextModel.from_pretrained(path, subfolder='text_encoder')`, trainer_edlora.py:41)."""
+        from mixofshow.utils.model_io import load_text_encoder
+        kw = {k: v for k, v in kw.items() if k in ('lora', 'lora_alpha', 'merge_lora', 'device')}
+        return load_text_encoder(pretrained_model_name_or_path, subfolder, **kw)
+
+    def save_pretrained(self, save_directory, **unused):
+        from mixofshow.utils.model_io import save_text_encoder
+        save_text_encoder(self, save_directory, subfolder=None)
+
     # ------------------------------------------------------------------ module-like surface
     def to(self, *a, **k):
         return self

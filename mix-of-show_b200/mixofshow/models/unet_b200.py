@@ -180,6 +180,17 @@ class UNet2DConditionModel(nn.Module):
         self.merge_lora = False
         self.use_graph = True
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder='unet', **unused):
+        """diffusers call shape (`UNet2DConditionModel.from_pretrained(path, subfolder='unet')`, trainer_edlora.py:44):
+        loads a diffusers-layout directory (mixofshow/utils/model_io.py)."""
+        from mixofshow.utils.model_io import load_unet
+        return load_unet(pretrained_model_name_or_path, subfolder)
+
+    def save_pretrained(self, save_directory, **unused):
+        from mixofshow.utils.model_io import save_unet
+        save_unet(self, save_directory, subfolder=None)
+
     def invalidate(self):
         """Force a re-pack on the next call (needed only after edits that bypass autograd's version counters, e.g.
         writes through `.data`; optimiser steps and `load_state_dict` are detected automatically)."""
