@@ -13,7 +13,8 @@ The optimiser is the same algorithm the reference calls (torch.optim.LBFGS: hist
 search, tolerance 1e-16, ONE .step of max_iter iterations, best iterate over all closure evaluations), restated here
 over CUDA vector primitives (mos_vec_*), working on the correction D = W - W0 so that the quadratic is evaluated
 without the cancellation of the raw Gram form.  The text-encoder half (merge_text_encoder) runs on the B200 CLIP engine
-(mos_b200/clip_engine.py); merge_new_concepts_ (tokenizer / embedding-table bookkeeping) stays with the caller.
+(mos_b200/clip_engine.py).  The reference's entry point (parse_new_concepts, merge_new_concepts_, get_text_feature,
+compose_concepts and the CLI) is restated at the bottom of this file over those stages.
 """
 import math
 
@@ -470,3 +471,186 @@ def merge_spatial_attention(unet_state_dict, unet_spatial_attn_list, alphas, con
             n += grams[c].rows[rec_key]
         new_w[name] = solve_from_gram(G, Cm, vv, n, W0, optimize_iters).reshape(unet_state_dict[name].shape).cpu()
     return new_w
+
+
+# ------------------------------------------------------------------------------------------------ orchestration (host)
+# The reference's entry point (gradient_fusion.py:750-851): checkpoint parsing, tokenizer / embedding-table bookkeeping,
+# prompt construction and the order of the three fusion stages, restated over the feature-level stage functions above and
+# this repo's model containers.  Pure host logic; the arithmetic lives in the stage functions.
+TEMPLATE_SIMPLE = 'photo of a {}'                      # gradient_fusion.py:19
+NUM_CROSS_ATTENTION_LAYERS = 16
+
+
+def parse_new_concepts(concept_cfg):
+    """gradient_fusion.py:262-322: split every concept's `.pth` into embedding / text-encoder / cross-K/V / spatial parts."""
+    import json
+    if isinstance(concept_cfg, str):
+        with open(concept_cfg, 'r') as f:
+            concept_list = json.load(f)
+    else:
+        concept_list = concept_cfg
+    embedding_list, text_encoder_list, unet_crosskv_list, unet_spatial_attn_list = [], [], [], []
+    crosskv_matches = ['attn2.to_k.lora', 'attn2.to_v.lora']
+    for concept in concept_list:
+        model = torch.load(concept['lora_path'], map_location='cpu')['params']
+        emb = model.get('new_concept_embedding')
+        embedding_list.append(emb if emb is not None and len(emb) != 0 else None)
+        te = model.get('text_encoder')
+        text_encoder_list.append(te if te is not None and len(te) != 0 else None)
+        if 'unet' in model and len(model['unet']) != 0:
+            kv = {k: v for k, v in model['unet'].items() if any(x in k for x in crosskv_matches)}
+            sp = {k: v for k, v in model['unet'].items() if all(x not in k for x in crosskv_matches)}
+            unet_crosskv_list.append(kv if len(kv) != 0 else None)
+            unet_spatial_attn_list.append(sp if len(sp) != 0 else None)
+        else:
+            unet_crosskv_list.append(None)
+            unet_spatial_attn_list.append(None)
+    return embedding_list, text_encoder_list, unet_crosskv_list, unet_spatial_attn_list, concept_list
+
+
+def merge_new_concepts_(embedding_list, concept_list, tokenizer, text_encoder):
+    """gradient_fusion.py:214-259: 16 new tokens `<new{k}>` per `<concept>` word (numbered consecutively over all
+    concepts), embedding table resized and the learned rows written; returns (embedding_features, new_concept_cfg)."""
+    embedding_features, new_concept_cfg = {}, {}
+    start_idx = 0
+    for embedding, concept in zip(embedding_list, concept_list):
+        for concept_name in concept['concept_name'].split(' '):
+            if not concept_name.startswith('<'):
+                continue
+            assert concept_name in embedding, 'check the config, the provide concept name is not in the lora model'
+            new_token_names = [f'<new{start_idx + layer_id}>' for layer_id in range(NUM_CROSS_ATTENTION_LAYERS)]
+            num_added_tokens = tokenizer.add_tokens(new_token_names)
+            assert num_added_tokens == NUM_CROSS_ATTENTION_LAYERS
+            new_token_ids = [tokenizer.convert_tokens_to_ids(n) for n in new_token_names]
+            text_encoder.resize_token_embeddings(len(tokenizer))
+            token_embeds = text_encoder.get_input_embeddings().weight.data
+            token_embeds[new_token_ids] = embedding[concept_name].to(token_embeds.device, token_embeds.dtype)
+            embedding_features[concept_name] = embedding[concept_name]
+            start_idx += NUM_CROSS_ATTENTION_LAYERS
+            new_concept_cfg[concept_name] = {'concept_token_ids': new_token_ids, 'concept_token_names': new_token_names}
+    return embedding_features, new_concept_cfg
+
+
+def _unpadded_ids(text, tokenizer):
+    return tokenizer(text, truncation=True, max_length=tokenizer.model_max_length, return_length=True,
+                     return_overflowing_tokens=False, padding='do_not_pad').input_ids
+
+
+@torch.no_grad()
+def get_text_feature(prompts, tokenizer, text_encoder, device, return_type='category_embedding', eos_id=49407):
+    """gradient_fusion.py:182-211.  'category_embedding': features at the positions whose token id is >= eos_id (the new
+    concept tokens AND the end token, :196-197) of every un-padded prompt, concatenated; 'full_embedding': [n, 77, 768]."""
+    if return_type == 'category_embedding':
+        feats = []
+        for text in prompts:
+            tokens = _unpadded_ids(text, tokenizer)
+            pos = torch.where(torch.tensor(tokens) >= eos_id)[0]
+            h = text_encoder(torch.LongTensor(tokens).reshape(1, -1).to(device))[0]
+            feats.append(h[:, pos.to(h.device)].reshape(-1, h.shape[-1]))
+        return torch.cat(feats, 0).float()
+    if return_type == 'full_embedding':
+        ids = tokenizer(prompts, padding='max_length', max_length=tokenizer.model_max_length, truncation=True,
+                        return_tensors='pt').input_ids
+        return text_encoder(ids.to(device))[0]
+    raise NotImplementedError(return_type)
+
+
+def cross_kv_layer_names(unet):
+    """[(cross_attention_idx, '<...>.attn2.to_k.weight'), (idx, '<...>.to_v.weight'), ...] in the reference's
+    down -> mid -> up parameter order (gradient_fusion.py:331-369)."""
+    names, idx = [], -1
+    for prefix, block in (('down_blocks.', unet.down_blocks), ('mid_block.', unet.mid_block), ('up_blocks.', unet.up_blocks)):
+        for name, _ in block.named_parameters():
+            if 'attn2.to_k' in name:
+                idx += 1
+                names.append((idx, prefix + name))
+                names.append((idx, prefix + name.replace('to_k', 'to_v')))
+    return names
+
+
+def compose_concepts(concept_cfg, optimize_textenc_iters, optimize_unet_iters, pretrained_model_path, save_path, suffix,
+                     device='cuda', tokenizer=None, log=print):
+    """gradient_fusion.py:750-813 on the B200 path.  `pretrained_model_path`: diffusers-layout directory (unet/,
+    text_encoder/, tokenizer/); the fused UNet / text encoder and new_concept_cfg.json are written to
+    `{save_path}/combined_model_{suffix}` (the VAE / scheduler / tokenizer folders of the base model are untouched by the
+    fusion and are not copied here)."""
+    import os
+    from mixofshow.pipelines.pipeline_edlora import bind_concept_prompt
+    from mixofshow.utils import model_io
+    log('------Step 1: load stable diffusion checkpoint------')
+    unet = model_io.load_unet(pretrained_model_path)
+    text_encoder = model_io.load_text_encoder(pretrained_model_path, device=device)
+    if tokenizer is None:
+        from transformers import CLIPTokenizer
+        tokenizer = CLIPTokenizer.from_pretrained(pretrained_model_path, subfolder='tokenizer')
+    log('------Step 2: load new concepts checkpoints------')
+    embedding_list, text_encoder_list, unet_crosskv_list, unet_spatial_attn_list, concept_list = \
+        parse_new_concepts(concept_cfg)
+    if any(item is not None for item in embedding_list):
+        log('------Step 3: merge token embedding------')
+        _, new_concept_cfg = merge_new_concepts_(embedding_list, concept_list, tokenizer, text_encoder)
+    else:
+        new_concept_cfg = {}
+
+    def prompts_of(concept):                                  # 32 layer-bound prompts (:515-520, :381-385)
+        return bind_concept_prompt([TEMPLATE_SIMPLE.format(concept['concept_name']), concept['concept_name']],
+                                   new_concept_cfg)
+
+    if any(item is not None for item in text_encoder_list):
+        log('------Step 4: merge text encoder------')
+        ids = [[torch.tensor(_unpadded_ids(p_, tokenizer)) for p_ in prompts_of(c)] for c in concept_list]
+        new_w = merge_text_encoder(text_encoder.state_dict(), text_encoder_list,
+                                   [c['text_encoder_alpha'] for c in concept_list], ids, optimize_textenc_iters,
+                                   device=device)
+        sd = text_encoder.state_dict()
+        sd.update(new_w)
+        text_encoder.load_state_dict(sd)
+    if any(item is not None for item in unet_crosskv_list):
+        log('------Step 5: merge kv of cross-attention in unet------')
+        feats = []
+        for c in concept_list:
+            cp = prompts_of(c)
+            n = len(cp) // NUM_CROSS_ATTENTION_LAYERS
+            feats.append({i: get_text_feature([cp[j * NUM_CROSS_ATTENTION_LAYERS + i] for j in range(n)], tokenizer,
+                                              text_encoder, device).cpu() for i in range(NUM_CROSS_ATTENTION_LAYERS)})
+        new_w = merge_kv_in_cross_attention(unet.state_dict(), cross_kv_layer_names(unet), feats, unet_crosskv_list,
+                                            [c['unet_alpha'] for c in concept_list], optimize_textenc_iters, device=device)
+        sd = unet.state_dict()
+        sd.update(new_w)
+        unet.load_state_dict(sd)
+    if any(item is not None for item in unet_spatial_attn_list):
+        log('------Step 6: merge spatial attention (q in cross-attention, qkv in self-attention) in unet------')
+        embeds = [get_text_feature(bind_concept_prompt([TEMPLATE_SIMPLE.format(c['concept_name'])], new_concept_cfg),
+                                   tokenizer, text_encoder, device, return_type='full_embedding').unsqueeze(0).cpu()
+                  for c in concept_list]
+        cfg = unet.config
+        new_w = merge_spatial_attention(unet.state_dict(), unet_spatial_attn_list,
+                                        [c['unet_alpha'] for c in concept_list], embeds, optimize_unet_iters,
+                                        device=device, block_out=tuple(cfg.block_out_channels),
+                                        layers=cfg.layers_per_block)
+        sd = unet.state_dict()
+        sd.update(new_w)
+        unet.load_state_dict(sd)
+    out_dir = os.path.join(save_path, f'combined_model_{suffix}')
+    model_io.save_combined_model(out_dir, unet, text_encoder, new_concept_cfg)
+    return out_dir, new_concept_cfg
+
+
+def parse_args(argv=None):
+    import argparse
+    parser = argparse.ArgumentParser('', add_help=False)
+    parser.add_argument('--concept_cfg', help='json file for multi-concept', required=True, type=str)
+    parser.add_argument('--save_path', help='folder name to save optimized weights', required=True, type=str)
+    parser.add_argument('--suffix', help='suffix name', default='base', type=str)
+    parser.add_argument('--pretrained_models', required=True, type=str)
+    parser.add_argument('--optimize_unet_iters', default=50, type=int)
+    parser.add_argument('--optimize_textenc_iters', default=500, type=int)
+    return parser.parse_args(argv)
+
+
+if __name__ == '__main__':
+    import os
+    args = parse_args()
+    os.makedirs(args.save_path, exist_ok=True)
+    compose_concepts(args.concept_cfg, args.optimize_textenc_iters, args.optimize_unet_iters, args.pretrained_models,
+                     args.save_path, args.suffix, device='cuda')
