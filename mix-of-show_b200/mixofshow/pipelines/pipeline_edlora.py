@@ -44,6 +44,22 @@ class EDLoRAPipeline:
         self.new_concept_cfg = None
         self.device = torch.device('cuda')
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, scheduler=None, vae=None, tokenizer=None, device='cuda',
+                        **unused):
+        """diffusers call shape (`EDLoRAPipeline.from_pretrained(path, scheduler=..., torch_dtype=...)`, test_edlora.py /
+        README.md:146): loads `unet/` and `text_encoder/` of a diffusers-layout directory into the B200 containers
+        (mixofshow/utils/model_io.py) and `tokenizer/` through transformers.  The VAE is §8f "next": pass one, or sample
+        with output_type='latent'."""
+        from mixofshow.utils import model_io
+        unet = model_io.load_unet(pretrained_model_name_or_path)
+        text_encoder = model_io.load_text_encoder(pretrained_model_name_or_path, device=device)
+        if tokenizer is None:
+            from transformers import CLIPTokenizer
+            tokenizer = CLIPTokenizer.from_pretrained(pretrained_model_name_or_path, subfolder='tokenizer')
+        pipe = cls(vae=vae, text_encoder=text_encoder, tokenizer=tokenizer, unet=unet, scheduler=scheduler)
+        return pipe.to(device)
+
     def to(self, device):
         self.device = torch.device(device)
         return self

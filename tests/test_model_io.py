@@ -82,3 +82,20 @@ def _tiny_unet():
     torch.manual_seed(2)
     return UNet2DConditionModel(block_out_channels=ou.TINY['block_out_channels'],
                                 layers_per_block=ou.TINY['layers_per_block'])
+
+
+def test_pipeline_from_pretrained_builds_the_b200_containers(tmp_path):
+    """EDLoRAPipeline.from_pretrained on a diffusers-layout directory (construction only: sampling needs the GPU)."""
+    from mixofshow.models.clip_b200 import CLIPTextModel
+    from mixofshow.models.unet_b200 import UNet2DConditionModel
+    from mixofshow.pipelines.pipeline_edlora import EDLoRAPipeline
+    from mixofshow.utils import model_io
+    base = str(tmp_path)
+    model_io.save_unet(_tiny_unet(), base)
+    _clip().save_pretrained(os.path.join(base, 'text_encoder'))
+    pipe = EDLoRAPipeline.from_pretrained(base, tokenizer=object(), device='cpu')
+    assert isinstance(pipe.unet, UNet2DConditionModel) and isinstance(pipe.text_encoder, CLIPTextModel)
+    # the reference's installer ran (pipeline_edlora.py:93): every attn2 got its cross_attention_idx in DFS order
+    idx = [m.processor.cross_attention_idx for n, m in pipe.unet.named_modules()
+           if m.__class__.__name__ == 'Attention' and n.endswith('attn2')]
+    assert idx == list(range(len(idx))) and len(idx) == 4
