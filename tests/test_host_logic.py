@@ -167,3 +167,16 @@ def test_clip_engine_packing_on_cpu():
     assert 'lora_down' not in em['qkv']
     Wq = sd[L + 'self_attn.q_proj.weight'] + 0.5 * lora[L + 'self_attn.q_proj.lora_up.weight'] @ lora[L + 'self_attn.q_proj.lora_down.weight']
     assert torch.equal(em['qkv']['W'][:960].view(12, 80, 768)[:, :64].reshape(768, 768).float(), Wq.to(torch.bfloat16).float())
+
+
+def test_regional_script_prepare_text_matches_reference_golden():
+    """regionally_controlable_sampling.py:67-94 (the box fractions feed the bit-exact region masks)."""
+    import os
+    import regionally_controlable_sampling as rcs
+    G = torch.load(os.path.join(os.path.dirname(__file__), 'golden', 'reference_golden.pt'))['prepare_text']
+    out = rcs.prepare_text('a context prompt', G['prompt_rewrite'], G['height'], G['width'])
+    assert out == G['out']                                   # strings and float64 fractions, exactly
+    assert rcs.prepare_text('p', '[a]-*-[b]-*-[]', 512, 512) == ('p', [('a', 'b', [0, 0, 1, 1])])
+    assert rcs.prepare_text('p', '', 512, 512) == ('p', [])
+    a = rcs.parse_args(['--pretrained_model', 'x', '--prompt_rewrite', 'r', '--seed', '3'])
+    assert a.seed == 3 and a.height == 768 and a.width == 1536 and a.keypose_adaptor_weight == 1.0
