@@ -126,6 +126,32 @@ def build_workload(tiny=False, images=1):
     return sd, lora, lat, ehs, cfg
 
 
+def build_pipeline(sd, lora, cfg, dev):
+    """The drop-in objects a user of the reference holds: B200 UNet container + LoRALinearLayer on all 128 attention
+    projections (trainer_edlora.py:121-133 / convert_edlora_to_diffusers.py) + EDLoRAPipeline."""
+    import contextlib
+    import io
+
+    import torch
+    from mixofshow.models.edlora import LoRALinearLayer
+    from mixofshow.models.unet_b200 import UNet2DConditionModel
+    from mixofshow.pipelines.pipeline_edlora import EDLoRAPipeline
+    unet = UNet2DConditionModel(**(cfg or {}))
+    unet.load_state_dict(sd)
+    mods = dict(unet.named_modules())
+    with torch.no_grad():
+        for k in lora:
+            if k.endswith('.lora_down.weight'):
+                name = k[:-len('.lora_down.weight')]
+                layer = LoRALinearLayer(name, mods[name], rank=4, alpha=1.0)
+                layer.lora_down.weight.copy_(lora[k])
+                layer.lora_up.weight.copy_(lora[name + '.lora_up.weight'])
+    with contextlib.redirect_stdout(io.StringIO()):      # the installers print a registration count (as the reference)
+        pipe = EDLoRAPipeline(unet=unet).to(dev)
+    pipe.set_new_concept_cfg({})
+    return pipe
+
+
 def build_cpu_reference(sd, lora, cfg):
     """CPU arm only: the fp32 oracle port of the reference path (oracle/ is test / baseline infrastructure), loaded with
     the SAME synthetic weights as the GPU arm."""
@@ -241,14 +267,18 @@ def main():
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=dev)
     from mos_b200 import ops
-    from mos_b200.engine import UNetEngine, ehs_to_layer_major
     from mos_b200.scheduler import DPMSolverPP2M
 
     sd, lora, lat, ehs, cfg = build_workload(args.tiny, args.images)
-    kw = dict(block_out=cfg['block_out_channels'], layers=cfg['layers_per_block']) if cfg else {}
     n_img = args.images
     B, H, W = 2 * n_img, lat.shape[2], lat.shape[3]
-    eng = UNetEngine(sd, B, H, W, lora=lora, lora_alpha=1.0, device=dev, **kw)
+    # The reference-facing objects: the UNet container with a LoRALinearLayer on every attention projection
+    # (installed as trainer_edlora.py:121-133 does) inside an EDLoRAPipeline.  Both legs below run on the engine this
+    # container packs: `value` replays its prepared session directly (inputs resident in HBM), `e2e` is the user's call.
+    pipe = build_pipeline(sd, lora, cfg, dev)
+    unet = pipe.unet
+    sess = unet.session(B, H, W, dev, ehs.to(dev))
+    eng = sess.eng
     nx = len(eng.xattn_names)
     sched = DPMSolverPP2M()
     total_steps = args.warmup + args.steps
@@ -257,7 +287,6 @@ def main():
 
     latents = lat.to(dev).clone()
     x0_prev = torch.zeros_like(latents)
-    eng.in_ehs.copy_(ehs_to_layer_major(ehs[:, :nx].to(dev), nx))
     unet_in = eng.in_latents.view(-1)
 
     def reset():
@@ -295,40 +324,39 @@ def main():
     launches = (eng.launches + 1) * args.steps
     final_lat = latents.clone()
 
-    # ---------------- end-to-end through host buffers (`e2e`): H2D latents + t + embeddings, D2H latents per step
+    # ---------------- end-to-end through the public API (`e2e`): EDLoRAPipeline.__call__ on HOST tensors.  One call =
+    # one image = `steps` denoise steps; per call the latents and the prompt embeddings travel host -> device (pinned
+    # memory), per step the callback reads the current latents back into pinned host memory (progress preview, the
+    # reference's `callback(i, t, latents)` hook, pipeline_edlora.py:298-300) and the final latents come back at the end.
     h_lat = lat.clone().pin_memory()
-    h_ehs = ehs_to_layer_major(ehs[:, :nx], nx).pin_memory()
-    h_t = torch.zeros(B).pin_memory()
+    h_cond = ehs[n_img:].clone().pin_memory()                      # [n, 16, 77, 768] layer-wise prompt embeddings
+    h_neg = ehs[:n_img, 0].clone().pin_memory()                    # [n, 77, 768] negative-prompt embeddings
+    h_step = torch.empty_like(h_lat).pin_memory()
     h_out = torch.empty_like(h_lat).pin_memory()
-    reset()
 
-    def e2e_step(i):
-        h_t.fill_(ts[i])
-        latents.copy_(h_lat, non_blocking=True)
-        eng.in_latents[:n_img].copy_(h_lat, non_blocking=True)
-        eng.in_latents[n_img:].copy_(h_lat, non_blocking=True)
-        eng.in_t.copy_(h_t, non_blocking=True)
-        eng.in_ehs.copy_(h_ehs, non_blocking=True)
-        eng.run()
-        ops.cfg_dpmpp_step(eng.out_eps, latents, x0_prev, None, cfg=True, guidance=7.5, coef=sched.coefficients(i))
-        h_out.copy_(latents, non_blocking=True)
-        torch.cuda.current_stream().synchronize()   # the caller consumes the step result on the host
-        h_lat.copy_(h_out)
+    def cb(i, t, latents_dev):
+        h_step.copy_(latents_dev, non_blocking=True)
 
-    for i in range(args.warmup):
-        e2e_step(i)
+    def pipeline_call(steps):
+        out = pipe(prompt_embeds=h_cond, negative_prompt_embeds=h_neg, latents=h_lat, num_inference_steps=steps,
+                   guidance_scale=7.5, output_type='latent', callback=cb, callback_steps=1)
+        h_out.copy_(out.images, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the caller consumes the image on the host
+        return h_out
+
+    pipeline_call(max(args.warmup, 3))
     barrier()
     t0 = time.perf_counter()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record()
-    for i in range(args.warmup, total_steps):
-        e2e_step(i)
+    pipeline_call(args.steps)
     g1.record()
     barrier()
     e2e_ms = max(g0.elapsed_time(g1), 1e3 * (time.perf_counter() - t0))
     clocks = sampler.stop() if rank == 0 else None      # sampled over both timed regions (device-resident and e2e)
-    h2d = h_lat.numel() * 4 * 2 + h_t.numel() * 4 + h_ehs.numel() * 2
-    d2h = h_out.numel() * 4
+    per_call_h2d = h_lat.numel() * 4 + h_cond.numel() * 4 + h_neg.numel() * 4
+    h2d = per_call_h2d / args.steps
+    d2h = h_step.numel() * 4 + h_out.numel() * 4 / args.steps
 
     # ---------------- per-kernel roofline of the dominant kernel (tcgen05 GEMM / implicit-GEMM conv), eager mode
     used_graph = eng.graph is not None
@@ -357,7 +385,10 @@ def main():
                    'step vs 126 MB L2, no explicit flush', 'cuda_graph': bool(used_graph), 'images_per_step': n_img},
         'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                'ms_per_step': e2e_ms / args.steps},
+                'ms_per_step': e2e_ms / args.steps,
+                'api': "EDLoRAPipeline.__call__(prompt_embeds=, negative_prompt_embeds=, latents=, num_inference_steps=steps, "
+                       "guidance_scale=7.5, output_type='latent', callback=) on pinned HOST tensors; one call of `steps` steps",
+                'h2d_bytes_per_call': per_call_h2d},
         'gpu_launches': launches,
         'step_tflops': FLOPS_PER_STEP * value / world / 1e12 if not args.tiny else None,   # per GPU, all images
     }

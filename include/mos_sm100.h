@@ -4,7 +4,9 @@
  * last failure on the calling thread is available from mos_last_error(). All pointers are raw device pointers
  * owned by the caller (PyTorch allocates everything); the library never allocates per call, never retains a
  * pointer after return and never synchronises: work is enqueued on the cudaStream_t passed as `stream`.
- * Activations are bf16, NHWC / token-major; weights are pre-packed bf16 K-major (see DESIGN.md "data layout").
+ * Activations are 16-bit, NHWC / token-major: bf16 (training) or fp16 (inference; `act_dtype` / MOS_DT_*, the three extra
+ * mantissa bits keep the classifier-free-guidance difference accurate); weights are pre-packed bf16 K-major
+ * (see DESIGN.md "data layout"); accumulation, statistics and softmax are fp32.
  *
  * Each entry point cites the reference call site it replaces (paths relative to TencentARC/Mix-of-Show).
  */
@@ -34,7 +36,8 @@ const char* mos_last_error(void);
  *   - diffusers ResnetBlock2D conv1/conv2, Transformer2DModel proj_in/proj_out, FeedForward GEGLU
  *     (called through unet(...) at mixofshow/pipelines/pipeline_edlora.py:277)
  * ---------------------------------------------------------------------------------------------------------- */
-enum { MOS_OUT_BF16 = 0, MOS_OUT_HEADS = 1, MOS_OUT_F32 = 2 };
+enum { MOS_DT_BF16 = 0, MOS_DT_F16 = 1 };   /* 16-bit storage type of activations (`act_dtype` arguments) */
+enum { MOS_OUT_BF16 = 0 /* 16-bit rows of type a_dtype */, MOS_OUT_HEADS = 1, MOS_OUT_F32 = 2 };
 enum { MOS_SEG_ROWS = 0 /* [b,h,row,dpad] (Q, K) */, MOS_SEG_TRANSPOSED = 1 /* [b,h,d,row] (V^T) */ };
 
 typedef struct mos_gemm_args {
@@ -70,6 +73,8 @@ typedef struct mos_gemm_args {
   int32_t w_static;       /* 1: W is not written by the kernels just ahead in the stream (model weights): its first tiles
                            * are requested before griddepcontrol.wait, overlapping the predecessor's tail.  0 = W may be
                            * an activation (Gram products): every load waits for the dependency. */
+  int32_t a_dtype;        /* MOS_DT_*: type of A, of the 16-bit outputs (rows, head-split) and of `residual` */
+  int32_t w_dtype;        /* MOS_DT_*: type of W and lora_down (model weights are bf16; Gram products pass activations) */
 } mos_gemm_args;
 
 int mos_gemm_bf16(const mos_gemm_args* args, void* stream);
@@ -88,7 +93,7 @@ int mos_debug_set_attn_timeline(void* buf);
 /* Sum split-K partials and apply bias / bias_batch / residual -> bf16 [M, ldc]. */
 int mos_splitk_finalize(const float* partial, int32_t splits, int64_t M, int64_t N, const float* bias,
                         const float* bias_batch, int64_t rows_per_batch, int64_t bias_batch_ld,
-                        const void* residual, int64_t ldr, void* out, int64_t ldc, void* stream);
+                        const void* residual, int64_t ldr, void* out, int64_t ldc, int32_t act_dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Flash attention (tcgen05 S = QK^T and PV in TMEM, online softmax in registers), head_dim in {40, 80, 160}.
@@ -102,7 +107,7 @@ int mos_splitk_finalize(const float* partial, int32_t splits, int64_t M, int64_t
  * ---------------------------------------------------------------------------------------------------------- */
 int mos_attention_fwd(const void* Q, const void* K, const void* Vt, void* out, int64_t ldo, float* probs,
                       int32_t batch, int32_t heads, int32_t head_dim, int32_t nq, int32_t nk, int32_t nk8,
-                      float scale, void* stream);
+                      float scale, int32_t act_dtype, void* stream);
 
 /* GroupNorm(32)(+SiLU) over NHWC bf16 rows: x [B, HW, ldx] -> y [B, HW, ldy]; partial = fp32 workspace of
  * partial_capacity_floats floats (>= B * 592 * 64 is always enough). The LAST 64 words of the workspace hold the grid-barrier
@@ -110,11 +115,11 @@ int mos_attention_fwd(const void* Q, const void* K, const void* Vt, void* out, i
  * Transformer2DModel.norm, conv_norm_out (reached from mixofshow/pipelines/pipeline_edlora.py:277). */
 int mos_groupnorm_fwd(const void* x, int64_t ldx, int32_t B, int32_t HW, int32_t C, const float* gamma,
                       const float* beta, float eps, int32_t silu_act, float* partial,
-                      int32_t partial_capacity_floats, void* y, int64_t ldy, void* stream);
+                      int32_t partial_capacity_floats, void* y, int64_t ldy, int32_t act_dtype, void* stream);
 
 /* LayerNorm over rows of bf16 [M, ldx] -> [M, ldy], C <= 1280 (BasicTransformerBlock.norm1/2/3). */
 int mos_layernorm_fwd(const void* x, int64_t ldx, int64_t M, int32_t C, const float* gamma, const float* beta,
-                      float eps, void* y, int64_t ldy, void* stream);
+                      float eps, void* y, int64_t ldy, int32_t act_dtype, void* stream);
 
 /* Sinusoidal timestep embedding [B, dim] fp32 = [cos | sin] (diffusers Timesteps, flip_sin_to_cos, shift 0). */
 int mos_timestep_embedding(const float* t, int32_t B, int32_t dim, float* out, void* stream);
@@ -126,17 +131,18 @@ int mos_gemv_bf16(const float* x, int32_t nb, int32_t K, const void* W, const fl
 
 /* conv_in: NCHW fp32 latents [B, Cin, H, W] -> NHWC bf16 [B, H, W, ldy]; w fp32 [9*Cin, Cout] tap-major. */
 int mos_conv_in(const float* x, int32_t B, int32_t Cin, int32_t H, int32_t W, const float* w, const float* bias,
-                int32_t Cout, void* y, int64_t ldy, void* stream);
+                int32_t Cout, void* y, int64_t ldy, int32_t act_dtype, void* stream);
 /* conv_out: NHWC bf16 [B, H, W, C] -> NCHW fp32 [B, Cout<=4, H, W]; w fp32 [Cout, 9, C]. */
 int mos_conv_out(const void* x, int32_t B, int32_t H, int32_t W, int32_t C, const float* w, const float* bias,
-                 int32_t Cout, float* y, void* stream);
+                 int32_t Cout, float* y, int32_t act_dtype, void* stream);
 
 /* Upsample2D nearest x2: NHWC bf16 [B, H, W, ldx] -> contiguous [B, 2H, 2W, C]. */
 int mos_upsample2x(const void* x, int64_t ldx, int32_t B, int32_t H, int32_t W, int32_t C, void* y, void* stream);
 /* Downsample2D (3x3, stride 2, pad 1) im2col: NHWC bf16 -> [B*H/2*W/2, 9*C] for mos_gemm_bf16. */
 int mos_im2col_s2(const void* x, int64_t ldx, int32_t B, int32_t H, int32_t W, int32_t C, void* col, void* stream);
 /* x[m, :C] += r[m, :C] (T2I-Adapter residuals, pipeline_regionally_t2iadapter.py:565). */
-int mos_add_rows(void* x, int64_t ldx, const void* r, int64_t ldr, int64_t M, int32_t C, void* stream);
+int mos_add_rows(void* x, int64_t ldx, const void* r, int64_t ldr, int64_t M, int32_t C, int32_t act_dtype,
+                 void* stream);
 
 /* ---- CLIP text encoder (transformers CLIPTextModel called at pipeline_edlora.py:133-145,
  * trainer_edlora.py:220-234, gradient_fusion.py:182-199).  The linears and LayerNorms reuse mos_gemm_bf16 / mos_layernorm_fwd. */
@@ -164,7 +170,7 @@ int mos_cfg_dpmpp_step(const float* noise_pred, float* latents, float* x0_prev, 
  * as the reference does (ceil / floor); region_ptrs_dev: device array of nregions bf16 pointers. */
 int mos_region_combine(const void* glob, const void* const* region_ptrs_dev, int32_t nregions,
                        const int32_t* boxes_host, int32_t B, int32_t FH, int32_t FW, int32_t C, int64_t ld, void* out,
-                       void* stream);
+                       int32_t act_dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Gradient fusion in Gram form (gradient_fusion.py:22-96 update_quasi_newton / chunk_compute_mse, :99-143 merge,

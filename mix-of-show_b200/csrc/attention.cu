@@ -74,7 +74,7 @@ struct AttnCfg {
 };
 
 // 16 logits of one row -> probabilities (fp32 sums, running raw maxima, packed bf16 pairs)
-template <bool WHOLE, bool PC>
+template <bool WHOLE, bool PC, bool F16>
 __device__ __forceinline__ void s_chunk(const uint32_t (&v)[16], int col0, int kv_valid, float c, float nm,
                                         float (&s4)[4], float (&m4)[4], uint32_t (&pk)[8], int pos0, int pos1,
                                         float& pc0, float& pc1) {
@@ -100,7 +100,7 @@ __device__ __forceinline__ void s_chunk(const uint32_t (&v)[16], int col0, int k
       pc1 = (col0 + i == pos1) ? e0 : pc1;
       pc1 = (col0 + i + 1 == pos1) ? e1 : pc1;
     }
-    pk[i >> 1] = pack_bf16x2(e0, e1);
+    pk[i >> 1] = pack16x2<F16>(e0, e1);
   }
 }
 
@@ -144,7 +144,7 @@ __device__ __forceinline__ void wait_p_empty(uint64_t* bar, uint32_t parity, int
 // TMEM loads are 32 columns wide and run one load ahead (a tcgen05.ld takes ~300 cycles to return while the tensor pipe
 // is busy, about the time the arithmetic of 32 columns needs); no branches besides the (normally already satisfied)
 // P-buffer wait.
-template <int BKV>
+template <int BKV, bool F16>
 __device__ __forceinline__ void s_softmax_pass_full(uint32_t ts, float c, float m_ref, uint32_t sPb, int r,
                                                     uint64_t* p_empty_bar, uint32_t pe_parity, int lane, float& rs,
                                                     float& mx) {
@@ -163,7 +163,7 @@ __device__ __forceinline__ void s_softmax_pass_full(uint32_t ts, float c, float 
     for (int h = 0; h < 2; ++h) {
       uint32_t pk[8];
       const uint32_t(&vh)[16] = *reinterpret_cast<const uint32_t(*)[16]>(&v[ch & 1][h * 16]);
-      s_chunk<true, false>(vh, ch * 32 + h * 16, BKV, c, nm, s4, m4, pk, -1, -1, unused0, unused1);
+      s_chunk<true, false, F16>(vh, ch * 32 + h * 16, BKV, c, nm, s4, m4, pk, -1, -1, unused0, unused1);
       if (ch == 0 && h == 0) wait_p_empty(p_empty_bar, pe_parity, lane);
       const int c16b = ch * 2 + h;        // 16-column chunk index inside the tile
       const uint32_t rowp = sPb + (c16b >> 2) * 16384 + r * 128;
@@ -180,7 +180,7 @@ __device__ __forceinline__ void s_softmax_pass_full(uint32_t ts, float c, float 
 
 // General pass (partial tiles, concept-token columns, causal rows, redo path): masks the columns >= row_lim
 // (row_lim == kv_valid unless the launch is causal; chunks >= kv_valid are skipped by the whole warp).
-template <int BKV, bool PC>
+template <int BKV, bool PC, bool F16>
 __device__ __noinline__ void s_softmax_pass(uint32_t ts, float c, float m_ref, int kv_valid, int row_lim, uint32_t sPb, int r,
                                             uint64_t* p_empty_bar, uint32_t pe_parity, bool wait_pe, int lane,
                                             float& rs, float& mx, int pos0, int pos1, float& pc0, float& pc1) {
@@ -196,7 +196,7 @@ __device__ __noinline__ void s_softmax_pass(uint32_t ts, float c, float m_ref, i
     tmem_ld_wait();
     if (ch + 1 < NCH && (ch + 1) * 16 < kv_valid) tmem_ld16(ts + (ch + 1) * 16, v[(ch + 1) & 1]);
     uint32_t pk[8];
-    s_chunk<false, PC>(v[ch & 1], ch * 16, row_lim, c, nm, s4, m4, pk, pos0, pos1, pc0, pc1);
+    s_chunk<false, PC, F16>(v[ch & 1], ch * 16, row_lim, c, nm, s4, m4, pk, pos0, pos1, pc0, pc1);
     if (ch == 0 && wait_pe) wait_p_empty(p_empty_bar, pe_parity, lane);
     const uint32_t rowp = sPb + (ch >> 2) * 16384 + r * 128;
 #pragma unroll
@@ -216,7 +216,7 @@ __device__ __noinline__ void s_softmax_pass(uint32_t ts, float c, float m_ref, i
     if (TL && blockIdx.x == 0 && blockIdx.y == 0 && (j) < 32) p.tl[(role) * 128 + (j) * 4 + (k)] = clock64();  \
   } while (0)
 
-template <int D, bool ONE, bool TL, bool CAUSAL = false>
+template <int D, bool ONE, bool TL, bool CAUSAL = false, bool F16 = false>
 __global__ void __launch_bounds__(192, AttnCfg<D, ONE>::MINB)
 attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
             const __grid_constant__ CUtensorMap tmV, const AttnDev p) {
@@ -291,8 +291,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   } else if (warp == 5) {
     // ================================================================= MMA issuer
     if (lane == 0) {
-      const uint32_t idesc_s = make_idesc(128, C::BKV, 1);
-      const uint32_t idesc_o = make_idesc(128, C::DV, 1);
+      const uint32_t idesc_s = make_idesc(128, C::BKV, F16 ? 0 : 1);
+      const uint32_t idesc_o = make_idesc(128, C::DV, F16 ? 0 : 1);
       mbar_wait(&q_full, 0);
       int st_s = 0, st_p = 0;          // K/V ring slot of the next S product / of the next PV product
       uint32_t ph_s = 0;
@@ -372,12 +372,12 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       if (j == 0) m_use = s_row_max<C::BKV>(ts, kv_valid, row_lim) * c;    // the only two-pass tile
       float rs, mx, mt, pc0 = 0.f, pc1 = 0.f;
       const bool fast = !CAUSAL && kv_valid == C::BKV && !want_pc;
-      if (fast) s_softmax_pass_full<C::BKV>(ts, c, m_use, sPb, r, &p_empty[pbuf], pe_parity, lane, rs, mx);
+      if (fast) s_softmax_pass_full<C::BKV, F16>(ts, c, m_use, sPb, r, &p_empty[pbuf], pe_parity, lane, rs, mx);
       else if (want_pc)
-        s_softmax_pass<C::BKV, true>(ts, c, m_use, kv_valid, row_lim, sPb, r, &p_empty[pbuf], pe_parity, true, lane, rs, mx,
+        s_softmax_pass<C::BKV, true, F16>(ts, c, m_use, kv_valid, row_lim, sPb, r, &p_empty[pbuf], pe_parity, true, lane, rs, mx,
                                      pos0 - j * C::BKV, pos1 - j * C::BKV, pc0, pc1);
       else
-        s_softmax_pass<C::BKV, false>(ts, c, m_use, kv_valid, row_lim, sPb, r, &p_empty[pbuf], pe_parity, true, lane, rs, mx, -1,
+        s_softmax_pass<C::BKV, false, F16>(ts, c, m_use, kv_valid, row_lim, sPb, r, &p_empty[pbuf], pe_parity, true, lane, rs, mx, -1,
                                       -1, pc0, pc1);
       mt = mx * c;
       if (j > 0 && __any_sync(0xffffffffu, mt > m_use + 32.f)) {
@@ -388,10 +388,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         a_pend *= a;
         m_use = m_new;
         if (want_pc)
-          s_softmax_pass<C::BKV, true>(ts, c, m_use, kv_valid, row_lim, sPb, r, &p_empty[pbuf], pe_parity, false, lane, rs, mx,
+          s_softmax_pass<C::BKV, true, F16>(ts, c, m_use, kv_valid, row_lim, sPb, r, &p_empty[pbuf], pe_parity, false, lane, rs, mx,
                                        pos0 - j * C::BKV, pos1 - j * C::BKV, pc0, pc1);
         else
-          s_softmax_pass<C::BKV, false>(ts, c, m_use, kv_valid, row_lim, sPb, r, &p_empty[pbuf], pe_parity, false, lane, rs,
+          s_softmax_pass<C::BKV, false, F16>(ts, c, m_use, kv_valid, row_lim, sPb, r, &p_empty[pbuf], pe_parity, false, lane, rs,
                                         mx, -1, -1, pc0, pc1);
         mt = mx * c;
       }
@@ -472,10 +472,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         for (int g = 0; g < 2; ++g) {
           if (cc * 16 + g * 8 < D) {
             uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]) * inv, __uint_as_float(v[g * 8 + 1]) * inv);
-            u.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]) * inv, __uint_as_float(v[g * 8 + 3]) * inv);
-            u.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]) * inv, __uint_as_float(v[g * 8 + 5]) * inv);
-            u.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]) * inv, __uint_as_float(v[g * 8 + 7]) * inv);
+            u.x = pack16x2<F16>(__uint_as_float(v[g * 8 + 0]) * inv, __uint_as_float(v[g * 8 + 1]) * inv);
+            u.y = pack16x2<F16>(__uint_as_float(v[g * 8 + 2]) * inv, __uint_as_float(v[g * 8 + 3]) * inv);
+            u.z = pack16x2<F16>(__uint_as_float(v[g * 8 + 4]) * inv, __uint_as_float(v[g * 8 + 5]) * inv);
+            u.w = pack16x2<F16>(__uint_as_float(v[g * 8 + 6]) * inv, __uint_as_float(v[g * 8 + 7]) * inv);
             *reinterpret_cast<uint4*>(orow + cc * 16 + g * 8) = u;
           }
         }
@@ -493,7 +493,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 
 static unsigned long long* g_attn_tl_host = nullptr;
 
-template <int D, bool ONE, bool CAUSAL = false>
+template <int D, bool ONE, bool CAUSAL = false, bool F16 = false>
 static int launch_attn(const void* Q, const void* K, const void* Vt, void* out, int64_t ldo, float* probs, int BH,
                        int heads, int nq, int nk, int nk8, float scale, cudaStream_t stream, float* lse2 = nullptr,
                        float* pcols = nullptr, const int* pos = nullptr) {
@@ -534,16 +534,16 @@ static int launch_attn(const void* Q, const void* K, const void* Vt, void* out, 
   p.tl = g_attn_tl_host;
   static bool configured = false;
   if (!configured) {
-    MOS_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel<D, ONE, false, CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    if (!CAUSAL)
-      MOS_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel<D, ONE, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    MOS_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel<D, ONE, false, CAUSAL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    if (!CAUSAL && !F16)
+      MOS_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel<D, ONE, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
   }
   dim3 grid((unsigned)ceil_div(nq, 128), (unsigned)BH);
-  if (!CAUSAL && p.tl != nullptr)
-    MOS_CHECK_CUDA(launch_pdl(attn_kernel<D, ONE, true, false>, grid, dim3(192), (size_t)C::SMEM_BYTES, stream, tmQ, tmK, tmV, p));
+  if (!CAUSAL && !F16 && p.tl != nullptr)
+    MOS_CHECK_CUDA(launch_pdl(attn_kernel<D, ONE, true, false, false>, grid, dim3(192), (size_t)C::SMEM_BYTES, stream, tmQ, tmK, tmV, p));
   else
-    MOS_CHECK_CUDA(launch_pdl(attn_kernel<D, ONE, false, CAUSAL>, grid, dim3(192), (size_t)C::SMEM_BYTES, stream, tmQ, tmK, tmV, p));
+    MOS_CHECK_CUDA(launch_pdl(attn_kernel<D, ONE, false, CAUSAL, F16>, grid, dim3(192), (size_t)C::SMEM_BYTES, stream, tmQ, tmK, tmV, p));
   return MOS_OK;
 }
 
@@ -553,24 +553,26 @@ using namespace mos;
 
 extern "C" int mos_attention_fwd(const void* Q, const void* K, const void* Vt, void* out, int64_t ldo, float* probs,
                                  int32_t batch, int32_t heads, int32_t head_dim, int32_t nq, int32_t nk,
-                                 int32_t nk8, float scale, void* stream_) {
+                                 int32_t nk8, float scale, int32_t act_dtype, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MOS_CHECK_ARG(Q && K && Vt && out, "mos_attention_fwd: NULL pointer");
   MOS_CHECK_ARG(batch > 0 && heads > 0 && nq > 0 && nk > 0, "mos_attention_fwd: bad shape");
   MOS_CHECK_ARG(nk8 >= nk && nk8 % 8 == 0, "mos_attention_fwd: nk8=%d must be >= nk=%d and a multiple of 8", nk8, nk);
   MOS_CHECK_ARG(ldo >= (int64_t)heads * head_dim && ldo % 8 == 0, "mos_attention_fwd: bad ldo");
+  MOS_CHECK_DTYPE(act_dtype, "mos_attention_fwd");
   const int BH = batch * heads;
   if (probs) MOS_CHECK_ARG(nk <= 128, "mos_attention_fwd: probs output needs a single kv tile (nk <= 128)");
+#define MOS_ATTN(D_, ONE_)                                                                                             \
+  (act_dtype == MOS_DT_F16                                                                                             \
+       ? launch_attn<D_, ONE_, false, true>(Q, K, Vt, out, ldo, probs, BH, heads, nq, nk, nk8, scale, stream)         \
+       : launch_attn<D_, ONE_, false, false>(Q, K, Vt, out, ldo, probs, BH, heads, nq, nk, nk8, scale, stream))
   switch (head_dim) {
-    case 40:
-      if (nk <= 128) return launch_attn<40, true>(Q, K, Vt, out, ldo, probs, BH, heads, nq, nk, nk8, scale, stream);
-      return launch_attn<40, false>(Q, K, Vt, out, ldo, probs, BH, heads, nq, nk, nk8, scale, stream);
-    case 80: return launch_attn<80, false>(Q, K, Vt, out, ldo, probs, BH, heads, nq, nk, nk8, scale, stream);
-    case 160:
-      if (nk <= 128) return launch_attn<160, true>(Q, K, Vt, out, ldo, probs, BH, heads, nq, nk, nk8, scale, stream);
-      return launch_attn<160, false>(Q, K, Vt, out, ldo, probs, BH, heads, nq, nk, nk8, scale, stream);
+    case 40: return nk <= 128 ? MOS_ATTN(40, true) : MOS_ATTN(40, false);
+    case 80: return MOS_ATTN(80, false);
+    case 160: return nk <= 128 ? MOS_ATTN(160, true) : MOS_ATTN(160, false);
     default: return set_err(MOS_EUNSUPPORTED, "mos_attention_fwd: head_dim %d not in {40, 80, 160}", head_dim);
   }
+#undef MOS_ATTN
 }
 
 

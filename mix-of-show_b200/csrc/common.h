@@ -26,6 +26,9 @@ int set_err(int code, const char* fmt, ...);  // stores thread-local message, re
                             __FILE__, __LINE__);                                                   \
   } while (0)
 
+#define MOS_CHECK_DTYPE(dt, who) \
+  MOS_CHECK_ARG((dt) == MOS_DT_BF16 || (dt) == MOS_DT_F16, who ": act_dtype %d is neither MOS_DT_BF16 nor MOS_DT_F16", (int)(dt))
+
 #define MOS_CHECK_LAUNCH() MOS_CHECK_CUDA(cudaGetLastError())
 
 // Encode a tiled bf16/fp32 tensor map. dims/strides innermost first; strides[i] is the byte pitch of dim i+1.

@@ -71,6 +71,7 @@ __global__ void gemv_kernel(const float* __restrict__ x, int K, const __nv_bfloa
 
 // ---------------------------------------------------------------------------------- conv_in / conv_out
 // x: NCHW fp32 [B, Cin(4), H, W]; w: fp32 [9*Cin][Cout] (tap-major, Cout contiguous); y: NHWC bf16 [B,H,W,ldy]
+template <bool F16>
 __global__ void conv_in_kernel(const float* __restrict__ x, int B, int Cin, int H, int W,
                                const float* __restrict__ w, const float* __restrict__ bias, int Cout,
                                __nv_bfloat16* __restrict__ y, long long ldy) {
@@ -105,15 +106,16 @@ __global__ void conv_in_kernel(const float* __restrict__ x, int B, int Cin, int 
     }
   }
   uint4 u;
-  u.x = pack_bf16x2(acc[0], acc[1]);
-  u.y = pack_bf16x2(acc[2], acc[3]);
-  u.z = pack_bf16x2(acc[4], acc[5]);
-  u.w = pack_bf16x2(acc[6], acc[7]);
+  u.x = pack16x2<F16>(acc[0], acc[1]);
+  u.y = pack16x2<F16>(acc[2], acc[3]);
+  u.z = pack16x2<F16>(acc[4], acc[5]);
+  u.w = pack16x2<F16>(acc[6], acc[7]);
   *reinterpret_cast<uint4*>(y + pix * ldy + o * 8) = u;
 }
 
 // x: NHWC bf16 [B,H,W,C] (contiguous, already GN+SiLU'd); w: fp32 [Cout(4)][9][C]; y: NCHW fp32 [B,Cout,H,W]
 // one warp per output pixel
+template <bool F16>
 __global__ void conv_out_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C,
                                 const float* __restrict__ w, const float* __restrict__ bias, int Cout,
                                 float* __restrict__ y) {
@@ -137,7 +139,7 @@ __global__ void conv_out_kernel(const __nv_bfloat16* __restrict__ x, int B, int 
       float xv[8];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        float2 f = unpack_bf16x2(uw[i]);
+        float2 f = unpack16x2<F16>(uw[i]);
         xv[2 * i] = f.x;
         xv[2 * i + 1] = f.y;
       }
@@ -205,6 +207,7 @@ __global__ void im2col_s2_kernel(const __nv_bfloat16* __restrict__ x, long long 
 }
 
 // x[m, :C] += r[m, :C]   (bf16, row pitches ldx / ldr)
+template <bool F16>
 __global__ void add_rows_kernel(__nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ r,
                                 long long ldr, long long M, int C) {
   pdl_wait();
@@ -219,8 +222,8 @@ __global__ void add_rows_kernel(__nv_bfloat16* __restrict__ x, long long ldx, co
   uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w}, ow[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float2 fa = unpack_bf16x2(aw[i]), fb = unpack_bf16x2(bw[i]);
-    ow[i] = pack_bf16x2(fa.x + fb.x, fa.y + fb.y);
+    float2 fa = unpack16x2<F16>(aw[i]), fb = unpack16x2<F16>(bw[i]);
+    ow[i] = pack16x2<F16>(fa.x + fb.x, fa.y + fb.y);
   }
   *reinterpret_cast<uint4*>(x + m * ldx + o * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
 }
@@ -305,6 +308,7 @@ struct RegionBoxes {
   int n;
   int box[8][4];  // sh, sw, eh, ew in feature pixels (host computes the ceil/floor in float64)
 };
+template <bool F16>
 __global__ void region_combine_kernel(const __nv_bfloat16* __restrict__ glob, const __nv_bfloat16* const* __restrict__ regs,
                                       RegionBoxes rb, int B, int FH, int FW, int C, long long ld,
                                       __nv_bfloat16* __restrict__ out) {
@@ -328,7 +332,7 @@ __global__ void region_combine_kernel(const __nv_bfloat16* __restrict__ glob, co
       uint32_t uw[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        float2 f = unpack_bf16x2(uw[i]);
+        float2 f = unpack16x2<F16>(uw[i]);
         acc[2 * i] += f.x;
         acc[2 * i + 1] += f.y;
       }
@@ -339,10 +343,10 @@ __global__ void region_combine_kernel(const __nv_bfloat16* __restrict__ glob, co
     res = __ldg(reinterpret_cast<const uint4*>(glob + pix * ld + o * 8));
   } else {
     float inv = 1.0f / (float)count;
-    res.x = pack_bf16x2(acc[0] * inv, acc[1] * inv);
-    res.y = pack_bf16x2(acc[2] * inv, acc[3] * inv);
-    res.z = pack_bf16x2(acc[4] * inv, acc[5] * inv);
-    res.w = pack_bf16x2(acc[6] * inv, acc[7] * inv);
+    res.x = pack16x2<F16>(acc[0] * inv, acc[1] * inv);
+    res.y = pack16x2<F16>(acc[2] * inv, acc[3] * inv);
+    res.z = pack16x2<F16>(acc[4] * inv, acc[5] * inv);
+    res.w = pack16x2<F16>(acc[6] * inv, acc[7] * inv);
   }
   *reinterpret_cast<uint4*>(out + pix * ld + o * 8) = res;
 }
@@ -381,20 +385,22 @@ extern "C" int mos_gemv_bf16(const float* x, int32_t nb, int32_t K, const void* 
 }
 
 extern "C" int mos_conv_in(const float* x, int32_t B, int32_t Cin, int32_t H, int32_t W, const float* w,
-                           const float* bias, int32_t Cout, void* y, int64_t ldy, void* stream) {
+                           const float* bias, int32_t Cout, void* y, int64_t ldy, int32_t act_dtype, void* stream) {
   MOS_CHECK_ARG(x && w && bias && y && Cout % 8 == 0 && ldy % 8 == 0, "mos_conv_in: bad arguments");
+  MOS_CHECK_DTYPE(act_dtype, "mos_conv_in");
   long long total = (long long)B * H * W * (Cout / 8);
-  MOS_CHECK_CUDA(launch_pdl(conv_in_kernel, dim3(nblk(total, 256)), dim3(256), 0, STREAM(stream), x, B, Cin, H, W, w, bias, Cout,
-                                                               reinterpret_cast<__nv_bfloat16*>(y), ldy));
+  MOS_CHECK_CUDA(launch_pdl(act_dtype ? conv_in_kernel<true> : conv_in_kernel<false>, dim3(nblk(total, 256)), dim3(256), 0,
+                            STREAM(stream), x, B, Cin, H, W, w, bias, Cout, reinterpret_cast<__nv_bfloat16*>(y), ldy));
   return MOS_OK;
 }
 
 extern "C" int mos_conv_out(const void* x, int32_t B, int32_t H, int32_t W, int32_t C, const float* w,
-                            const float* bias, int32_t Cout, float* y, void* stream) {
+                            const float* bias, int32_t Cout, float* y, int32_t act_dtype, void* stream) {
   MOS_CHECK_ARG(x && w && bias && y && C % 8 == 0 && Cout <= 4, "mos_conv_out: bad arguments");
+  MOS_CHECK_DTYPE(act_dtype, "mos_conv_out");
   long long pix = (long long)B * H * W;
-  MOS_CHECK_CUDA(launch_pdl(conv_out_kernel, dim3(nblk(pix, 8)), dim3(256), 0, STREAM(stream), reinterpret_cast<const __nv_bfloat16*>(x), B, H, W, C, w,
-                                                            bias, Cout, y));
+  MOS_CHECK_CUDA(launch_pdl(act_dtype ? conv_out_kernel<true> : conv_out_kernel<false>, dim3(nblk(pix, 8)), dim3(256), 0,
+                            STREAM(stream), reinterpret_cast<const __nv_bfloat16*>(x), B, H, W, C, w, bias, Cout, y));
   return MOS_OK;
 }
 
@@ -416,9 +422,11 @@ extern "C" int mos_im2col_s2(const void* x, int64_t ldx, int32_t B, int32_t H, i
   return MOS_OK;
 }
 
-extern "C" int mos_add_rows(void* x, int64_t ldx, const void* r, int64_t ldr, int64_t M, int32_t C, void* stream) {
+extern "C" int mos_add_rows(void* x, int64_t ldx, const void* r, int64_t ldr, int64_t M, int32_t C, int32_t act_dtype,
+                            void* stream) {
   MOS_CHECK_ARG(x && r && C % 8 == 0 && ldx % 8 == 0 && ldr % 8 == 0, "mos_add_rows: bad arguments");
-  MOS_CHECK_CUDA(launch_pdl(add_rows_kernel, dim3(nblk(M * (C / 8), 256)), dim3(256), 0, STREAM(stream),
+  MOS_CHECK_DTYPE(act_dtype, "mos_add_rows");
+  MOS_CHECK_CUDA(launch_pdl(act_dtype ? add_rows_kernel<true> : add_rows_kernel<false>, dim3(nblk(M * (C / 8), 256)), dim3(256), 0, STREAM(stream),
                             reinterpret_cast<__nv_bfloat16*>(x), (long long)ldx,
                             reinterpret_cast<const __nv_bfloat16*>(r), (long long)ldr, (long long)M, (int)C));
   return MOS_OK;
@@ -454,15 +462,17 @@ extern "C" int mos_cfg_dpmpp_step(const float* noise_pred, float* latents, float
 
 extern "C" int mos_region_combine(const void* glob, const void* const* region_ptrs_dev, int32_t nregions,
                                   const int32_t* boxes_host, int32_t B, int32_t FH, int32_t FW, int32_t C, int64_t ld,
-                                  void* out, void* stream) {
+                                  void* out, int32_t act_dtype, void* stream) {
   MOS_CHECK_ARG(glob && out && region_ptrs_dev && boxes_host && nregions >= 0 && nregions <= 8 && C % 8 == 0,
                 "mos_region_combine: bad arguments (at most 8 regions)");
+  MOS_CHECK_DTYPE(act_dtype, "mos_region_combine");
   RegionBoxes rb;
   rb.n = nregions;
   for (int r = 0; r < nregions; ++r)
     for (int k = 0; k < 4; ++k) rb.box[r][k] = boxes_host[r * 4 + k];
   long long total = (long long)B * FH * FW * (C / 8);
-  MOS_CHECK_CUDA(launch_pdl(region_combine_kernel, dim3(nblk(total, 256)), dim3(256), 0, STREAM(stream), 
+  MOS_CHECK_CUDA(launch_pdl(act_dtype ? region_combine_kernel<true> : region_combine_kernel<false>, dim3(nblk(total, 256)),
+                            dim3(256), 0, STREAM(stream),
       reinterpret_cast<const __nv_bfloat16*>(glob), reinterpret_cast<const __nv_bfloat16* const*>(region_ptrs_dev), rb,
       B, FH, FW, C, ld, reinterpret_cast<__nv_bfloat16*>(out)));
   return MOS_OK;

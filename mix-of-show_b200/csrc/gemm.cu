@@ -72,14 +72,16 @@ struct GemmDev {
   int accum;           // MOS_OUT_F32: out += result (Gram accumulation)
   unsigned long long* tl;   // optional timeline buffer (mos_debug_set_timeline)
   int w_static;        // W tiles may be requested before griddepcontrol.wait
+  int w_f16;           // W (and the LoRA rows) are fp16 instead of bf16 (Gram products of fp16 activations)
 };
 
-__device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v) {
+template <bool F16>
+__device__ __forceinline__ void store16x8(__nv_bfloat16* dst, const float* v) {
   uint4 u;
-  u.x = pack_bf16x2(v[0], v[1]);
-  u.y = pack_bf16x2(v[2], v[3]);
-  u.z = pack_bf16x2(v[4], v[5]);
-  u.w = pack_bf16x2(v[6], v[7]);
+  u.x = pack16x2<F16>(v[0], v[1]);
+  u.y = pack16x2<F16>(v[2], v[3]);
+  u.z = pack16x2<F16>(v[4], v[5]);
+  u.w = pack16x2<F16>(v[6], v[7]);
   *reinterpret_cast<uint4*>(dst) = u;
 }
 
@@ -173,6 +175,7 @@ __device__ __forceinline__ void stage_copy(const GemmDev& p, const TileCoord& t,
   }
 }
 
+template <bool F16>   // 16-bit type of A, of the row / head-split outputs and of the residual: fp16 or bf16
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmL, const GemmDev p) {
@@ -302,7 +305,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(BM, p.lora ? BN + LORA_N : BN, 1);
+      const uint32_t idesc = make_idesc_ab(BM, p.lora ? BN + LORA_N : BN, F16 ? 0 : 1, p.w_f16 ? 0 : 1);
       const uint16_t mask_all = (uint16_t)((1u << csize) - 1);
       int stage = 0;
       uint32_t phase = 0;
@@ -435,7 +438,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               }
               o[j] = a * gelu_erf(g);
             }
-            store_bf16x8(reinterpret_cast<__nv_bfloat16*>(srow + c * 16), o);
+            store16x8<F16>(reinterpret_cast<__nv_bfloat16*>(srow + c * 16), o);
           }
         } else {
 #pragma unroll 1
@@ -475,13 +478,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                  const float2 f = unpack_bf16x2(rr[j]);
+                  const float2 f = unpack16x2<F16>(rr[j]);
                   o[2 * j] += f.x;
                   o[2 * j + 1] += f.y;
                 }
               }
-              store_bf16x8(reinterpret_cast<__nv_bfloat16*>(srow + nl * 2), o);
-              store_bf16x8(reinterpret_cast<__nv_bfloat16*>(srow + nl * 2 + 16), o + 8);
+              store16x8<F16>(reinterpret_cast<__nv_bfloat16*>(srow + nl * 2), o);
+              store16x8<F16>(reinterpret_cast<__nv_bfloat16*>(srow + nl * 2 + 16), o + 8);
             } else if (p.out_mode == MOS_OUT_F32) {
               if (valid) {
                 float* orow = reinterpret_cast<float*>(p.out) + m * p.ldc + nc;
@@ -509,12 +512,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(p.seg_ptr[seg]);
                 const long long bh = bb * p.heads + head;
                 if (p.seg_kind[seg] == MOS_SEG_ROWS) {
-                  store_bf16x8(base + (bh * p.seg_rows_pad[seg] + tok) * p.dpad + j0, o + half * 8);
+                  store16x8<F16>(base + (bh * p.seg_rows_pad[seg] + tok) * p.dpad + j0, o + half * 8);
                 } else {
                   __nv_bfloat16* d = base + (bh * p.dv_pad + j0) * p.seg_rows_pad[seg] + tok;
 #pragma unroll
                   for (int e = 0; e < 8; ++e)
-                    d[(long long)e * p.seg_rows_pad[seg]] = __float2bfloat16(o[half * 8 + e]);
+                    reinterpret_cast<uint16_t*>(d)[(long long)e * p.seg_rows_pad[seg]] = cvt16<F16>(o[half * 8 + e]);
                 }
               }
             }
@@ -552,6 +555,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 }
 
 // ---------------------------------------------------------------------------------------------- split-K finalize
+template <bool F16>
 __global__ void splitk_finalize_kernel(const float* __restrict__ partial, int splits, long long M, long long N,
                                        const float* __restrict__ bias, const float* __restrict__ bias_batch,
                                        long long rows_per_batch, long long bias_batch_ld,
@@ -582,12 +586,12 @@ __global__ void splitk_finalize_kernel(const float* __restrict__ partial, int sp
   }
   if (residual) {
     uint2 r = __ldg(reinterpret_cast<const uint2*>(residual + m * ldr + n));
-    float2 a = unpack_bf16x2(r.x), b = unpack_bf16x2(r.y);
+    float2 a = unpack16x2<F16>(r.x), b = unpack16x2<F16>(r.y);
     acc.x += a.x; acc.y += a.y; acc.z += b.x; acc.w += b.y;
   }
   uint2 o;
-  o.x = pack_bf16x2(acc.x, acc.y);
-  o.y = pack_bf16x2(acc.z, acc.w);
+  o.x = pack16x2<F16>(acc.x, acc.y);
+  o.y = pack16x2<F16>(acc.z, acc.w);
   *reinterpret_cast<uint2*>(out + m * ldc + n) = o;
 }
 
@@ -612,6 +616,9 @@ extern "C" int mos_gemm_bf16(const mos_gemm_args* a, void* stream_) {
   MOS_CHECK_ARG(a->N % BN == 0, "mos_gemm_bf16: N=%lld must be a multiple of %d", (long long)a->N, BN);
   MOS_CHECK_ARG(a->K % BK == 0, "mos_gemm_bf16: K=%lld must be a multiple of %d", (long long)a->K, BK);
   MOS_CHECK_ARG(is_aligned(a->A, 16) && is_aligned(a->W, 16), "mos_gemm_bf16: A/W must be 16-byte aligned");
+  MOS_CHECK_DTYPE(a->a_dtype, "mos_gemm_bf16 (a_dtype)");
+  MOS_CHECK_DTYPE(a->w_dtype, "mos_gemm_bf16 (w_dtype)");
+  const bool f16 = a->a_dtype == MOS_DT_F16;
   const int splits = a->splits > 0 ? a->splits : 1;
   const bool lora = a->lora_down != nullptr;
   if (splits > 1) {
@@ -766,6 +773,7 @@ extern "C" int mos_gemm_bf16(const mos_gemm_args* a, void* stream_) {
   p.accum = a->accumulate;
   p.tl = g_timeline_host;
   p.w_static = a->w_static;
+  p.w_f16 = a->w_dtype == MOS_DT_F16;
   if (a->bias_batch && !a->conv)
     MOS_CHECK_ARG(p.rows_per_batch >= 32, "mos_gemm_bf16: bias_batch needs rows_per_batch >= 32 in plain mode");
   p.total_super = (p.n_tiles / p.cx) * (m_tiles / p.cm) * splits;
@@ -784,7 +792,8 @@ extern "C" int mos_gemm_bf16(const mos_gemm_args* a, void* stream_) {
     int dev = 0;
     MOS_CHECK_CUDA(cudaGetDevice(&dev));
     MOS_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    MOS_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM));
+    MOS_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM));
+    MOS_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM));
   }
   // persistent: one CTA per SM; each cluster loops over its share of (super-tile, split) work items
   cudaLaunchConfig_t cfg;
@@ -814,7 +823,7 @@ extern "C" int mos_gemm_bf16(const mos_gemm_args* a, void* stream_) {
       cudaLaunchAttribute only_cluster[1] = {attr[1]};
       cfg.attrs = only_cluster;
       cfg.numAttrs = 1;
-      MOS_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_kernel, &cfg));
+      MOS_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_kernel<false>, &cfg));
       cfg.attrs = attr;
       MOS_CHECK_ARG(n > 0, "mos_gemm_bf16: cluster size %d cannot be scheduled", csize);
     } else {
@@ -827,7 +836,8 @@ extern "C" int mos_gemm_bf16(const mos_gemm_args* a, void* stream_) {
   cfg.gridDim = dim3((unsigned)(clusters * csize));
   cfg.dynamicSmemBytes = (size_t)smem_bytes;
   cfg.numAttrs = csize > 1 ? 2 : 1;   // no cluster attribute at all for unclustered launches
-  MOS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel, tmA, tmB, tmL, p));
+  if (f16) MOS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<true>, tmA, tmB, tmL, p));
+  else MOS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<false>, tmA, tmB, tmL, p));
   return MOS_OK;
 }
 
@@ -838,13 +848,16 @@ extern "C" int mos_debug_set_timeline(void* buf) {
 
 extern "C" int mos_splitk_finalize(const float* partial, int32_t splits, int64_t M, int64_t N, const float* bias,
                                    const float* bias_batch, int64_t rows_per_batch, int64_t bias_batch_ld,
-                                   const void* residual, int64_t ldr, void* out, int64_t ldc, void* stream_) {
+                                   const void* residual, int64_t ldr, void* out, int64_t ldc, int32_t act_dtype,
+                                   void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MOS_CHECK_ARG(partial && out && splits >= 1 && M > 0 && N > 0 && N % 4 == 0, "mos_splitk_finalize: bad arguments");
+  MOS_CHECK_DTYPE(act_dtype, "mos_splitk_finalize");
   long long total = M * (N / 4);
   int threads = 256;
   long long blocks = ceil_div(total, threads);
-  MOS_CHECK_CUDA(launch_pdl(splitk_finalize_kernel, dim3((unsigned)blocks), dim3(threads), 0, stream, partial,
+  MOS_CHECK_CUDA(launch_pdl(act_dtype == MOS_DT_F16 ? splitk_finalize_kernel<true> : splitk_finalize_kernel<false>,
+                            dim3((unsigned)blocks), dim3(threads), 0, stream, partial,
                             (int)splits, (long long)M, (long long)N, bias, bias_batch,
                             (long long)(rows_per_batch > 0 ? rows_per_batch : 1),
                             (long long)(bias_batch_ld > 0 ? bias_batch_ld : N),

@@ -13,6 +13,7 @@ namespace mos {
 constexpr int GN_GROUPS = 32;
 
 // partial[b][chunk][g][2] = (sum, sumsq) over rows [chunk*rows_per_chunk, ...) of batch b
+template <bool F16>
 __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int HW, int C,
                                 int rows_per_chunk, float* __restrict__ partial) {
   extern __shared__ float red[];  // [blockDim][16]: per-thread channel sums / sums of squares
@@ -39,7 +40,7 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long l
       const uint32_t w[4] = {u4[k].x, u4[k].y, u4[k].z, u4[k].w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        float2 f = unpack_bf16x2(w[i]);
+        float2 f = unpack16x2<F16>(w[i]);
         s[2 * i] += f.x;
         q[2 * i] += f.x * f.x;
         s[2 * i + 1] += f.y;
@@ -69,6 +70,7 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long l
   }
 }
 
+template <bool F16>
 __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int HW, int C,
                                 const float* __restrict__ partial, int nchunks, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float eps, int silu_act, int rows_per_block,
@@ -131,7 +133,7 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long l
         float v[8];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          float2 f = unpack_bf16x2(w[i]);
+          float2 f = unpack16x2<F16>(w[i]);
           v[2 * i] = f.x * sc[2 * i] + sh[2 * i];
           v[2 * i + 1] = f.y * sc[2 * i + 1] + sh[2 * i + 1];
         }
@@ -140,10 +142,10 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long l
           for (int i = 0; i < 8; ++i) v[i] = silu(v[i]);
         }
         uint4 out;
-        out.x = pack_bf16x2(v[0], v[1]);
-        out.y = pack_bf16x2(v[2], v[3]);
-        out.z = pack_bf16x2(v[4], v[5]);
-        out.w = pack_bf16x2(v[6], v[7]);
+        out.x = pack16x2<F16>(v[0], v[1]);
+        out.y = pack16x2<F16>(v[2], v[3]);
+        out.z = pack16x2<F16>(v[4], v[5]);
+        out.w = pack16x2<F16>(v[6], v[7]);
         *reinterpret_cast<uint4*>(yb + (long long)r * ldy) = out;
       }
     }
@@ -151,6 +153,7 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long l
 }
 
 // One warp per row; C <= 1280 (5 octets per lane), two-pass statistics in registers.
+template <bool F16>
 __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, long long M, int C,
                                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                  __nv_bfloat16* __restrict__ y, long long ldy) {
@@ -171,7 +174,7 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long 
       uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        float2 f = unpack_bf16x2(w[i]);
+        float2 f = unpack16x2<F16>(w[i]);
         v[k][2 * i] = f.x;
         v[k][2 * i + 1] = f.y;
         s += f.x + f.y;
@@ -211,10 +214,10 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long 
 #pragma unroll
       for (int i = 0; i < 8; ++i) r[i] = (v[k][i] - mean) * rstd * gg[i] + bb[i];
       uint4 out;
-      out.x = pack_bf16x2(r[0], r[1]);
-      out.y = pack_bf16x2(r[2], r[3]);
-      out.z = pack_bf16x2(r[4], r[5]);
-      out.w = pack_bf16x2(r[6], r[7]);
+      out.x = pack16x2<F16>(r[0], r[1]);
+      out.y = pack16x2<F16>(r[2], r[3]);
+      out.z = pack16x2<F16>(r[4], r[5]);
+      out.w = pack16x2<F16>(r[6], r[7]);
       *reinterpret_cast<uint4*>(yr + o * 8) = out;
     }
   }
@@ -227,6 +230,7 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long 
 // of x, one write of y, one launch.
 constexpr int GN_MAXR = 8;   // rows per thread kept in registers
 
+template <bool F16>
 __global__ void __launch_bounds__(320, 2)
 gn_fused_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int HW, int C, int rows_per_chunk,
                 float* __restrict__ partial, unsigned int* __restrict__ counters, const float* __restrict__ gamma,
@@ -258,7 +262,7 @@ gn_fused_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int HW, int 
       const uint32_t w[4] = {rows[k].x, rows[k].y, rows[k].z, rows[k].w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float2 f = unpack_bf16x2(w[i]);
+        const float2 f = unpack16x2<F16>(w[i]);
         s[2 * i] += f.x;
         q[2 * i] += f.x * f.x;
         s[2 * i + 1] += f.y;
@@ -353,7 +357,7 @@ gn_fused_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int HW, int 
       float v[8];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float2 f = unpack_bf16x2(w[i]);
+        const float2 f = unpack16x2<F16>(w[i]);
         v[2 * i] = f.x * sc[2 * i] + sh[2 * i];
         v[2 * i + 1] = f.y * sc[2 * i + 1] + sh[2 * i + 1];
       }
@@ -362,10 +366,10 @@ gn_fused_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int HW, int 
         for (int i = 0; i < 8; ++i) v[i] = silu(v[i]);
       }
       uint4 out;
-      out.x = pack_bf16x2(v[0], v[1]);
-      out.y = pack_bf16x2(v[2], v[3]);
-      out.z = pack_bf16x2(v[4], v[5]);
-      out.w = pack_bf16x2(v[6], v[7]);
+      out.x = pack16x2<F16>(v[0], v[1]);
+      out.y = pack16x2<F16>(v[2], v[3]);
+      out.z = pack16x2<F16>(v[4], v[5]);
+      out.w = pack16x2<F16>(v[6], v[7]);
       *reinterpret_cast<uint4*>(yb + (long long)r * ldy) = out;
     }
   }
@@ -675,9 +679,12 @@ using namespace mos;
 // nchunks = *nchunks_io (0 = choose; the chosen value is returned through the pointer).
 extern "C" int mos_groupnorm_fwd(const void* x, int64_t ldx, int32_t B, int32_t HW, int32_t C, const float* gamma,
                                  const float* beta, float eps, int32_t silu_act, float* partial,
-                                 int32_t partial_capacity_floats, void* y, int64_t ldy, void* stream_) {
+                                 int32_t partial_capacity_floats, void* y, int64_t ldy, int32_t act_dtype,
+                                 void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MOS_CHECK_ARG(x && y && gamma && beta && partial, "mos_groupnorm_fwd: NULL pointer");
+  MOS_CHECK_DTYPE(act_dtype, "mos_groupnorm_fwd");
+  const bool f16 = act_dtype == MOS_DT_F16;
   MOS_CHECK_ARG(C % 32 == 0 && C % 8 == 0 && C <= 2560 && ldx % 8 == 0 && ldy % 8 == 0 && ldx >= C && ldy >= C,
                 "mos_groupnorm_fwd: bad C=%d ldx=%lld ldy=%lld", C, (long long)ldx, (long long)ldy);
   const int threads = gn_block_threads(C);
@@ -693,7 +700,7 @@ extern "C" int mos_groupnorm_fwd(const void* x, int64_t ldx, int32_t B, int32_t 
     int dev = 0, sms = 0, per_sm = 0;
     MOS_CHECK_CUDA(cudaGetDevice(&dev));
     MOS_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    MOS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_fused_kernel, 320, 320 * 16 * sizeof(float)));
+    MOS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_fused_kernel<false>, 320, 320 * 16 * sizeof(float)));
     capacity = sms * (per_sm > 0 ? per_sm : 1);
   }
   if (use_fused) {
@@ -705,7 +712,7 @@ extern "C" int mos_groupnorm_fwd(const void* x, int64_t ldx, int32_t B, int32_t 
     const long long need = (long long)B * nchunks * GN_GROUPS * 2 + 64;   // + per-sample ticket counters
     if (rows_per_chunk <= GN_MAXR * lanes && B <= 32 && need <= partial_capacity_floats && B * nchunks <= capacity) {
       unsigned int* counters = reinterpret_cast<unsigned int*>(partial + partial_capacity_floats - 64);
-      MOS_CHECK_CUDA(launch_pdl(gn_fused_kernel, dim3(nchunks, B), dim3(threads), threads * 16 * sizeof(float), stream,
+      MOS_CHECK_CUDA(launch_pdl(f16 ? gn_fused_kernel<true> : gn_fused_kernel<false>, dim3(nchunks, B), dim3(threads), threads * 16 * sizeof(float), stream,
                                 reinterpret_cast<const __nv_bfloat16*>(x), (long long)ldx, (int)HW, (int)C,
                                 rows_per_chunk, partial, counters, gamma, beta, eps, (int)silu_act,
                                 reinterpret_cast<__nv_bfloat16*>(y), (long long)ldy));
@@ -727,10 +734,10 @@ extern "C" int mos_groupnorm_fwd(const void* x, int64_t ldx, int32_t B, int32_t 
   MOS_CHECK_ARG((long long)B * nchunks * GN_GROUPS * 2 <= partial_capacity_floats,
                 "mos_groupnorm_fwd: partial workspace too small (need %lld floats)",
                 (long long)B * nchunks * GN_GROUPS * 2);
-  MOS_CHECK_CUDA(launch_pdl(gn_stats_kernel, dim3(nchunks, B), dim3(threads), threads * 16 * sizeof(float), stream,
-                            reinterpret_cast<const __nv_bfloat16*>(x), (long long)ldx, (int)HW, (int)C, rows_per_chunk,
-                            partial));
-  MOS_CHECK_CUDA(launch_pdl(gn_apply_kernel, dim3(nchunks, B), dim3(threads), 0, stream,
+  MOS_CHECK_CUDA(launch_pdl(f16 ? gn_stats_kernel<true> : gn_stats_kernel<false>, dim3(nchunks, B), dim3(threads),
+                            threads * 16 * sizeof(float), stream, reinterpret_cast<const __nv_bfloat16*>(x), (long long)ldx,
+                            (int)HW, (int)C, rows_per_chunk, partial));
+  MOS_CHECK_CUDA(launch_pdl(f16 ? gn_apply_kernel<true> : gn_apply_kernel<false>, dim3(nchunks, B), dim3(threads), 0, stream,
                             reinterpret_cast<const __nv_bfloat16*>(x), (long long)ldx, (int)HW, (int)C,
                             (const float*)partial, nchunks, gamma, beta, eps, (int)silu_act, rows_per_chunk,
                             reinterpret_cast<__nv_bfloat16*>(y), (long long)ldy));
@@ -738,12 +745,14 @@ extern "C" int mos_groupnorm_fwd(const void* x, int64_t ldx, int32_t B, int32_t 
 }
 
 extern "C" int mos_layernorm_fwd(const void* x, int64_t ldx, int64_t M, int32_t C, const float* gamma,
-                                 const float* beta, float eps, void* y, int64_t ldy, void* stream_) {
+                                 const float* beta, float eps, void* y, int64_t ldy, int32_t act_dtype, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MOS_CHECK_ARG(x && y && gamma && beta, "mos_layernorm_fwd: NULL pointer");
+  MOS_CHECK_DTYPE(act_dtype, "mos_layernorm_fwd");
   MOS_CHECK_ARG(C % 8 == 0 && C <= 1280 && ldx % 8 == 0 && ldy % 8 == 0, "mos_layernorm_fwd: bad C=%d", C);
   const int warps = 8;
-  MOS_CHECK_CUDA(launch_pdl(layernorm_kernel, dim3((unsigned)ceil_div(M, warps)), dim3(warps * 32), 0, stream,
+  MOS_CHECK_CUDA(launch_pdl(act_dtype == MOS_DT_F16 ? layernorm_kernel<true> : layernorm_kernel<false>,
+                            dim3((unsigned)ceil_div(M, warps)), dim3(warps * 32), 0, stream,
                             reinterpret_cast<const __nv_bfloat16*>(x), (long long)ldx, (long long)M, (int)C, gamma, beta,
                             eps, reinterpret_cast<__nv_bfloat16*>(y), (long long)ldy));
   return MOS_OK;
@@ -776,7 +785,7 @@ extern "C" int mos_groupnorm_bwd(const void* x, int64_t ldx, const void* dy, int
   float* p2 = workspace + (long long)B * nchunks * GN_GROUPS * 2;
   const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
   const __nv_bfloat16* db = reinterpret_cast<const __nv_bfloat16*>(dy);
-  MOS_CHECK_CUDA(launch_pdl(gn_stats_kernel, dim3(nchunks, B), dim3(threads), threads * 16 * sizeof(float), stream, xb,
+  MOS_CHECK_CUDA(launch_pdl(gn_stats_kernel<false>, dim3(nchunks, B), dim3(threads), threads * 16 * sizeof(float), stream, xb,
                             (long long)ldx, (int)HW, (int)C, rows_per_chunk, p1));
   MOS_CHECK_CUDA(launch_pdl(gn_bwd_reduce_kernel, dim3(nchunks, B), dim3(threads), threads * 16 * sizeof(float), stream,
                             xb, (long long)ldx, db, (long long)lddy, (int)HW, (int)C, (const float*)p1, gamma, beta, eps,

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -270,6 +271,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int fmt) {
   return (1u << 4) | (uint32_t(fmt) << 7) | (uint32_t(fmt) << 10) | (uint32_t(N >> 3) << 17) |
          (uint32_t(M >> 4) << 24);
 }
+// same with separate A / B formats (kind::f16 takes f16 and bf16 operands in any combination: fp16 activations against
+// bf16 weights)
+__host__ __device__ constexpr uint32_t make_idesc_ab(int M, int N, int afmt, int bfmt) {
+  return (1u << 4) | (uint32_t(afmt) << 7) | (uint32_t(bfmt) << 10) | (uint32_t(N >> 3) << 17) |
+         (uint32_t(M >> 4) << 24);
+}
 
 // ------------------------------------------------------------------ small math helpers
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -279,6 +286,34 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(t);
+}
+// 16-bit activation storage is bf16 (training) or fp16 (inference: 3 more mantissa bits, which is what keeps the
+// classifier-free-guidance difference c - u accurate; profiles/README.md "numerics, round 2"); F16 selects the codec.
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 t = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t u) {
+  __half2 t = *reinterpret_cast<__half2*>(&u);
+  return __half22float2(t);
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi) {
+  return F16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
+}
+template <bool F16>
+__device__ __forceinline__ float2 unpack16x2(uint32_t u) {
+  return F16 ? unpack_f16x2(u) : unpack_bf16x2(u);
+}
+template <bool F16>
+__device__ __forceinline__ uint16_t cvt16(float v) {
+  if (F16) return __half_as_ushort(__float2half_rn(v));
+  return __bfloat16_as_ushort(__float2bfloat16(v));
+}
+template <bool F16>
+__device__ __forceinline__ float ld16(const __nv_bfloat16* p) {   // 16-bit storage is typed __nv_bfloat16* throughout
+  const uint16_t u = *reinterpret_cast<const uint16_t*>(p);
+  return F16 ? __half2float(__ushort_as_half(u)) : __bfloat162float(__ushort_as_bfloat16(u));
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }

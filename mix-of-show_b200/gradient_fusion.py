@@ -400,9 +400,9 @@ class GramRecorder:
         if first:
             G = self.G[key] = torch.zeros(C, C, device=self.dev, dtype=F32)
             self.rows[key] = 0
-        xt = self._xt.get((C, M))
+        xt = self._xt.get((C, M, A.dtype))
         if xt is None:
-            xt = self._xt[(C, M)] = torch.empty(C, M, device=self.dev, dtype=torch.bfloat16)
+            xt = self._xt[(C, M, A.dtype)] = torch.empty(C, M, device=self.dev, dtype=A.dtype)
         ops.transpose_bf16(A, xt, rows=M, C=C, ldx=A.stride(0))
         ops.gemm(xt, xt, G, out_f32=True, accumulate=True)
         self.rows[key] += M

@@ -18,6 +18,15 @@ from mos_b200.engine import ehs_to_layer_major
 from mos_b200.scheduler import DPMSolverPP2M
 
 
+def numpy_to_pil(images):
+    """[N,H,W,3] floats in [0,1] -> list of PIL images (diffusers `DiffusionPipeline.numpy_to_pil`, reached from the
+    reference at pipeline_edlora.py:313), so that `.images[0].save(...)` works as in the reference's scripts."""
+    from PIL import Image
+    if images.ndim == 3:
+        images = images[None]
+    return [Image.fromarray(im) for im in (images * 255).round().astype('uint8')]
+
+
 def bind_concept_prompt(prompts, new_concept_cfg):
     """Each prompt becomes 16 layer-specific prompts; `concept_name` -> `concept_token_names[layer]`
     (reference :18-29). Output order: prompt-major, layer fastest."""
@@ -152,17 +161,25 @@ class EDLoRAPipeline:
 
         controller = getattr(self, 'controller', None)
         x0_prev = torch.zeros_like(latents)
-        unet_in = torch.cat([latents] * 2) if do_cfg else latents.clone()
+        nb = 2 * batch_size if do_cfg else batch_size
+        # one prepared session: weights verified / packed and the step-invariant inputs uploaded ONCE; a step is then one
+        # graph replay + one fused kernel, with no host synchronisation inside the loop (reference loop :271-301)
+        sess = self.unet.session(nb, h, w, device, prompt_embeds, cross_attention_kwargs)
+        unet_in = sess.latents_in
+        unet_in.copy_(torch.cat([latents] * 2) if do_cfg else latents)
+        sess.t_in.fill_(float(timesteps[0]))
         for i, t in enumerate(timesteps):
-            noise_pred = self.unet(unet_in, torch.full((unet_in.shape[0],), float(t), device=device),
-                                   encoder_hidden_states=prompt_embeds,
-                                   cross_attention_kwargs=cross_attention_kwargs).sample
-            # CFG combine + scheduler.step + cat([latents]*2), one kernel (reference :285-290, :273)
-            ops.cfg_dpmpp_step(noise_pred.float().contiguous(), latents, x0_prev, unet_in.view(-1), cfg=do_cfg,
-                               guidance=float(guidance_scale), coef=self.scheduler.coefficients(i))
+            noise_pred = sess.step()
+            # CFG combine + scheduler.step + cat([latents]*2) + next timestep, one kernel (reference :285-290, :273)
+            t_next = float(timesteps[i + 1]) if i + 1 < len(timesteps) else 0.0
+            ops.cfg_dpmpp_step(noise_pred, latents, x0_prev, unet_in.view(-1), cfg=do_cfg,
+                               guidance=float(guidance_scale), coef=self.scheduler.coefficients(i), t_out=sess.t_in,
+                               t_next=t_next)
             if controller is not None and hasattr(controller, 'step_callback'):
-                dtype = latents.dtype
-                latents = controller.step_callback(latents).to(dtype)
+                new_latents = controller.step_callback(latents)
+                if new_latents is not latents:      # a controller may return edited latents (reference :293-295)
+                    latents.copy_(new_latents.to(latents.dtype))
+                    unet_in.copy_(torch.cat([latents] * 2) if do_cfg else latents)
             if callback is not None and i % callback_steps == 0:
                 callback(i, t, latents)
         if output_type == 'latent':
@@ -172,6 +189,8 @@ class EDLoRAPipeline:
                 raise ValueError("no VAE supplied: use output_type='latent'")
             image = self.vae.decode(latents / 0.18215).sample
             image = (image / 2 + 0.5).clamp(0, 1).cpu().permute(0, 2, 3, 1).float().numpy()
+            if output_type == 'pil':
+                image = numpy_to_pil(image)
         if not return_dict:
             return (image)
         return SimpleNamespace(images=image, nsfw_content_detected=None)

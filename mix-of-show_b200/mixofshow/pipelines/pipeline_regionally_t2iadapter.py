@@ -188,14 +188,19 @@ class RegionallyT2IAdapterPipeline:
                 adapter_state.append(torch.cat([v] * 2, dim=0) if do_cfg else v)
 
         x0_prev = torch.zeros_like(latents)
-        unet_in = torch.cat([latents] * 2) if do_cfg else latents.clone()
         kwargs = {'region_list': region_list, 'height': height, 'width': width}
+        # one prepared session (reference loop :548-580): region embeddings / boxes and the adapter residuals are
+        # step-invariant and uploaded once; a step is one graph replay + one fused CFG / DPM-Solver++ kernel
+        sess = self.unet.session(2 if do_cfg else 1, h, w, device, prompt_embeds, kwargs, adapter_state)
+        unet_in = sess.latents_in
+        unet_in.copy_(torch.cat([latents] * 2) if do_cfg else latents)
+        sess.t_in.fill_(float(timesteps[0]))
         for i, t in enumerate(timesteps):
-            noise_pred = self.unet(unet_in, torch.full((unet_in.shape[0],), float(t), device=device),
-                                   encoder_hidden_states=prompt_embeds, cross_attention_kwargs=kwargs,
-                                   down_block_additional_residuals=adapter_state).sample
-            ops.cfg_dpmpp_step(noise_pred.float().contiguous(), latents, x0_prev, unet_in.view(-1), cfg=do_cfg,
-                               guidance=float(guidance_scale), coef=self.scheduler.coefficients(i))
+            noise_pred = sess.step()
+            t_next = float(timesteps[i + 1]) if i + 1 < len(timesteps) else 0.0
+            ops.cfg_dpmpp_step(noise_pred, latents, x0_prev, unet_in.view(-1), cfg=do_cfg,
+                               guidance=float(guidance_scale), coef=self.scheduler.coefficients(i), t_out=sess.t_in,
+                               t_next=t_next)
             if callback is not None and i % callback_steps == 0:
                 callback(i, t, latents)
         if output_type == 'latent':
@@ -205,6 +210,9 @@ class RegionallyT2IAdapterPipeline:
                 raise ValueError("no VAE supplied: use output_type='latent'")
             image = self.vae.decode(latents / 0.18215).sample
             image = (image / 2 + 0.5).clamp(0, 1).cpu().permute(0, 2, 3, 1).float().numpy()
+            if output_type == 'pil':
+                from mixofshow.pipelines.pipeline_edlora import numpy_to_pil
+                image = numpy_to_pil(image)
         if not return_dict:
             return (image, None)
         return SimpleNamespace(images=image, nsfw_content_detected=None)

@@ -9,6 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'libmos_sm100.so')
 
 MOS_OUT_BF16, MOS_OUT_HEADS, MOS_OUT_F32 = 0, 1, 2
+MOS_DT_BF16, MOS_DT_F16 = 0, 1
 MOS_SEG_ROWS, MOS_SEG_TRANSPOSED = 0, 1
 
 c_i32, c_i64, c_f32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
@@ -28,6 +29,7 @@ class GemmArgs(ctypes.Structure):
         ('seg_ptr', c_vp * 3), ('seg_kind', c_i32 * 3), ('seg_rows_pad', c_i64 * 3),
         ('heads', c_i32), ('head_dim', c_i32), ('dpad', c_i32), ('dv_pad', c_i32),
         ('tokens_per_batch', c_i64), ('accumulate', c_i32), ('w_static', c_i32),
+        ('a_dtype', c_i32), ('w_dtype', c_i32),
     ]
 
 
@@ -57,6 +59,17 @@ def check(rc, what=''):
         if rc == -1:
             raise ValueError(f'{what}: {msg}')
         raise MosError(f'{what}: rc={rc}: {msg}')
+
+
+def act_dtype(*tensors):
+    """MOS_DT_* of the 16-bit activation tensors of one call (they must agree): bf16 (training) or fp16 (inference)."""
+    import torch
+    dts = {t.dtype for t in tensors if t is not None}
+    if dts == {torch.float16}:
+        return MOS_DT_F16
+    if dts == {torch.bfloat16}:
+        return MOS_DT_BF16
+    raise TypeError(f'16-bit activation tensors must all be bf16 or all fp16, got {sorted(str(d) for d in dts)}')
 
 
 def ptr(t):

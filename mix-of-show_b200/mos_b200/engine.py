@@ -18,7 +18,8 @@ import torch
 from . import ops
 from ._lib import MOS_SEG_ROWS, MOS_SEG_TRANSPOSED
 
-BF16 = torch.bfloat16
+BF16 = torch.bfloat16       # weights (and the training engine's activations)
+F16 = torch.float16
 # Experiment (opt-in, MOS_GEMM_PREFETCH_W=1): request the first weight tiles of every GEMM before griddepcontrol.wait.
 # Measured on B200 in round 1: no gain for the batch-2 denoise step (6.41 -> 6.55 ms together with a cheaper erf), so off.
 PREFETCH_W = os.environ.get('MOS_GEMM_PREFETCH_W') == '1'
@@ -46,10 +47,16 @@ def cross_attention_names(block_out=(320, 640, 1280, 1280), layers=2):
 class UNetEngine:
     def __init__(self, state_dict, batch, height, width, *, lora=None, lora_alpha=1.0, merge_lora=False,
                  device='cuda', block_out=(320, 640, 1280, 1280), layers=2, heads=8, cross_dim=768, n_text=77,
-                 emit_probs=False, use_graph=True):
+                 emit_probs=False, use_graph=True, act_dtype=F16):
         """state_dict: diffusers-named fp32 tensors of the UNet.  lora: {f'{module}.lora_down.weight': [r,in],
         f'{module}.lora_up.weight': [out,r]} exactly as EDLoRATrainer.delta_state_dict()['unet'] stores it
-        (trainer_edlora.py:371-378); rank <= 4.  batch includes the CFG duplication.  height/width: latent size."""
+        (trainer_edlora.py:371-378); rank <= 4.  batch includes the CFG duplication.  height/width: latent size.
+        act_dtype: 16-bit storage type of every activation.  Sampling uses fp16 against bf16 weights: with classifier-free
+        guidance the scheduler consumes u + g (c - u), so the rounding noise of the two (nearly equal) halves is amplified
+        by g while weight rounding cancels; fp16's 3 extra mantissa bits bring the CFG-7.5 latents from 2.8e-3 to 4.6e-4
+        rel-L2 (tests/numerics_emulation.py, profiles/README.md).  Training keeps bf16 (gradient range)."""
+        assert act_dtype in (F16, BF16)
+        self.ACT = act_dtype
         self.dev = torch.device(device)
         self.B, self.H, self.W = batch, height, width
         self.block_out, self.layers, self.heads = tuple(block_out), layers, heads
@@ -216,7 +223,8 @@ class UNetEngine:
         self.sd = None  # drop the fp32 master copy reference
 
     # ------------------------------------------------------------------------------------------ buffers
-    def buf(self, name, shape, dtype=BF16, zero=False):
+    def buf(self, name, shape, dtype=None, zero=False):
+        dtype = self.ACT if dtype is None else dtype
         key = (name, tuple(shape), dtype)
         if key not in self.bufs:
             self.bufs[key] = (torch.zeros if zero else torch.empty)(shape, device=self.dev, dtype=dtype)
@@ -226,7 +234,7 @@ class UNetEngine:
         B, H, W = self.B, self.H, self.W
         self.in_latents = torch.zeros(B, 4, H, W, device=self.dev)
         self.in_t = torch.zeros(B, device=self.dev)
-        self.in_ehs = torch.zeros(len(self.xattn_names), B, self.n_text, self.cross_dim, device=self.dev, dtype=BF16)
+        self.in_ehs = torch.zeros(len(self.xattn_names), B, self.n_text, self.cross_dim, device=self.dev, dtype=self.ACT)
         self.out_eps = torch.zeros(B, 4, H, W, device=self.dev)
         self.gn_partial = torch.zeros(B * 592 * 64, device=self.dev)   # tail words: grid-barrier state (zero once)
         # concat buffers of the 12 up-block resnets: [h | skip]
@@ -248,7 +256,7 @@ class UNetEngine:
             for j in range(self.layers + 1):
                 cs = skip_ch[len(skip_ch) - 1 - k]
                 ch = h_ch if j == 0 else rev[i]
-                self.cat.append(torch.empty(M, ch + cs, device=self.dev, dtype=BF16))
+                self.cat.append(torch.empty(M, ch + cs, device=self.dev, dtype=self.ACT))
                 self.cat_ch.append((ch, cs))
                 k += 1
             h_ch = rev[i]
@@ -630,11 +638,12 @@ class UNetEngine:
         self.graph.replay()
 
 
-def ehs_to_layer_major(ehs, n_layers=16):
-    """[B,16,77,768] (pipeline layout, pipeline_edlora.py:145) or [B,77,768] -> bf16 [16,B,77,768]."""
+def ehs_to_layer_major(ehs, n_layers=16, dtype=F16):
+    """[B,16,77,768] (pipeline layout, pipeline_edlora.py:145) or [B,77,768] -> 16-bit [16,B,77,768] (the engine's
+    activation type; `in_ehs.copy_()` converts if they differ)."""
     if ehs.ndim == 3:
         ehs = ehs[:, None].expand(-1, n_layers, -1, -1)
     elif ehs.shape[1] > n_layers:      # a smaller topology uses the first n_layers embeddings (idx < n_layers)
         ehs = ehs[:, :n_layers]
     assert ehs.shape[1] == n_layers, f'need {n_layers} layer-wise embeddings, got {ehs.shape[1]}'
-    return ehs.permute(1, 0, 2, 3).to(BF16).contiguous()
+    return ehs.permute(1, 0, 2, 3).to(dtype).contiguous()

@@ -8,7 +8,8 @@ import torch
 from . import ops
 from ._lib import MOS_SEG_ROWS, MOS_SEG_TRANSPOSED
 
-BF16 = torch.bfloat16
+BF16 = torch.bfloat16      # weights
+ACT = torch.float16        # activations of the (inference-only) operator path: see mos_b200/engine.py
 
 
 def _r(x, m):
@@ -96,10 +97,10 @@ def lora_linear(module, x):
     conv = module.__class__.__name__ == 'Conv2d'
     if conv:
         b, c, h, w = x.shape
-        A = x.permute(0, 2, 3, 1).reshape(b * h * w, c).to(BF16).contiguous()
+        A = x.permute(0, 2, 3, 1).reshape(b * h * w, c).to(ACT).contiguous()
     else:
-        A = x.reshape(-1, x.shape[-1]).to(BF16).contiguous()
-    out = torch.empty(A.shape[0], ent['N'], device=x.device, dtype=BF16)
+        A = x.reshape(-1, x.shape[-1]).to(ACT).contiguous()
+    out = torch.empty(A.shape[0], ent['N'], device=x.device, dtype=ACT)
     ops.gemm(A, ent['W'], out, bias=ent['bias'], **_lora_kw(ent))
     if conv:
         return out.view(b, h, w, ent['N']).permute(0, 3, 1, 2).to(x.dtype)
@@ -125,13 +126,13 @@ def attention_block(attn, hidden_states, encoder_hidden_states=None, want_probs=
     inner = Hh * d
     BH = B * Hh
     dp, dv = _r(d, 64), _r(d, 16)
-    x = hidden_states.reshape(B * N, C).to(BF16).contiguous()
-    Q = torch.zeros(BH, N, dp, device=dev, dtype=BF16)
+    x = hidden_states.reshape(B * N, C).to(ACT).contiguous()
+    Q = torch.zeros(BH, N, dp, device=dev, dtype=ACT)
     if encoder_hidden_states is None:
         M = N
         ent = _cached(attn, 'qkv', [attn.to_q, attn.to_k, attn.to_v], dev)
-        K = torch.zeros(BH, M, dp, device=dev, dtype=BF16)
-        Vt = torch.zeros(BH, dv, _r(M, 8), device=dev, dtype=BF16)
+        K = torch.zeros(BH, M, dp, device=dev, dtype=ACT)
+        Vt = torch.zeros(BH, dv, _r(M, 8), device=dev, dtype=ACT)
         ops.gemm(x, ent['W'], None, heads=dict(
             seg_ptr=[Q, K, Vt], seg_kind=[MOS_SEG_ROWS, MOS_SEG_ROWS, MOS_SEG_TRANSPOSED],
             seg_rows_pad=[N, M, _r(M, 8)], heads=Hh, head_dim=d, dpad=dp, dv_pad=dv, tokens_per_batch=N),
@@ -143,7 +144,7 @@ def attention_block(attn, hidden_states, encoder_hidden_states=None, want_probs=
                                                 head_dim=d, dpad=dp, dv_pad=dv, tokens_per_batch=N),
                  **_lora_kw(entq))
         K, Vt = _project_kv(attn, encoder_hidden_states, Hh, d, dev)
-    o = torch.empty(B, N, inner, device=dev, dtype=BF16)
+    o = torch.empty(B, N, inner, device=dev, dtype=ACT)
     probs = torch.empty(BH, N, M, device=dev, dtype=torch.float32) if want_probs else None
     if want_probs and M > 128:
         raise ValueError('attention-probability output is limited to one key tile (cross-attention, <= 128 keys)')
@@ -161,7 +162,7 @@ def attention_block(attn, hidden_states, encoder_hidden_states=None, want_probs=
         ptrs = torch.tensor([t.data_ptr() for t in outs], dtype=torch.int64, device=dev)
         ops.region_combine(o, ptrs, boxes, o, B=B, FH=fh, FW=fw, C=inner, ld=inner)
     ento = _cached(attn, 'out', [attn.to_out[0]], dev)
-    y = torch.empty(B * N, ento['N'], device=dev, dtype=BF16)
+    y = torch.empty(B * N, ento['N'], device=dev, dtype=ACT)
     ops.gemm(o.view(B * N, inner), ento['W'], y, bias=ento['bias'], **_lora_kw(ento))
     return y.view(B, N, -1).to(hidden_states.dtype), probs
 
@@ -170,9 +171,9 @@ def _project_kv(attn, ehs, Hh, d, dev):
     B, M, Cc = ehs.shape
     dp, dv = _r(d, 64), _r(d, 16)
     ent = _cached(attn, 'kv', [attn.to_k, attn.to_v], dev)
-    e = ehs.reshape(B * M, Cc).to(BF16).contiguous()
-    K = torch.zeros(B * Hh, M, dp, device=dev, dtype=BF16)
-    Vt = torch.zeros(B * Hh, dv, _r(M, 8), device=dev, dtype=BF16)
+    e = ehs.reshape(B * M, Cc).to(ACT).contiguous()
+    K = torch.zeros(B * Hh, M, dp, device=dev, dtype=ACT)
+    Vt = torch.zeros(B * Hh, dv, _r(M, 8), device=dev, dtype=ACT)
     ops.gemm(e, ent['W'], None, heads=dict(seg_ptr=[K, Vt], seg_kind=[MOS_SEG_ROWS, MOS_SEG_TRANSPOSED],
                                            seg_rows_pad=[M, _r(M, 8)], heads=Hh, head_dim=d, dpad=dp, dv_pad=dv,
                                            tokens_per_batch=M), **_lora_kw(ent))

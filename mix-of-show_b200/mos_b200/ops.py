@@ -7,15 +7,15 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import (MOS_OUT_BF16, MOS_OUT_F32, MOS_OUT_HEADS, MOS_SEG_ROWS, MOS_SEG_TRANSPOSED, GemmArgs, check,
+from ._lib import (MOS_OUT_BF16, MOS_OUT_F32, MOS_OUT_HEADS, MOS_SEG_ROWS, MOS_SEG_TRANSPOSED, GemmArgs, act_dtype, check,
                    current_stream, ptr)
 
 BN = 160
 BK = 64
 
 
-def _is_bf16(t):
-    return t is None or t.dtype == torch.bfloat16
+def _dt(*tensors):
+    return ctypes.c_int32(act_dtype(*tensors))
 
 
 def gemm(A, W, out=None, *, bias=None, bias_batch=None, rows_per_batch=0, residual=None, geglu=False,
@@ -24,12 +24,14 @@ def gemm(A, W, out=None, *, bias=None, bias_batch=None, rows_per_batch=0, residu
          w_static=False):
     """out = epilogue(A @ W^T [+ LoRA]).
 
-    A: bf16 [M, K] (row pitch lda) or, with conv=(B, H, Wd, C), the NHWC activation [B, H, Wd, C].
-    W: bf16 [N, K] (conv: [N, 9*C]).  heads: dict(seg_ptr=[...], seg_kind=[...], seg_rows_pad=[...], heads=,
+    A: bf16 / fp16 [M, K] (row pitch lda) or, with conv=(B, H, Wd, C), the NHWC activation [B, H, Wd, C]; the 16-bit
+    outputs and the residual have A's dtype.  W: bf16 (weights) or fp16 (activations, Gram products) [N, K] (conv: [N, 9*C]).  heads: dict(seg_ptr=[...], seg_kind=[...], seg_rows_pad=[...], heads=,
     head_dim=, dpad=, dv_pad=, tokens_per_batch=) selects the head-split epilogue (Q/K rows, V transposed).
     """
-    assert A.dtype == torch.bfloat16 and W.dtype == torch.bfloat16
     a = GemmArgs()
+    a.a_dtype = act_dtype(A, residual, None if out_f32 or heads is not None else out,
+                          *(heads['seg_ptr'] if heads is not None else ()))
+    a.w_dtype = act_dtype(W, lora_down)
     a.A, a.W = ptr(A), ptr(W)
     N = W.shape[0]
     if conv is not None:
@@ -51,14 +53,13 @@ def gemm(A, W, out=None, *, bias=None, bias_batch=None, rows_per_batch=0, residu
     a.bias_batch = ptr(bias_batch)
     a.rows_per_batch = rows_per_batch
     a.bias_batch_ld = bias_batch_ld
-    assert _is_bf16(residual)
     a.residual = ptr(residual)
     if residual is not None:
         a.ldr = residual.stride(0) if ldr is None else ldr
     a.geglu = 1 if geglu else 0
     a.w_static = 1 if w_static else 0      # W = model weights: prefetch ahead of the stream dependency
     if lora_down is not None:
-        assert lora_down.dtype == torch.bfloat16 and lora_down.shape[0] == 16 and lora_up.dtype == torch.float32
+        assert lora_down.shape[0] == 16 and lora_up.dtype == torch.float32
         a.lora_down, a.lora_up = ptr(lora_down), ptr(lora_up)
         a.lora_seg = lora_seg or N
     if heads is not None:
@@ -86,7 +87,8 @@ def splitk_finalize(partial, splits, M, N, out, *, bias=None, bias_batch=None, r
         ptr(partial), ctypes.c_int32(splits), ctypes.c_int64(M), ctypes.c_int64(N), ptr(bias), ptr(bias_batch),
         ctypes.c_int64(rows_per_batch), ctypes.c_int64(bias_batch_ld), ptr(residual),
         ctypes.c_int64((residual.stride(0) if ldr is None else ldr) if residual is not None else 0), ptr(out),
-        ctypes.c_int64(out.stride(0) if ldc is None else ldc), current_stream()), 'mos_splitk_finalize')
+        ctypes.c_int64(out.stride(0) if ldc is None else ldc), _dt(out, residual), current_stream()),
+        'mos_splitk_finalize')
     return out
 
 
@@ -100,7 +102,8 @@ def attention(Q, K, Vt, out, *, batch, heads, head_dim, nq, nk, scale=None, prob
     check(_lib.lib().mos_attention_fwd(
         ptr(Q), ptr(K), ptr(Vt), ptr(out), ctypes.c_int64(out.stride(-2) if ldo is None else ldo), ptr(probs),
         ctypes.c_int32(batch), ctypes.c_int32(heads), ctypes.c_int32(head_dim), ctypes.c_int32(nq),
-        ctypes.c_int32(nk), ctypes.c_int32(Vt.shape[-1]), ctypes.c_float(scale), _s()), 'mos_attention_fwd')
+        ctypes.c_int32(nk), ctypes.c_int32(Vt.shape[-1]), ctypes.c_float(scale), _dt(Q, K, Vt, out), _s()),
+        'mos_attention_fwd')
     return out
 
 
@@ -109,7 +112,7 @@ def groupnorm(x, gamma, beta, y, partial, *, B, HW, C, eps, silu, ldx=None, ldy=
         ptr(x), ctypes.c_int64(x.stride(-2) if ldx is None else ldx), ctypes.c_int32(B), ctypes.c_int32(HW),
         ctypes.c_int32(C), ptr(gamma), ptr(beta), ctypes.c_float(eps), ctypes.c_int32(1 if silu else 0),
         ptr(partial), ctypes.c_int32(partial.numel()), ptr(y),
-        ctypes.c_int64(y.stride(-2) if ldy is None else ldy), _s()), 'mos_groupnorm_fwd')
+        ctypes.c_int64(y.stride(-2) if ldy is None else ldy), _dt(x, y), _s()), 'mos_groupnorm_fwd')
     return y
 
 
@@ -117,7 +120,7 @@ def layernorm(x, gamma, beta, y, *, M, C, eps=1e-5, ldx=None, ldy=None):
     check(_lib.lib().mos_layernorm_fwd(
         ptr(x), ctypes.c_int64(x.stride(-2) if ldx is None else ldx), ctypes.c_int64(M), ctypes.c_int32(C),
         ptr(gamma), ptr(beta), ctypes.c_float(eps), ptr(y), ctypes.c_int64(y.stride(-2) if ldy is None else ldy),
-        _s()), 'mos_layernorm_fwd')
+        _dt(x, y), _s()), 'mos_layernorm_fwd')
     return y
 
 
@@ -140,13 +143,13 @@ def conv_in(x, w, bias, y, *, ldy=None):
     B, Cin, H, W = x.shape
     check(_lib.lib().mos_conv_in(ptr(x), ctypes.c_int32(B), ctypes.c_int32(Cin), ctypes.c_int32(H), ctypes.c_int32(W),
                                  ptr(w), ptr(bias), ctypes.c_int32(w.shape[1]), ptr(y),
-                                 ctypes.c_int64(w.shape[1] if ldy is None else ldy), _s()), 'mos_conv_in')
+                                 ctypes.c_int64(w.shape[1] if ldy is None else ldy), _dt(y), _s()), 'mos_conv_in')
     return y
 
 
 def conv_out(x, w, bias, y, *, B, H, W, C):
     check(_lib.lib().mos_conv_out(ptr(x), ctypes.c_int32(B), ctypes.c_int32(H), ctypes.c_int32(W), ctypes.c_int32(C),
-                                  ptr(w), ptr(bias), ctypes.c_int32(w.shape[0]), ptr(y), _s()), 'mos_conv_out')
+                                  ptr(w), ptr(bias), ctypes.c_int32(w.shape[0]), ptr(y), _dt(x), _s()), 'mos_conv_out')
     return y
 
 
@@ -166,7 +169,7 @@ def im2col_s2(x, col, *, B, H, W, C, ldx=None):
 
 def add_rows(x, r, *, M, C, ldx, ldr):
     check(_lib.lib().mos_add_rows(ptr(x), ctypes.c_int64(ldx), ptr(r), ctypes.c_int64(ldr), ctypes.c_int64(M),
-                                  ctypes.c_int32(C), _s()), 'mos_add_rows')
+                                  ctypes.c_int32(C), _dt(x, r), _s()), 'mos_add_rows')
     return x
 
 
@@ -190,7 +193,7 @@ def region_combine(glob, region_ptrs_dev, boxes, out, *, B, FH, FW, C, ld):
             arr[4 * i + k] = int(bx[k])
     check(_lib.lib().mos_region_combine(ptr(glob), ptr(region_ptrs_dev), ctypes.c_int32(n), arr, ctypes.c_int32(B),
                                         ctypes.c_int32(FH), ctypes.c_int32(FW), ctypes.c_int32(C), ctypes.c_int64(ld),
-                                        ptr(out), _s()), 'mos_region_combine')
+                                        ptr(out), _dt(glob, out), _s()), 'mos_region_combine')
     return out
 
 

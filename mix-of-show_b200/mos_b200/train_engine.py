@@ -35,7 +35,8 @@ class TrainEngine(UNetEngine):
         self.tgraph = None
         self._tgraphs = {}
         self._accumulate = False
-        super().__init__(state_dict, batch, height, width, lora=lora, lora_alpha=lora_alpha, use_graph=False, **kw)
+        super().__init__(state_dict, batch, height, width, lora=lora, lora_alpha=lora_alpha, use_graph=False,
+                         act_dtype=BF16, **kw)
         self.attn_reg_weight = attn_reg_weight
         self.reg_full_identity = reg_full_identity
         self.wb = {}

@@ -33,8 +33,12 @@ def test_argument_validation_without_gpu():
     a = _lib.GemmArgs()
     rc = lib.mos_gemm_bf16(ctypes.byref(a), None)
     assert rc == -1 and b'NULL' in lib.mos_last_error()
-    rc = lib.mos_attention_fwd(None, None, None, None, ctypes.c_int64(0), None, 1, 8, 40, 1, 1, 8, ctypes.c_float(1), None)
+    rc = lib.mos_attention_fwd(None, None, None, None, ctypes.c_int64(0), None, 1, 8, 40, 1, 1, 8, ctypes.c_float(1), 0, None)
     assert rc == -1
+    # the activation dtype is validated too (MOS_DT_BF16 = 0 / MOS_DT_F16 = 1)
+    rc = lib.mos_layernorm_fwd(ctypes.c_void_p(16), ctypes.c_int64(8), ctypes.c_int64(1), 8, ctypes.c_void_p(16), ctypes.c_void_p(16),
+                               ctypes.c_float(1e-5), ctypes.c_void_p(16), ctypes.c_int64(8), 7, None)
+    assert rc == -1 and b'act_dtype' in lib.mos_last_error()
 
 
 def test_sass_is_blackwell_native():

@@ -202,3 +202,45 @@ def test_text_encoder_fusion_two_concepts(cuda):
         # evaluated on the oracle's fp32 features) is bounded relative to the starting point instead
         assert r_new < 0.1 * r0
         assert rel(Wn, W_or) < 2e-2
+
+
+def test_merge_kv_in_cross_attention_vs_reference_construction(cuda):
+    """Config 3's cross-K/V stage: `merge_kv_in_cross_attention` (Gram form, one solve per layer) against the reference's
+    own construction (gradient_fusion.py:394-455): per layer X = cat_c(features_c), V = cat_c(features_c @ merged_c^T),
+    Wnew = update_quasi_newton(X, V, W0, iters) — run through the oracle port of `update_quasi_newton`, which is pinned
+    to the reference's output by the golden test above.  3 concepts x 6 text positions (18 rows << 768 inputs:
+    under-determined, exactly the reference's regime), two layers (K and V of one cross-attention, 320 x 768).
+    Tolerances: fused weight rel-Frobenius <= 1e-4, the UPDATE (Wnew - W0) rel-Frobenius <= 5e-2 (the trajectory of a
+    quasi-Newton iteration in Gram form rounds differently), final residual within 2 % of the reference's."""
+    from gradient_fusion import merge_kv_in_cross_attention
+    from oracle import edlora_ref as er
+    g = torch.Generator().manual_seed(21)
+    n_c, n_pos, C, D, iters = 3, 6, 320, 768, 200
+    names = [(0, 'down_blocks.0.attentions.0.transformer_blocks.0.attn2.to_k.weight'),
+             (0, 'down_blocks.0.attentions.0.transformer_blocks.0.attn2.to_v.weight'),
+             (1, 'down_blocks.0.attentions.1.transformer_blocks.0.attn2.to_k.weight')]
+    sd = {n: torch.randn(C, D, generator=g) * D ** -0.5 for _, n in names}
+    feats = [{l: torch.randn(n_pos, D, generator=g) for l in (0, 1)} for _ in range(n_c)]
+    tuned, alphas = [], [1.0, 0.7, 1.3]
+    for c in range(n_c):
+        t = {}
+        for _, n in names:
+            dn = n.replace('to_k.weight', 'to_k.lora_down.weight').replace('to_v.weight', 'to_v.lora_down.weight')
+            t[dn] = torch.randn(4, D, generator=g) * D ** -0.5
+            t[dn.replace('lora_down', 'lora_up')] = torch.randn(C, 4, generator=g) * 0.1
+        tuned.append(t)
+    new_w = merge_kv_in_cross_attention(sd, names, feats, tuned, alphas, iters, device='cuda')
+    for layer_idx, n in names:
+        dn = n.replace('to_k.weight', 'to_k.lora_down.weight').replace('to_v.weight', 'to_v.lora_down.weight')
+        X = torch.cat([feats[c][layer_idx] for c in range(n_c)], 0)
+        V = torch.cat([(((sd[n] + alphas[c] * tuned[c][dn.replace('lora_down', 'lora_up')] @ tuned[c][dn])
+                         @ feats[c][layer_idx].T).T) for c in range(n_c)], 0)          # reference :403-429
+        Wref = er.update_quasi_newton(X, V, sd[n].clone(), iters)
+        Wn = new_w[n]
+        r0 = (X @ sd[n].t() - V).norm().item()
+        rr, rn = (X @ Wref.t() - V).norm().item(), (X @ Wn.t() - V).norm().item()
+        e_w, e_d = rel(Wn, Wref), rel(Wn - sd[n], Wref - sd[n])
+        print(f'cross-KV fusion {n.split(".")[-2]}[{layer_idx}]: W rel-Frob {e_w:.2e}, update rel-Frob {e_d:.2e}; residual '
+              f'ours {rn:.3e} reference {rr:.3e} start {r0:.3e}')
+        assert e_w < 1e-4 and e_d < 5e-2
+        assert rn <= rr * 1.02 + 1e-6 * r0

@@ -168,3 +168,49 @@ def test_gemm_bad_args(cuda):
     out = torch.empty((128, 100), device=cuda, dtype=torch.bfloat16)
     with pytest.raises(ValueError):
         ops.gemm(A, W, out)
+
+
+# ---------------------------------------------------------------------------------------------- fp16 activations
+# Sampling stores activations as fp16 and keeps the weights bf16 (mos_b200/engine.py): tcgen05 kind::f16 takes the two
+# operand formats independently (instruction-descriptor a_format / b_format).  Tolerance: operands are exact in both paths,
+# fp32 accumulation, final fp16 rounding (eps 4.9e-4): rel-L2 <= 6e-4.
+def test_gemm_f16_activations_bf16_weights(cuda):
+    from mos_b200 import ops
+    M, N, K = 2 * 1024, 640, 640
+    g = torch.Generator().manual_seed(5)
+    A = torch.randn(M, K, generator=g).to(cuda).half()
+    W = mk((N, K), cuda, K ** -0.5, seed=2)
+    bias = torch.randn(N, device=cuda)
+    res = torch.randn(M, N, generator=g).to(cuda).half()
+    down16 = torch.zeros(16, K, device=cuda, dtype=torch.bfloat16)
+    down16[:4] = mk((4, K), cuda, K ** -0.5, seed=11)
+    up = (torch.randn(N, 4, device=cuda) * 0.5).contiguous()
+    out = torch.empty((M, N), device=cuda, dtype=torch.float16)
+    ops.gemm(A, W, out, bias=bias, residual=res, lora_down=down16, lora_up=up, lora_seg=N)
+    torch.cuda.synchronize()
+    ref = A.float() @ W.float().t() + bias + res.float() + (A.float() @ down16[:4].float().t()) @ up.t()
+    e = rel_l2(out, ref)
+    print(f'fp16 x bf16 gemm rel-L2 {e:.2e}')
+    assert e < 6e-4
+    # mixing the dtypes of the activation tensors of one call is a caller bug
+    with pytest.raises(TypeError):
+        ops.gemm(A, W, out.to(torch.bfloat16))
+
+
+def test_conv3x3_and_splitk_f16(cuda):
+    from mos_b200 import ops
+    B, H, Wd, C, N = 2, 16, 16, 1280, 1280
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(B, H, Wd, C, generator=g).to(cuda).half()
+    w = (torch.randn(N, C, 3, 3, generator=g) * (9 * C) ** -0.5).to(cuda).to(torch.bfloat16)
+    Wp = w.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous()
+    bias = torch.randn(N, device=cuda)
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1)
+    out = torch.empty(B * H * Wd, N, device=cuda, dtype=torch.float16)
+    ops.gemm(x, Wp, out, bias=bias, conv=(B, H, Wd, C))
+    assert rel_l2(out, ref.reshape(-1, N)) < 6e-4
+    partial = torch.empty(4 * B * H * Wd * N, device=cuda)
+    ops.gemm(x, Wp, None, conv=(B, H, Wd, C), splits=4, partial=partial)
+    out2 = torch.empty_like(out)
+    ops.splitk_finalize(partial, 4, B * H * Wd, N, out2, bias=bias)
+    assert rel_l2(out2, ref.reshape(-1, N)) < 6e-4

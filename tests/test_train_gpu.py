@@ -80,8 +80,8 @@ def test_train_step_vs_oracle_autograd(cuda, reg_weight, full):
     fg, fr = torch.cat(flat_g), torch.cat(flat_r)
     cos = torch.nn.functional.cosine_similarity(fg, fr, dim=0).item()
     print(f'    flat LoRA gradient: rel-L2 {rel_l2(fg, fr):.3e}, cosine {cos:.5f}; worst tensor {worst[1]} {worst[0]:.3e}')
-    assert cos > 0.995 and rel_l2(fg, fr) < 8e-2
-    assert worst[0] < 0.25
+    assert cos > 0.9995 and rel_l2(fg, fr) < 2e-2     # measured 8e-3 (bf16 activations, fp32 accumulation)
+    assert worst[0] < 5e-2
 
 
 def test_optimizer_step_changes_forward(cuda):
@@ -161,7 +161,7 @@ def test_train_step_full_sd15_topology(cuda):
     cos = torch.nn.functional.cosine_similarity(fg, fr, dim=0).item()
     print(f'    flat LoRA gradient ({fg.numel()} params): rel-L2 {rel_l2(fg, fr):.3e}, cosine {cos:.5f}')
     assert fg.numel() == 797184                      # UNet `where: Attention` rank-4 parameter count
-    assert cos > 0.99 and rel_l2(fg, fr) < 0.12
+    assert cos > 0.9995 and rel_l2(fg, fr) < 2e-2     # measured 8e-3 on the full topology
     # timing of the step (forward + loss + backward in one CUDA graph, + AdamW + LoRA re-pack)
     import time
     for _ in range(2):

@@ -1,10 +1,11 @@
 """End-to-end parity of the B200 UNet engine against the fp32 CPU oracle (oracle/unet.py + oracle/inject.py).
 
-Metric: rel-L2 = ||a-b||_2 / ||b||_2.  Tolerances: the engine computes in bf16 with fp32 accumulation, the oracle in
-fp32: eps (UNet output) rel-L2 <= 2e-2; post-scheduler latents of BASELINE config 1 (one DPM-Solver++ step from a
-50-step schedule, guidance <= 1) rel-L2 <= 1e-3 — the target BASELINE.json states.  With classifier-free
-guidance 7.5 the scheduler input is u + 7.5 (c - u): the bf16 rounding noise of the two halves is amplified ~10x
-relative to the (small) conditional difference, so that variant is gated at 5e-3 and its value is printed.
+Metric: rel-L2 = ||a-b||_2 / ||b||_2.  The engine multiplies bf16 weights with fp16 activations (fp32 accumulation,
+fp32 statistics), the oracle is fp32.  Tolerances: eps (UNet output) rel-L2 <= 1e-2 (dominated by the bf16 weights:
+tests/numerics_emulation.py predicts 5.0e-3); post-scheduler latents (one DPM-Solver++ step from a 50-step schedule,
+SURVEY.md §8d) rel-L2 <= 1e-3 — the target BASELINE.json states — BOTH for BASELINE config 1 (guidance <= 1) and for
+classifier-free guidance 7.5, which is what bench.py times (the scheduler input u + 7.5 (c - u) amplifies the activation
+rounding noise of the two halves ~10x: 2.8e-3 with bf16 activations in round 1, 4.6e-4 predicted with fp16).
 """
 import pytest
 import torch
@@ -57,7 +58,7 @@ def test_unet_tiny(cuda, lora_mode):
     torch.cuda.synchronize()
     assert torch.equal(out2, out), 'CUDA-graph replay must be bitwise reproducible'
     print(f'tiny unet [{lora_mode}] eps rel-L2 = {e1:.3e}, launches = {eng.launches}')
-    assert e1 < 2e-2
+    assert e1 < 1e-2
 
 
 def test_unet_sd15_step(cuda):
@@ -97,6 +98,6 @@ def test_unet_sd15_step(cuda):
     e_lat1 = rel_l2(lat_ng, ref1)
     print(f'sd1.5 unet eps rel-L2 = {e_eps:.3e}; post-scheduler latents rel-L2: guidance 1 = {e_lat1:.3e}, '
           f'guidance 7.5 = {e_lat:.3e}; launches = {eng.launches}')
-    assert e_eps < 2e-2
+    assert e_eps < 1e-2
     assert e_lat1 < 1e-3
-    assert e_lat < 5e-3
+    assert e_lat < 1e-3
