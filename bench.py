@@ -166,26 +166,14 @@ def build_cpu_reference(sd, lora, cfg):
 
 
 def pick_cpu_threads():
-    """Thread count for the CPU arm: the fastest of {8, 16, 32, 64, all} on a representative 3x3 convolution (using all
-    128 hyper-threads of the GPU box is 18x SLOWER than 8 threads of a small VM for this fp32 workload; the baseline
-    should be the CPU at its best)."""
+    """Thread count of the CPU arm: PINNED to min(32, host CPUs) so that both arms of every run (and every round) use the
+    same count.  (Round 1 picked the fastest of {8..128} per run; the pick flipped between 32 / 64 / 128 threads and the
+    baseline moved 0.13-0.28 steps/s with it.  32 was the most frequent winner on the 128-thread GPU host: fp32 convs of
+    this size stop scaling there and oversubscription costs an order of magnitude.)"""
     import torch
-    import torch.nn.functional as F
-    n = os.cpu_count() or 1
-    cands = sorted({c for c in (8, 16, 32, 64, n) if c <= n})
-    x, w = torch.randn(2, 320, 64, 64), torch.randn(320, 320, 3, 3)
-    best, best_t = cands[0], float('inf')
-    for c in cands:
-        torch.set_num_threads(c)
-        F.conv2d(x, w, padding=1)
-        t0 = time.perf_counter()
-        for _ in range(2):
-            F.conv2d(x, w, padding=1)
-        dt = time.perf_counter() - t0
-        if dt < best_t:
-            best, best_t = c, dt
-    torch.set_num_threads(best)
-    return best
+    n = min(32, os.cpu_count() or 1)
+    torch.set_num_threads(n)
+    return n
 
 
 def cpu_reference_steps(unet, lora, lat, ehs, steps, warmup, budget_s):
@@ -232,6 +220,12 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--tiny', action='store_true', help='debug: 2-level UNet')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--act-dtype', default='fp16', choices=['fp16', 'bf16'],
+                    help='operand type (weights and activations) of the sampling engine.  fp16 (default) is the reference\'s '
+                         'own sampling precision and meets the 1e-3 latent tolerance at guidance 7.5; bf16 runs at the same '
+                         'speed but measures 2.8e-3 (tests/test_unet_gpu.py, profiles/README.md)')
+    ap.add_argument('--no-train', action='store_true', help='skip the data-parallel training leg (extra.train)')
+    ap.add_argument('--train-batch', type=int, default=8, help='per-GPU batch of the training leg (BASELINE config 5: 8)')
     ap.add_argument('--images', type=int, default=1,
                     help='images denoised together per step (default 1 = the BASELINE workload; > 1 is a separate, '
                          'labelled throughput mode: value counts image-steps)')
@@ -277,6 +271,7 @@ def main():
     # container packs: `value` replays its prepared session directly (inputs resident in HBM), `e2e` is the user's call.
     pipe = build_pipeline(sd, lora, cfg, dev)
     unet = pipe.unet
+    unet.act_dtype = torch.float16 if args.act_dtype == 'fp16' else torch.bfloat16
     sess = unet.session(B, H, W, dev, ehs.to(dev))
     eng = sess.eng
     nx = len(eng.xattn_names)
@@ -364,6 +359,13 @@ def main():
     if rank == 0:
         roof = gemm_roofline(eng, ops, torch)
 
+    # ---------------- data-parallel ED-LoRA training leg (BASELINE configs 2 / 5): the path that actually shards
+    train = None
+    if not args.no_train:
+        del pipe, unet, sess, eng
+        torch.cuda.empty_cache()
+        train = train_leg(args, rank, world, dev, sd, lora, cfg)
+
     if world > 1:
         tt = torch.tensor([ms, e2e_ms], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -379,8 +381,13 @@ def main():
     out = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'bf16', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'parallelism': f'replicas x{world} (independent images per GPU, no data-path '
+        'dtype': args.act_dtype, 'data': 'synthetic',
+        'config': {'workload': WORKLOAD,
+                   'precision': ('fp16 tensor-core operands (weights + activations), fp32 accumulation / statistics / softmax: '
+                                 'the reference\'s own sampling precision (README.md:146 torch_dtype=float16); same tcgen05 '
+                                 'kind::f16 rate as bf16.  bf16 operands (--act-dtype bf16) run at the same speed but miss the '
+                                 '1e-3 latent tolerance at guidance 7.5 (2.8e-3)') if args.act_dtype == 'fp16' else
+                                'bf16 operands, fp32 accumulation', 'parallelism': f'replicas x{world} (independent images per GPU, no data-path '
                    'collective; SURVEY.md 8e)', 'l2': 'inputs larger than L2: 1.72 GB of bf16 weights streamed per '
                    'step vs 126 MB L2, no explicit flush', 'cuda_graph': bool(used_graph), 'images_per_step': n_img},
         'clocks': clocks,
@@ -392,6 +399,8 @@ def main():
         'gpu_launches': launches,
         'step_tflops': FLOPS_PER_STEP * value / world / 1e12 if not args.tiny else None,   # per GPU, all images
     }
+    if train is not None:
+        out['extra'] = {'train': train}
     if roof is not None:
         frac = roof['achieved'] / peaks['tflops']
         out['roofline'] = {'bound': 'tensor', 'achieved': roof['achieved'], 'peak': peaks['tflops'], 'unit': 'TFLOP/s',
@@ -414,6 +423,87 @@ def main():
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def train_leg(args, rank, world, dev, sd, lora, cfg):
+    """BASELINE config 5 (config 2 at N = 1): data-parallel ED-LoRA training of the UNet-LoRA group.  Every rank runs the
+    captured forward + masked-MSE + attention-regulariser + backward graph on ITS shard of the global batch (per-GPU batch
+    fixed: weak scaling), then the step's ONE collective - an NCCL all-reduce (sum) of the flat fp32 gradient buffer
+    [797 184 LoRA gradients | loss | Norm_mean] - then the fused flat AdamW + LoRA re-pack (train_edlora.py:105-158;
+    SURVEY.md 8e).  Timed with CUDA events, max over ranks; the all-reduce alone is timed separately."""
+    import torch
+    import torch.distributed as dist
+    from mos_b200 import dp
+    from mos_b200.engine import ehs_to_layer_major
+    from mos_b200.train_engine import TrainEngine
+    kw = dict(block_out=cfg['block_out_channels'], layers=cfg['layers_per_block']) if cfg else {}
+    B = args.train_batch
+    eng = TrainEngine(sd, B, 64, 64, lora=lora, attn_reg_weight=0.01, device=dev, **kw)
+    g = torch.Generator().manual_seed(100 + rank)              # per-rank data (train_edlora.py:48,70)
+    x0 = torch.randn(B, 4, 64, 64, generator=g).to(dev)
+    noise = torch.randn(B, 4, 64, 64, generator=g).to(dev)
+    t = torch.randint(0, 1000, (B,), generator=g).to(dev)
+    nx = len(eng.xattn_names)
+    ehs = ehs_to_layer_major(torch.randn(B, 16, 77, 768, generator=g)[:, :nx].to(dev), nx, torch.bfloat16)
+    masks = torch.zeros(B, 1, 64, 64)
+    masks[:, :, 8:56, 16:48] = 1.0                               # SURVEY.md 8d config 2
+    masks = masks.to(dev)
+    pos = [[2, 3]] * B
+
+    def step():
+        out = eng.forward_backward(x0, noise, t, ehs, masks, token_pos=pos)
+        scale = dp.allreduce_flat_device(eng.state, out[0:1])
+        dp.optimizer_step(eng.state, scale)
+        eng.refresh_lora()
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    steps, warm = min(args.steps, 10), 3
+    for _ in range(warm):
+        step()
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    sync()
+    ms = e0.elapsed_time(e1) / steps
+    # the collective alone (same buffer, back to back)
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    scratch = eng.state.grads.clone()
+    reps = 20
+    a0.record()
+    for _ in range(reps):
+        if world > 1:
+            dist.all_reduce(scratch, op=dist.ReduceOp.SUM)
+    a1.record()
+    sync()
+    ar_us = a0.elapsed_time(a1) / reps * 1e3 if world > 1 else 0.0
+    # replicas must hold bit-identical parameters after the steps (same init, same reduced gradient on every rank)
+    identical = True
+    tt = torch.tensor([ms, ar_us], device=dev)
+    if world > 1:
+        hi, lo = eng.state.params.clone(), eng.state.params.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        identical = bool(torch.equal(hi, lo))
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms, ar_us = tt[0].item(), tt[1].item()
+    loss = eng.state.grads[eng.state.n].item() / world
+    per_sample_tflop = 1.61 if not cfg else None             # SURVEY.md 8d: UNet fwd + dX-only bwd + LoRA dW
+    return {'metric': 'ED-LoRA train samples/sec (SD1.5 UNet @512x512, bf16, UNet-LoRA group; forward + masked MSE + '
+                      'attention regulariser + backward + all-reduce + AdamW)',
+            'value': B * world / ms * 1e3, 'unit': 'samples/s', 'n_gpus': world, 'ms_per_step': ms, 'steps': steps,
+            'warmup': warm, 'batch_per_gpu': B, 'global_batch': B * world, 'scaling': 'weak',
+            'collective': 'ONE NCCL all-reduce (sum, fp32) of the flat gradient buffer per optimiser step',
+            'allreduce_bytes_per_step': (eng.state.n + 2) * 4, 'allreduce_us': ar_us, 'lora_params': eng.state.n,
+            'params_bit_identical_across_ranks': identical, 'mean_loss': loss,
+            'step_tflops_per_gpu': (per_sample_tflop * B / (ms * 1e-3)) if per_sample_tflop else None,
+            'data': 'synthetic (per-rank seeds), latents in, VAE / CLIP upstream not included'}
 
 
 def gemm_roofline(eng, ops, torch):

@@ -4,9 +4,10 @@
  * last failure on the calling thread is available from mos_last_error(). All pointers are raw device pointers
  * owned by the caller (PyTorch allocates everything); the library never allocates per call, never retains a
  * pointer after return and never synchronises: work is enqueued on the cudaStream_t passed as `stream`.
- * Activations are 16-bit, NHWC / token-major: bf16 (training) or fp16 (inference; `act_dtype` / MOS_DT_*, the three extra
- * mantissa bits keep the classifier-free-guidance difference accurate); weights are pre-packed bf16 K-major
- * (see DESIGN.md "data layout"); accumulation, statistics and softmax are fp32.
+ * Activations and packed weights are 16-bit, NHWC / token-major resp. K-major: bf16 (training) or fp16 (sampling: the
+ * reference's own sampling precision; its three extra mantissa bits keep the classifier-free-guidance difference accurate,
+ * DESIGN.md "numerics"); `act_dtype` / MOS_DT_* selects the type.  tcgen05 kind::f16 takes ONE operand format per MMA, so
+ * the operands of a GEMM share the type.  Accumulation, statistics and softmax are fp32.
  *
  * Each entry point cites the reference call site it replaces (paths relative to TencentARC/Mix-of-Show).
  */
@@ -74,7 +75,7 @@ typedef struct mos_gemm_args {
                            * are requested before griddepcontrol.wait, overlapping the predecessor's tail.  0 = W may be
                            * an activation (Gram products): every load waits for the dependency. */
   int32_t a_dtype;        /* MOS_DT_*: type of A, of the 16-bit outputs (rows, head-split) and of `residual` */
-  int32_t w_dtype;        /* MOS_DT_*: type of W and lora_down (model weights are bf16; Gram products pass activations) */
+  int32_t w_dtype;        /* MOS_DT_*: type of W and lora_down; must equal a_dtype (one operand format per tcgen05 MMA) */
 } mos_gemm_args;
 
 int mos_gemm_bf16(const mos_gemm_args* args, void* stream);
@@ -154,7 +155,16 @@ int mos_quick_gelu(void* x, int64_t ld, int64_t M, int32_t C, void* stream);
 /* Causal self-attention over one key tile (n <= 128): layouts as mos_attention_fwd; head_dim 80 only (CLIP's 64-dim heads
  * run zero-padded to 80 with scale = 64^-0.5). */
 int mos_attention_fwd_causal(const void* Q, const void* K, const void* Vt, void* out, int64_t ldo, int32_t batch,
-                             int32_t heads, int32_t head_dim, int32_t n, int32_t n8, float scale, void* stream);
+                             int32_t heads, int32_t head_dim, int32_t n, int32_t n8, float scale, float* lse2,
+                             void* stream);   /* lse2 (optional) [batch*heads, n]: saved for mos_attention_bwd (causal) */
+/* Training pieces of the CLIP text encoder (trainer_edlora.py:220-234 reached through loss.backward(), train_edlora.py:120):
+ * out-of-place quick-GELU (the pre-activation is kept) and its backward; the gradient of the new-concept rows of the
+ * token-embedding table: out[r, :C] (+)= sum_{m: ids[m] == rows[r]} dx[m, :C]  (fp32 [n_rows, C], fixed summation order). */
+int mos_quick_gelu_fwd(const void* x, int64_t ldx, int64_t M, int32_t C, void* y, int64_t ldy, void* stream);
+int mos_quick_gelu_bwd(const void* x, int64_t ldx, const void* dy, int64_t lddy, int64_t M, int32_t C, void* dx,
+                       int64_t lddx, void* stream);
+int mos_clip_embed_bwd(const int32_t* ids, const void* dx, int64_t ld, int64_t M, int32_t C, const int32_t* rows,
+                       int32_t n_rows, int32_t accumulate, float* out, void* stream);
 
 /* One fused kernel for mixofshow/pipelines/pipeline_edlora.py:273-290: classifier-free-guidance combine,
  * DPM-Solver++(2M) data-prediction update and re-duplication of the latents for the next UNet call.
@@ -225,7 +235,7 @@ int mos_attention_bwd(const void* Q, const void* K, const void* V, const void* d
                       const void* dOt, const float* lse2, const float* delta, const float* gcols, const int32_t* pos,
                       void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int32_t batch,
                       int32_t heads, int32_t head_dim, int32_t nq, int32_t nk, int32_t nq8, int32_t nk8, float scale,
-                      void* stream);
+                      int32_t causal /* 1: keys <= query only (nq == nk; CLIP text encoder) */, void* stream);
 /* dst[bh, j, r] = src[bh, r, j]: rows [BH, R, DP] -> transposed [BH, DV, R8] (dst zero-initialised by the caller). */
 int mos_heads_transpose(const void* src, int32_t BH, int32_t R, int32_t DP, int32_t DV, int32_t R8, void* dst,
                         void* stream);

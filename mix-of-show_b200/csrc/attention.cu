@@ -611,14 +611,14 @@ extern "C" int mos_attention_fwd_train(const void* Q, const void* K, const void*
 // at mixofshow/pipelines/pipeline_edlora.py:133-145 and trainer_edlora.py:220-234.
 extern "C" int mos_attention_fwd_causal(const void* Q, const void* K, const void* Vt, void* out, int64_t ldo, int32_t batch,
                                         int32_t heads, int32_t head_dim, int32_t n, int32_t n8, float scale,
-                                        void* stream_) {
+                                        float* lse2, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MOS_CHECK_ARG(Q && K && Vt && out, "mos_attention_fwd_causal: NULL pointer");
   MOS_CHECK_ARG(batch > 0 && heads > 0 && n > 0 && n <= 128, "mos_attention_fwd_causal: needs 0 < n <= 128 (one key tile)");
   MOS_CHECK_ARG(n8 >= n && n8 % 8 == 0, "mos_attention_fwd_causal: n8 must be >= n and a multiple of 8");
   MOS_CHECK_ARG(ldo >= (int64_t)heads * head_dim && ldo % 8 == 0, "mos_attention_fwd_causal: bad ldo");
   if (head_dim != 80) return set_err(MOS_EUNSUPPORTED, "mos_attention_fwd_causal: head_dim %d (only 80 is built)", head_dim);
-  return launch_attn<80, true, true>(Q, K, Vt, out, ldo, nullptr, batch * heads, heads, n, n, n8, scale, stream);
+  return launch_attn<80, true, true>(Q, K, Vt, out, ldo, nullptr, batch * heads, heads, n, n, n8, scale, stream, lse2);
 }
 
 extern "C" int mos_debug_set_attn_timeline(void* buf) {

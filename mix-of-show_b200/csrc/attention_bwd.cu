@@ -68,6 +68,7 @@ struct BwdDev {
   const float* delta;   // [BH, nq]
   const float* gcols;   // optional [B, nq, 2]: gradient on the probabilities at key columns pos[b][0..1]
   const int* pos;       // optional [B, 2]
+  int causal;           // self-attention with keys <= query only (CLIP text encoder)
   __nv_bfloat16* dq;    // token-major outputs
   long long lddq;
   __nv_bfloat16* dk;
@@ -242,7 +243,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           float pr = ex2_approx_b(fmaf(__uint_as_float(sv[i]), p.scale_log2, -lse));
-          pr = (c * 32 + i < kv_valid) ? pr : 0.f;
+          pr = (c * 32 + i < kv_valid && (!p.causal || k0 + i <= q_idx)) ? pr : 0.f;
           float dp = __uint_as_float(dv[i]);
           if (p.gcols != nullptr) dp += (k0 + i == pos0) ? g0 : ((k0 + i == pos1) ? g1 : 0.f);
           ds[i] = pr * (dp - dl) * p.scale;
@@ -455,7 +456,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         for (int k = 0; k < 32; ++k) {
           const int col = c * 32 + k;
           float e = ex2_approx_b(fmaf(__uint_as_float(sv[k]), p.scale_log2, -sL[buf][col]));
-          e = row_ok ? e : 0.f;
+          e = (row_ok && (!p.causal || key <= i * BT + col)) ? e : 0.f;
           float dp = __uint_as_float(dv[k]);
           if (gsel != 0) dp += gp[col];
           pr[k] = e;
@@ -559,7 +560,7 @@ extern "C" int mos_attention_bwd(const void* Q, const void* K, const void* V, co
                                  const void* Kt, const void* dOt, const float* lse2, const float* delta,
                                  const float* gcols, const int32_t* pos, void* dq, int64_t lddq, void* dk, int64_t lddk,
                                  void* dv, int64_t lddv, int32_t batch, int32_t heads, int32_t head_dim, int32_t nq,
-                                 int32_t nk, int32_t nq8, int32_t nk8, float scale, void* stream_) {
+                                 int32_t nk, int32_t nq8, int32_t nk8, float scale, int32_t causal, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MOS_CHECK_ARG(Q && K && V && dO && Qt && Kt && dOt && lse2 && delta && dq && dk && dv, "mos_attention_bwd: NULL pointer");
   MOS_CHECK_ARG(batch > 0 && heads > 0 && nq > 0 && nk > 0 && nq8 >= nq && nk8 >= nk && nq8 % 8 == 0 && nk8 % 8 == 0,
@@ -575,6 +576,8 @@ extern "C" int mos_attention_bwd(const void* Q, const void* K, const void* V, co
   p.delta = delta;
   p.gcols = gcols;
   p.pos = reinterpret_cast<const int*>(pos);
+  p.causal = causal ? 1 : 0;
+  MOS_CHECK_ARG(!causal || nq == nk, "mos_attention_bwd: causal needs nq == nk");
   p.dq = reinterpret_cast<__nv_bfloat16*>(dq);
   p.lddq = lddq;
   p.dk = reinterpret_cast<__nv_bfloat16*>(dk);

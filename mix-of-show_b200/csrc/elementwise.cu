@@ -272,6 +272,67 @@ __global__ void quick_gelu_kernel(__nv_bfloat16* __restrict__ x, long long ld, l
   *reinterpret_cast<uint4*>(x + m * ld + o * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
 }
 
+// out-of-place quick-GELU (training forward keeps the pre-activation) and its backward:
+//   y = x s, s = sigmoid(1.702 x);   dx = dy (s + 1.702 x s (1 - s))
+__global__ void quick_gelu_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, long long M, int C,
+                                      __nv_bfloat16* __restrict__ y, long long ldy) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int oct = C / 8;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * oct) return;
+  const int o = (int)(idx % oct);
+  const long long m = idx / oct;
+  uint4 a = __ldg(reinterpret_cast<const uint4*>(x + m * ldx + o * 8));
+  uint32_t aw[4] = {a.x, a.y, a.z, a.w}, ow[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = unpack_bf16x2(aw[i]);
+    ow[i] = pack_bf16x2(f.x / (1.0f + __expf(-1.702f * f.x)), f.y / (1.0f + __expf(-1.702f * f.y)));
+  }
+  *reinterpret_cast<uint4*>(y + m * ldy + o * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+}
+__device__ __forceinline__ float quick_gelu_grad(float x) {
+  const float s = 1.0f / (1.0f + __expf(-1.702f * x));
+  return s + 1.702f * x * s * (1.0f - s);
+}
+__global__ void quick_gelu_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ dy,
+                                      long long lddy, long long M, int C, __nv_bfloat16* __restrict__ dx, long long lddx) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int oct = C / 8;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * oct) return;
+  const int o = (int)(idx % oct);
+  const long long m = idx / oct;
+  uint4 a = __ldg(reinterpret_cast<const uint4*>(x + m * ldx + o * 8));
+  uint4 g = __ldg(reinterpret_cast<const uint4*>(dy + m * lddy + o * 8));
+  uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w}, ow[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = unpack_bf16x2(aw[i]), d = unpack_bf16x2(gw[i]);
+    ow[i] = pack_bf16x2(d.x * quick_gelu_grad(f.x), d.y * quick_gelu_grad(f.y));
+  }
+  *reinterpret_cast<uint4*>(dx + m * lddx + o * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+}
+
+// gradient of the token-embedding rows `rows[r]` (the new-concept tokens, trainer_edlora.py:86-88: only those rows keep
+// their update, train_edlora.py:133-136): out[r, c] (+)= sum over the positions m with ids[m] == rows[r] of dx[m, c].
+// One block per row, fixed summation order (ascending m) -> bitwise reproducible.
+__global__ void clip_embed_bwd_kernel(const int* __restrict__ ids, const __nv_bfloat16* __restrict__ dx, long long ld,
+                                      long long M, int C, const int* __restrict__ rows, int accumulate,
+                                      float* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int tok = __ldg(rows + blockIdx.x);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = accumulate ? out[(long long)blockIdx.x * C + c] : 0.f;
+    for (long long m = 0; m < M; ++m)
+      if (__ldg(ids + m) == tok) acc += __bfloat162float(dx[m * ld + c]);
+    out[(long long)blockIdx.x * C + c] = acc;
+  }
+}
+
 // ---------------------------------------------------------------------------------- CFG + DPM-Solver++(2M)
 // eps = cfg ? u + g (c - u) : e ;  x0 = (x - sigma_s eps) / alpha_s ;  x <- c_x x + c_m0 x0 + c_m1 x0_prev ;
 // x0_prev <- x0 ; unet_in (both CFG halves) <- x
@@ -448,6 +509,35 @@ extern "C" int mos_quick_gelu(void* x, int64_t ld, int64_t M, int32_t C, void* s
   MOS_CHECK_ARG(x && M > 0 && C % 8 == 0 && ld % 8 == 0 && ld >= C, "mos_quick_gelu: bad arguments");
   MOS_CHECK_CUDA(launch_pdl(quick_gelu_kernel, dim3(nblk(M * (C / 8), 256)), dim3(256), 0, STREAM(stream),
                             reinterpret_cast<__nv_bfloat16*>(x), (long long)ld, (long long)M, (int)C));
+  return MOS_OK;
+}
+
+extern "C" int mos_quick_gelu_fwd(const void* x, int64_t ldx, int64_t M, int32_t C, void* y, int64_t ldy, void* stream) {
+  MOS_CHECK_ARG(x && y && M > 0 && C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && ldx >= C && ldy >= C,
+                "mos_quick_gelu_fwd: bad arguments");
+  MOS_CHECK_CUDA(launch_pdl(quick_gelu_fwd_kernel, dim3(nblk(M * (C / 8), 256)), dim3(256), 0, STREAM(stream),
+                            reinterpret_cast<const __nv_bfloat16*>(x), (long long)ldx, (long long)M, (int)C,
+                            reinterpret_cast<__nv_bfloat16*>(y), (long long)ldy));
+  return MOS_OK;
+}
+
+extern "C" int mos_quick_gelu_bwd(const void* x, int64_t ldx, const void* dy, int64_t lddy, int64_t M, int32_t C, void* dx,
+                                  int64_t lddx, void* stream) {
+  MOS_CHECK_ARG(x && dy && dx && M > 0 && C % 8 == 0 && ldx % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0,
+                "mos_quick_gelu_bwd: bad arguments");
+  MOS_CHECK_CUDA(launch_pdl(quick_gelu_bwd_kernel, dim3(nblk(M * (C / 8), 256)), dim3(256), 0, STREAM(stream),
+                            reinterpret_cast<const __nv_bfloat16*>(x), (long long)ldx,
+                            reinterpret_cast<const __nv_bfloat16*>(dy), (long long)lddy, (long long)M, (int)C,
+                            reinterpret_cast<__nv_bfloat16*>(dx), (long long)lddx));
+  return MOS_OK;
+}
+
+extern "C" int mos_clip_embed_bwd(const int32_t* ids, const void* dx, int64_t ld, int64_t M, int32_t C, const int32_t* rows,
+                                  int32_t n_rows, int32_t accumulate, float* out, void* stream) {
+  MOS_CHECK_ARG(ids && dx && rows && out && M > 0 && C > 0 && n_rows > 0 && ld >= C, "mos_clip_embed_bwd: bad arguments");
+  MOS_CHECK_CUDA(launch_pdl(clip_embed_bwd_kernel, dim3((unsigned)n_rows), dim3(256), 0, STREAM(stream),
+                            reinterpret_cast<const int*>(ids), reinterpret_cast<const __nv_bfloat16*>(dx), (long long)ld,
+                            (long long)M, (int)C, reinterpret_cast<const int*>(rows), (int)accumulate, out));
   return MOS_OK;
 }
 

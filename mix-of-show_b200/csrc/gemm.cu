@@ -2,14 +2,13 @@
 //
 //   out[m,n] = epilogue( sum_k A[m,k] W[n,k] )        A, W bf16 K-major; fp32 accumulation in TMEM
 //
-// Persistent kernel: one CTA per SM loops over 128 x 160 output tiles (160 divides every SD1.5 channel count).
-// CTAs are grouped in thread-block clusters of CX x CM (CX = 2 along N, CM = 1/2/4 along M): the A tile is shared by
-// the CX column neighbours and the W tile by the CM row neighbours, so every CTA fetches only 1/CX of A and 1/CM of W
-// from L2 and TMA-multicasts it to its peers (the mainloop is L2-bandwidth bound without this: 73 FLOP/B per tile).
-// Roles (192 threads):
-//   warp 0      TMA producer   cp.async.bulk.tensor(.multicast) -> 128B-swizzled smem ring, mbarrier complete_tx
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x (160|176) x 16), 2 accumulator stages
-//   warps 2..5  epilogue       tcgen05.ld (32x32b) -> registers -> fused epilogue -> smem staging -> coalesced stores;
+// Persistent kernel: one CTA per SM loops over 128 x 160 output tiles (160 divides every SD1.5 channel count); when the
+// problem has an even number of 128-row tiles the CTAs work in PAIRS (2-CTA clusters, tcgen05 cta_group::2) on 256 x 160
+// tiles and each CTA fetches only half of the W tile (see the PAIR comment at the kernel).
+// Roles (64 + 256 threads):
+//   warp 0      TMA producer   cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128|256 x (160|176) x 16), 2 accumulator stages
+//   warps 2..9  epilogue       tcgen05.ld (32x32b) -> registers -> fused epilogue -> smem staging -> coalesced stores;
 //                              runs concurrently with the next tile's mainloop
 // LoRA fusion (edlora.py:244-246): the rank-padded down matrix [16, K] rides along as 16 extra B rows, so the
 // same MMA also produces t = x * down^T in TMEM columns 160..175; the epilogue adds t * (alpha*up)^T.
@@ -45,14 +44,12 @@ struct GemmDev {
   int kb_per_split;
   int stages;
   int conv, H, W, B, kc_per_tap, TW, TH, TB, lgTW, lgTH, tiles_w, tiles_h;
-  int half_dim;        // conv, CX == 2: which box dimension (1 = W, 2 = H, 3 = B) is split between the A halves
-  int half_off;        // coordinate offset of the second half along that dimension
   int lora;
   int geglu;
   int out_mode;
   int splits;
   int n_tiles, m_tiles, total_super, nbatch;
-  int cx, cm;          // cluster shape (N x M)
+  int pair;            // work items are 256 x 160 tiles of a 2-CTA cluster (tcgen05 cta_group::2)
   float* partial;
   const float* bias;
   const float* bias_batch;
@@ -72,7 +69,6 @@ struct GemmDev {
   int accum;           // MOS_OUT_F32: out += result (Gram accumulation)
   unsigned long long* tl;   // optional timeline buffer (mos_debug_set_timeline)
   int w_static;        // W tiles may be requested before griddepcontrol.wait
-  int w_f16;           // W (and the LoRA rows) are fp16 instead of bf16 (Gram products of fp16 activations)
 };
 
 template <bool F16>
@@ -111,14 +107,13 @@ __device__ __forceinline__ void cp_async_wait_all() {
 struct TileCoord {
   int n0, m0, cb0, ch0, cw0, split;
 };
-// super-item ws (shared by the whole cluster) + cluster rank -> this CTA's tile
-__device__ __forceinline__ TileCoord item_coord(const GemmDev& p, int ws, int nx, int my) {
+// work item ws (of a CTA, or of a CTA pair) + cluster rank -> this CTA's 128 x 160 tile
+__device__ __forceinline__ TileCoord item_coord(const GemmDev& p, int ws, int rank) {
   TileCoord t;
   t.split = ws % p.splits;
   const int tt = ws / p.splits;
-  const int sn = p.n_tiles / p.cx;
-  const int tn = (tt % sn) * p.cx + nx;
-  const int tm = (tt / sn) * p.cm + my;
+  const int tn = tt % p.n_tiles;
+  const int tm = p.pair ? 2 * (tt / p.n_tiles) + rank : tt / p.n_tiles;
   t.n0 = tn * BN;
   t.m0 = tm * BM;
   t.cb0 = t.ch0 = t.cw0 = 0;
@@ -175,16 +170,78 @@ __device__ __forceinline__ void stage_copy(const GemmDev& p, const TileCoord& t,
   }
 }
 
-template <bool F16>   // 16-bit type of A, of the row / head-split outputs and of the residual: fp16 or bf16
+// ---- CTA-pair primitives (tcgen05 cta_group::2): the two CTAs of a cluster sit on the two SMs of one TPC; one MMA of the
+// leader (cluster rank 0) multiplies a 256-row A tile (128 rows in each CTA's shared memory) with an N-row W tile of which
+// each CTA holds one half, and writes 128 accumulator rows into each CTA's TMEM.  PTX forms as in the CUTLASS headers of
+// this image (cute/arch/copy_sm100_tma.hpp SM100_TMA_2SM_LOAD_*, cutlass/arch/barrier.h umma_arrive_multicast_2x1SM,
+// cute/arch/tmem_allocator_sm100.hpp Allocator2Sm).
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // shared::cluster address of the same object in cluster rank 0
+
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  // issued by both CTAs; the transaction bytes count on the LEADER's mbarrier
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                                int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {   // arrives on this barrier in BOTH CTAs of the pair
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* dst_smem, uint32_t ncols) {   // same warp index in both CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// arrive (release, cluster scope) on the mbarrier at the same shared-memory offset in cluster rank `rank`
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+
+// F16 : 16-bit type of A, of the row / head-split outputs and of the residual (fp16 or bf16).
+// PAIR: the grid is made of 2-CTA clusters and a work item is a 256 x 160 output tile computed with cta_group::2 MMAs:
+//       every CTA fetches its own 128 A rows but only HALF of the W tile per k-block (26 KB instead of 36 KB for the same
+//       MMA work per SM - the mainloop of the 1-CTA kernel sits on the L2 -> SM fabric limit, profiles/README.md), the
+//       leader issues the MMAs for both, each CTA drains its own 128 accumulator rows.
+template <bool F16, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const __grid_constant__ CUtensorMap tmL, const GemmDev p) {
+            const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmL, const GemmDev p) {
   extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment is required by SWIZZLE_128B; the dynamic smem base offset is identical in every CTA of the
-  // cluster (same kernel, same static smem), which the multicast addressing relies on.
+  // 1024-byte alignment is required by SWIZZLE_128B; the dynamic smem base offset is identical in both CTAs of a pair
+  // (same kernel, same static smem), which the cta_group::2 operand addressing relies on.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int b_bytes = B_STAGE_BYTES + (p.lora ? L_STAGE_BYTES : 0);
-  const int stage_bytes = A_STAGE_BYTES + b_bytes;
+  // W rows held by one CTA per k-block: the whole tile (160, + 16 LoRA rows), or in a pair one half of N = 160 / 176
+  const int b_rows = PAIR ? (p.lora ? (BN + LORA_N) / 2 : BN / 2) : (p.lora ? BN + LORA_N : BN);
+  const int stage_bytes = A_STAGE_BYTES + b_rows * 128;
   uint8_t* stg = smem + p.stages * stage_bytes;                    // epilogue staging tile [128][STG_PITCH]
   float* cb_s = reinterpret_cast<float*>(stg + STG_BYTES);          // [4][BN] bias (+ per-batch bias)
   float4* up_s = reinterpret_cast<float4*>(cb_s + 4 * BN);          // [BN] LoRA up rows (pre-scaled by alpha)
@@ -197,104 +254,79 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int csize = p.cx * p.cm;
-  const int crank = csize > 1 ? (int)cluster_ctarank() : 0;
-  const int nx = crank % p.cx, my = crank / p.cx;
-  const int cluster_id = blockIdx.x / csize;
-  const int num_clusters = gridDim.x / csize;
+  const int epi_warps = ((int)blockDim.x - 64) >> 5;
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;      // 0 = leader
+  const int unit_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // CTA (or CTA pair) index
+  const int num_units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   if (threadIdx.x == 0) stamp(0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(PAIR && rank == 1 && p.lora ? &tmB1 : &tmB);
     if (p.lora) tma_prefetch_desc(&tmL);
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], csize);   // one tcgen05.commit arrival from every CTA of the cluster
+      mbar_init(&full_bar[s], 1);        // one arrive.expect_tx (pair: by the leader's producer, for the bytes of both)
+      mbar_init(&empty_bar[s], 1);       // one tcgen05.commit (pair: multicast to both CTAs)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], blockDim.x - 64);
+      mbar_init(&tmem_empty_bar[s], (PAIR ? 2 : 1) * epi_warps);   // one arrival per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(&tmem_base_holder, TMEM_COLS);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_2cta(&tmem_base_holder, TMEM_COLS);
+    else tmem_alloc(&tmem_base_holder, TMEM_COLS);
+  }
   tc_fence_before();
-  if (csize > 1)
-    cluster_sync_all();   // peers must see initialised barriers before any remote arrive / multicast lands
-  else
-    __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer must see initialised barriers before any remote complete_tx / commit / arrive
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_holder;
 
   // Everything above touched no global memory written by the previous kernel in the stream.
   if (threadIdx.x == 0) stamp(1);
-  const bool is_producer = warp == 0 && lane == 0;
-  if (!is_producer) pdl_wait();
+  pdl_wait();
   pdl_launch_dependents();
 
   if (warp == 0) {
-    // ===================================================================== TMA producer
+    // ===================================================================== TMA producer (every CTA)
     if (lane == 0) {
-      // multicast masks: A goes to the CX column neighbours (same my), W to the CM row neighbours (same nx)
-      uint16_t mask_a = 0, mask_b = 0;
-      for (int j = 0; j < p.cx; ++j) mask_a |= (uint16_t)(1u << (my * p.cx + j));
-      for (int j = 0; j < p.cm; ++j) mask_b |= (uint16_t)(1u << (j * p.cx + nx));
-      const int a_rows = BM / p.cx;           // rows of A this CTA fetches
-      const int b_rows = BN / p.cm;           // rows of W this CTA fetches
-      // The weights are static: request the W tiles of the first ring pass BEFORE waiting for the previous kernel, so
-      // that their HBM round trip overlaps the predecessor's tail (the 1.72 GB of weights stream from HBM every step;
-      // the activations behind the dependency come from L2).  A (and the LoRA rows, which the training step rewrites)
-      // follow after griddepcontrol.wait and complete the same mbarrier transaction.
-      int pre = 0;
-      if (p.w_static && csize == 1 && cluster_id < p.total_super) {
-        const TileCoord t0 = item_coord(p, cluster_id, nx, my);
-        const int kb0 = t0.split * p.kb_per_split;
-        pre = min(p.stages, min(p.kb_total, kb0 + p.kb_per_split) - kb0);
-        for (int i = 0; i < pre; ++i) {
-          mbar_expect_tx(&full_bar[i], (uint32_t)stage_bytes);
-          tma_load_2d(smem + i * stage_bytes + A_STAGE_BYTES, &tmB, &full_bar[i], (kb0 + i) * BK, t0.n0);
-        }
-      }
-      pdl_wait();
       stamp(2);
       int stage = 0;
       uint32_t phase = 0;
-      int issued = 0;
-      for (int ws = cluster_id; ws < p.total_super; ws += num_clusters) {
-        const TileCoord t = item_coord(p, ws, nx, my);
+      for (int ws = unit_id; ws < p.total_super; ws += num_units) {
+        const TileCoord t = item_coord(p, ws, rank);
         const int kb_begin = t.split * p.kb_per_split;
         const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
-        for (int kb = kb_begin; kb < kb_end; ++kb, ++issued) {
-          const bool w_requested = issued < pre;     // W tile already in flight, transaction bytes already expected
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + A_STAGE_BYTES;
-          if (!w_requested) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);   // every CTA of the cluster has released this slot
-            mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-          }
-          uint8_t* sa_dst = sa + nx * a_rows * 128;
+          mbar_wait(&empty_bar[stage], phase ^ 1);     // the MMAs that read this slot have retired
+          if (!PAIR) mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+          else if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * (uint32_t)stage_bytes);
           if (p.conv) {
             const int tap = kb / p.kc_per_tap;
             const int kc = kb - tap * p.kc_per_tap;
             const int kh = tap / 3, kw = tap - kh * 3;
-            int cw = t.cw0 + kw - 1, chh = t.ch0 + kh - 1, cb = t.cb0;
-            if (nx == 1) {
-              if (p.half_dim == 1) cw += p.half_off;
-              else if (p.half_dim == 2) chh += p.half_off;
-              else cb += p.half_off;
-            }
-            if (p.cx > 1) tma_load_4d_mc(sa_dst, &tmA, &full_bar[stage], kc * BK, cw, chh, cb, mask_a);
-            else tma_load_4d(sa_dst, &tmA, &full_bar[stage], kc * BK, cw, chh, cb);
+            if (PAIR) tma_load_4d_2sm(sa, &tmA, &full_bar[stage], kc * BK, t.cw0 + kw - 1, t.ch0 + kh - 1, t.cb0);
+            else tma_load_4d(sa, &tmA, &full_bar[stage], kc * BK, t.cw0 + kw - 1, t.ch0 + kh - 1, t.cb0);
           } else {
-            if (p.cx > 1) tma_load_2d_mc(sa_dst, &tmA, &full_bar[stage], kb * BK, t.m0 + nx * a_rows, mask_a);
-            else tma_load_2d(sa_dst, &tmA, &full_bar[stage], kb * BK, t.m0);
+            if (PAIR) tma_load_2d_2sm(sa, &tmA, &full_bar[stage], kb * BK, t.m0);
+            else tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, t.m0);
           }
-          if (p.cm > 1)
-            tma_load_2d_mc(sb + my * b_rows * 128, &tmB, &full_bar[stage], kb * BK, t.n0 + my * b_rows, mask_b);
-          else if (!w_requested)
+          if (!PAIR) {
             tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, t.n0);
-          if (p.lora) tma_load_2d(sb + B_STAGE_BYTES, &tmL, &full_bar[stage], kb * BK, 0);
+            if (p.lora) tma_load_2d(sb + B_STAGE_BYTES, &tmL, &full_bar[stage], kb * BK, 0);
+          } else if (!p.lora) {
+            tma_load_2d_2sm(sb, &tmB, &full_bar[stage], kb * BK, t.n0 + rank * (BN / 2));
+          } else if (rank == 0) {       // N = 176 = [160 W rows | 16 LoRA rows]: leader holds W rows 0..87 ...
+            tma_load_2d_2sm(sb, &tmB, &full_bar[stage], kb * BK, t.n0);
+          } else {                      // ... the peer W rows 88..159 and the 16 LoRA rows
+            constexpr int W1 = BN - (BN + LORA_N) / 2;     // 72
+            tma_load_2d_2sm(sb, &tmB1, &full_bar[stage], kb * BK, t.n0 + (BN + LORA_N) / 2);
+            tma_load_2d_2sm(sb + W1 * 128, &tmL, &full_bar[stage], kb * BK, 0);
+          }
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
@@ -303,19 +335,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_ab(BM, p.lora ? BN + LORA_N : BN, F16 ? 0 : 1, p.w_f16 ? 0 : 1);
-      const uint16_t mask_all = (uint16_t)((1u << csize) - 1);
+    // ===================================================================== MMA issuer (pair: the leader only)
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc(PAIR ? 2 * BM : BM, p.lora ? BN + LORA_N : BN, F16 ? 0 : 1);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int ws = cluster_id; ws < p.total_super; ws += num_clusters, ++it) {
-        const TileCoord t = item_coord(p, ws, nx, my);
+      for (int ws = unit_id; ws < p.total_super; ws += num_units, ++it) {
+        const TileCoord t = item_coord(p, ws, 0);
         const int kb_begin = t.split * p.kb_per_split;
         const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
         const int acc = it & 1;
-        mbar_wait(&tmem_empty_bar[acc], ((it >> 1) & 1) ^ 1);   // epilogue drained this accumulator
+        mbar_wait(&tmem_empty_bar[acc], ((it >> 1) & 1) ^ 1);   // the epilogue (of both CTAs) drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
@@ -327,31 +358,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const uint64_t bdesc = make_desc_sw128(smem_u32(sa + A_STAGE_BYTES));
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 bf16 = 32 B along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            // advance 16 elements = 32 B along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
+            const uint32_t accf = (kb > kb_begin || k > 0) ? 1u : 0u;
+            if (PAIR) umma_f16_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accf);
+            else umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accf);
           }
-          // frees the smem slot (in every CTA of the cluster) once these MMAs retire
-          if (csize > 1) umma_commit_mc(&empty_bar[stage], mask_all);
+          // frees the smem slot (in both CTAs of a pair) once these MMAs retire
+          if (PAIR) umma_commit_2cta(&empty_bar[stage]);
           else umma_commit(&empty_bar[stage]);
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full_bar[acc]);
+        if (PAIR) umma_commit_2cta(&tmem_full_bar[acc]);
+        else umma_commit(&tmem_full_bar[acc]);
       }
     }
   } else {
-    // ===================================================================== epilogue (warps 2..9)
+    // ===================================================================== epilogue (warps 2..9; every CTA, own 128 rows)
     const int q = warp & 3;                  // TMEM lane quadrant this warp may access
     const int chalf0 = (warp - 2) >> 2;      // first column half this warp handles
-    const int chalf_step = ((int)blockDim.x - 64) >> 7;   // 1 (4 epilogue warps: both halves) or 2 (8 warps)
+    const int chalf_step = epi_warps >> 2;   // 1 (4 epilogue warps: both halves) or 2 (8 warps)
     const int r = q * 32 + lane;             // tile row owned by this thread
     const int et = threadIdx.x - 64;         // 0..255
     const bool staged = (p.splits == 1) && (p.out_mode == MOS_OUT_BF16);
     int it = 0;
-    for (int ws = cluster_id; ws < p.total_super; ws += num_clusters, ++it) {
-      const TileCoord t = item_coord(p, ws, nx, my);
+    for (int ws = unit_id; ws < p.total_super; ws += num_units, ++it) {
+      const TileCoord t = item_coord(p, ws, rank);
       const int acc = it & 1;
       long long m;
       int b;
@@ -395,42 +429,50 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint8_t* srow = stg + r * STG_PITCH;
 
       for (int chalf = chalf0; chalf < 2; chalf += chalf_step) {
-      if (p.splits > 1) {
-        float* dst = p.partial + ((long long)t.split * p.M + m) * p.N + t.n0;
-#pragma unroll 1
-        for (int c = chalf * 5; c < chalf * 5 + 5; ++c) {
-          uint32_t v[16];
-          tmem_ld16(trow + c * 16, v);
-          tmem_ld_wait();
-          if (valid) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4)
-              *reinterpret_cast<uint4*>(dst + c * 16 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          }
-        }
-      } else {
+        // this warp's 80 accumulator columns (and the 16 LoRA columns) in ONE round of TMEM loads: a tcgen05.ld costs a few
+        // hundred cycles of latency while the tensor pipe is busy, and a load-wait-compute loop pays it once per chunk
+        uint32_t vv[5][16];
         float t4[16];
-        if (p.lora) {
+        if (p.geglu) {
+          // tile columns [0,80) = a, [80,160) = gate for the same 80 outputs; this warp: outputs [40*chalf, +40)
+#pragma unroll
+          for (int c = 0; c < 5; ++c) {
+            tmem_ld8(trow + (chalf * 5 + c) * 8, *reinterpret_cast<uint32_t(*)[8]>(&vv[c][0]));
+            tmem_ld8(trow + BN / 2 + (chalf * 5 + c) * 8, *reinterpret_cast<uint32_t(*)[8]>(&vv[c][8]));
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 5; ++c) tmem_ld16(trow + (chalf * 5 + c) * 16, vv[c]);
+        }
+        if (p.lora && p.splits == 1) {
           uint32_t tv[16];
           tmem_ld16(trow + BN, tv);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) t4[j] = __uint_as_float(tv[j]);
+        } else {
+          tmem_ld_wait();
         }
-        if (p.geglu) {
-          // tile columns [0,80) = a, [80,160) = gate for the same 80 outputs; this warp: outputs [40*chalf, +40)
-#pragma unroll 1
-          for (int c = chalf * 5; c < chalf * 5 + 5; ++c) {
-            uint32_t va[8], vg[8];
-            tmem_ld8(trow + c * 8, va);
-            tmem_ld8(trow + BN / 2 + c * 8, vg);
-            tmem_ld_wait();
+        if (p.splits > 1) {
+          if (valid) {
+            float* dst = p.partial + ((long long)t.split * p.M + m) * p.N + t.n0 + chalf * 80;
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<uint4*>(dst + c * 16 + j) = make_uint4(vv[c][j], vv[c][j + 1], vv[c][j + 2], vv[c][j + 3]);
+            }
+          }
+        } else if (p.geglu) {
+#pragma unroll
+          for (int cc = 0; cc < 5; ++cc) {
+            const int c = chalf * 5 + cc;
             float o[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int na = c * 8 + j, ng = na + BN / 2;
-              float a = __uint_as_float(va[j]) + cb[na];
-              float g = __uint_as_float(vg[j]) + cb[ng];
+              float a = __uint_as_float(vv[cc][j]) + cb[na];
+              float g = __uint_as_float(vv[cc][8 + j]) + cb[ng];
               if (p.lora) {
                 const float4 ua = up_s[na], ug = up_s[ng];
                 a += t4[0] * ua.x + t4[1] * ua.y + t4[2] * ua.z + t4[3] * ua.w;
@@ -441,11 +483,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             store16x8<F16>(reinterpret_cast<__nv_bfloat16*>(srow + c * 16), o);
           }
         } else {
-#pragma unroll 1
-          for (int c = chalf * 5; c < chalf * 5 + 5; ++c) {
-            uint32_t vv[16];
-            tmem_ld16(trow + c * 16, vv);
-            tmem_ld_wait();
+#pragma unroll
+          for (int cc = 0; cc < 5; ++cc) {
+            const int c = chalf * 5 + cc;
             const int nl = c * 16;               // column inside the tile
             const int nc = t.n0 + nl;            // global column
             float o[16];
@@ -459,10 +499,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
             for (int j4 = 0; j4 < 16; j4 += 4) {
               const float4 cbv = *reinterpret_cast<const float4*>(cb + nl + j4);
-              o[j4 + 0] = __uint_as_float(vv[j4 + 0]) + cbv.x;
-              o[j4 + 1] = __uint_as_float(vv[j4 + 1]) + cbv.y;
-              o[j4 + 2] = __uint_as_float(vv[j4 + 2]) + cbv.z;
-              o[j4 + 3] = __uint_as_float(vv[j4 + 3]) + cbv.w;
+              o[j4 + 0] = __uint_as_float(vv[cc][j4 + 0]) + cbv.x;
+              o[j4 + 1] = __uint_as_float(vv[cc][j4 + 1]) + cbv.y;
+              o[j4 + 2] = __uint_as_float(vv[cc][j4 + 2]) + cbv.z;
+              o[j4 + 3] = __uint_as_float(vv[cc][j4 + 3]) + cbv.w;
             }
             if (p.lora) {
 #pragma unroll
@@ -506,9 +546,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               for (int half = 0; half < 2; ++half) {
                 const int n = nc + half * 8;
                 const int seg = n / seg_len;
-                const int cc = n - seg * seg_len;
-                const int head = cc / p.head_dim;
-                const int j0 = cc - head * p.head_dim;
+                const int cc2 = n - seg * seg_len;
+                const int head = cc2 / p.head_dim;
+                const int j0 = cc2 - head * p.head_dim;
                 __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(p.seg_ptr[seg]);
                 const long long bh = bb * p.heads + head;
                 if (p.seg_kind[seg] == MOS_SEG_ROWS) {
@@ -521,16 +561,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
               }
             }
-            __syncwarp();
           }
         }
-      }
       }  // column halves
-      // ---- 4. accumulator drained: hand it back to the MMA warp (next-but-one tile)
+      // ---- 4. accumulator drained: hand it back to the MMA thread of the leader (next-but-one tile)
       tc_fence_before();
-      mbar_arrive(&tmem_empty_bar[acc]);
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+        else mbar_arrive(&tmem_empty_bar[acc]);
+      }
       if (et == 0 && it == 0) stamp(6);
-      // ---- 5. coalesced write-out of the staged bf16 tile
+      // ---- 5. coalesced write-out of the staged 16-bit tile
       if (staged) {
         epi_bar();
         __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out);
@@ -543,14 +585,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tc_fence_before();
   }
 
-  // no CTA may exit while a peer can still multicast into its smem or arrive on its barriers
-  if (csize > 1)
-    cluster_sync_all();
-  else
-    __syncthreads();
+  // a CTA of a pair may not exit while its peer can still read its shared memory (MMA operands), complete transactions or
+  // arrive on its barriers
+  if (PAIR) cluster_sync_all();
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) tmem_dealloc_2cta(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -618,6 +660,9 @@ extern "C" int mos_gemm_bf16(const mos_gemm_args* a, void* stream_) {
   MOS_CHECK_ARG(is_aligned(a->A, 16) && is_aligned(a->W, 16), "mos_gemm_bf16: A/W must be 16-byte aligned");
   MOS_CHECK_DTYPE(a->a_dtype, "mos_gemm_bf16 (a_dtype)");
   MOS_CHECK_DTYPE(a->w_dtype, "mos_gemm_bf16 (w_dtype)");
+  MOS_CHECK_ARG(a->a_dtype == a->w_dtype,
+                "mos_gemm_bf16: A and W must share the 16-bit type (tcgen05 kind::f16 takes one operand format per MMA; a "
+                "mixed fp16 x bf16 descriptor raises an illegal-instruction fault on B200)");
   const bool f16 = a->a_dtype == MOS_DT_F16;
   const int splits = a->splits > 0 ? a->splits : 1;
   const bool lora = a->lora_down != nullptr;
@@ -686,55 +731,53 @@ extern "C" int mos_gemm_bf16(const mos_gemm_args* a, void* stream_) {
     p.kb_total = (int)(a->K / BK);
   }
   p.m_tiles = m_tiles;
-  // ---- cluster shape: CX column neighbours share A, CM row neighbours share W
-  // Measured on B200 (profiles/README.md): with 4 smem stages the multicast hand-shake (remote slot release + multicast
-  // latency) costs more than the L2 traffic it saves (0.44 vs 0.36 us per k-block on the 320->320 conv), so clusters
-  // are opt-in (MOS_GEMM_CLUSTER=1) until the stage budget grows (2-CTA UMMA, next round).
-  static int use_cluster = -1;
-  if (use_cluster < 0) {
-    const char* e = getenv("MOS_GEMM_CLUSTER");
-    use_cluster = (e && e[0] == '1') ? 1 : 0;
+  // ---- CTA pairs (tcgen05 cta_group::2): a work item is a 256 x 160 tile of a 2-CTA cluster; needs an even number of
+  // 128-row tiles.  MOS_GEMM_PAIR=0 forces the 1-CTA kernel (A/B comparison, profiles/README.md).
+  static int use_pair = -1;
+  if (use_pair < 0) {
+    const char* e = getenv("MOS_GEMM_PAIR");
+    use_pair = (e && e[0] == '0') ? 0 : 1;
   }
-  p.cx = p.cm = 1;
-  if (use_cluster) {
-    p.cx = (p.n_tiles % 2 == 0) ? 2 : 1;
-    p.cm = (m_tiles % 4 == 0) ? 4 : (m_tiles % 2 == 0) ? 2 : 1;
-  }
-  const int csize = p.cx * p.cm;
+  const bool pair = use_pair && (m_tiles % 2 == 0);
+  p.pair = pair ? 1 : 0;
 
-  // ---- tensor maps (the A box is 1/CX of the tile rows, the W box 1/CM of the tile columns)
+  // ---- tensor maps.  W box: the whole tile (160 rows), or a pair's half: 80 rows, with LoRA (N = 176 = 160 W rows + 16
+  // LoRA rows) 88 rows for the leader (tmB) and 72 W rows + the 16 LoRA rows for its peer (tmB1, tmL).
+  CUtensorMap tmB1;
+  memset(&tmB1, 0, sizeof(tmB1));
+  const uint32_t wrows0 = pair ? (lora ? (BN + LORA_N) / 2 : BN / 2) : BN;
+  const uint32_t wrows1 = BN - (BN + LORA_N) / 2;
   if (a->conv) {
-    uint32_t bw = (uint32_t)p.TW, bh = (uint32_t)p.TH, bb = (uint32_t)p.TB;
-    if (p.cx == 2) {
-      if (bb >= 2) { bb /= 2; p.half_dim = 3; p.half_off = (int)bb; }
-      else if (bh >= 2) { bh /= 2; p.half_dim = 2; p.half_off = (int)bh; }
-      else { bw /= 2; p.half_dim = 1; p.half_off = (int)bw; }
-    }
     uint64_t dims[4] = {(uint64_t)a->C, (uint64_t)a->Wd, (uint64_t)a->H, (uint64_t)a->B};
     const uint64_t pitch = (uint64_t)(a->lda > 0 ? a->lda : a->C);
     MOS_CHECK_ARG(pitch >= (uint64_t)a->C && pitch % 8 == 0, "mos_gemm_bf16: conv pixel pitch %llu invalid",
                   (unsigned long long)pitch);
     uint64_t str[3] = {pitch * 2, (uint64_t)a->Wd * pitch * 2, (uint64_t)a->H * a->Wd * pitch * 2};
-    uint32_t box[4] = {BK, bw, bh, bb};
+    uint32_t box[4] = {BK, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TB};
     int rc = encode_tmap(&tmA, a->A, 2, 4, dims, str, box, 3);
     if (rc) return rc;
     uint64_t wd[2] = {(uint64_t)a->K * 9, (uint64_t)a->N};
     uint64_t ws[1] = {(uint64_t)a->K * 9 * 2};
-    uint32_t wb[2] = {BK, (uint32_t)(BN / p.cm)};
+    uint32_t wb[2] = {BK, wrows0};
     rc = encode_tmap(&tmB, a->W, 2, 2, wd, ws, wb, 3);
     if (rc) return rc;
   } else {
     uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->M};
     uint64_t str[1] = {(uint64_t)a->lda * 2};
-    uint32_t box[2] = {BK, (uint32_t)(BM / p.cx)};
+    uint32_t box[2] = {BK, (uint32_t)BM};
     int rc = encode_tmap(&tmA, a->A, 2, 2, dims, str, box, 3);
     if (rc) return rc;
     uint64_t wd[2] = {(uint64_t)a->K, (uint64_t)a->N};
     uint64_t ws[1] = {(uint64_t)a->K * 2};
-    uint32_t wb[2] = {BK, (uint32_t)(BN / p.cm)};
+    uint32_t wb[2] = {BK, wrows0};
     rc = encode_tmap(&tmB, a->W, 2, 2, wd, ws, wb, 3);
     if (rc) return rc;
     if (lora) {
+      if (pair) {
+        uint32_t wb1[2] = {BK, wrows1};
+        rc = encode_tmap(&tmB1, a->W, 2, 2, wd, ws, wb1, 3);
+        if (rc) return rc;
+      }
       uint64_t ld[2] = {(uint64_t)a->K, LORA_N};
       uint64_t ls[1] = {(uint64_t)a->K * 2};
       uint32_t lb[2] = {BK, LORA_N};
@@ -773,13 +816,13 @@ extern "C" int mos_gemm_bf16(const mos_gemm_args* a, void* stream_) {
   p.accum = a->accumulate;
   p.tl = g_timeline_host;
   p.w_static = a->w_static;
-  p.w_f16 = a->w_dtype == MOS_DT_F16;
   if (a->bias_batch && !a->conv)
     MOS_CHECK_ARG(p.rows_per_batch >= 32, "mos_gemm_bf16: bias_batch needs rows_per_batch >= 32 in plain mode");
-  p.total_super = (p.n_tiles / p.cx) * (m_tiles / p.cm) * splits;
+  p.total_super = p.n_tiles * (pair ? m_tiles / 2 : m_tiles) * splits;
   p.nbatch = a->conv ? a->B : (int)ceil_div(a->M, p.rows_per_batch);
 
-  const int stage_bytes = A_STAGE_BYTES + B_STAGE_BYTES + (lora ? L_STAGE_BYTES : 0);
+  const int b_rows = pair ? (int)wrows0 : (lora ? BN + LORA_N : BN);
+  const int stage_bytes = A_STAGE_BYTES + b_rows * 128;
   int stages = a->stages > 0 ? a->stages : MAX_STAGES;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   while (stages * stage_bytes + EPI_SMEM_BYTES + 1024 > MAX_DYN_SMEM) --stages;
@@ -792,10 +835,12 @@ extern "C" int mos_gemm_bf16(const mos_gemm_args* a, void* stream_) {
     int dev = 0;
     MOS_CHECK_CUDA(cudaGetDevice(&dev));
     MOS_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    MOS_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM));
-    MOS_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM));
+    MOS_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM));
+    MOS_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM));
+    MOS_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM));
+    MOS_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM));
   }
-  // persistent: one CTA per SM; each cluster loops over its share of (super-tile, split) work items
+  // persistent: one CTA per SM; each CTA (or CTA pair) loops over its share of the (tile, split) work items
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   static int epi_warps = 0;
@@ -804,40 +849,27 @@ extern "C" int mos_gemm_bf16(const mos_gemm_args* a, void* stream_) {
     epi_warps = (e && e[0] == '4') ? 4 : 8;
   }
   cfg.blockDim = dim3(64 + 32 * epi_warps);
-  cfg.dynamicSmemBytes = (size_t)MAX_DYN_SMEM;
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   attr[1].id = cudaLaunchAttributeClusterDimension;
-  attr[1].val.clusterDim.x = (unsigned)csize;
+  attr[1].val.clusterDim.x = 2;
   attr[1].val.clusterDim.y = 1;
   attr[1].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  static int max_clusters[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // co-resident clusters per cluster size (GPC packing)
-  if (max_clusters[csize] == 0) {
-    int n = 0;
-    cfg.gridDim = dim3((unsigned)(csize * (num_sms / csize)));
-    cfg.numAttrs = 2;
-    if (csize > 1) {
-      cudaLaunchAttribute only_cluster[1] = {attr[1]};
-      cfg.attrs = only_cluster;
-      cfg.numAttrs = 1;
-      MOS_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_kernel<false>, &cfg));
-      cfg.attrs = attr;
-      MOS_CHECK_ARG(n > 0, "mos_gemm_bf16: cluster size %d cannot be scheduled", csize);
-    } else {
-      n = num_sms;
-    }
-    max_clusters[csize] = n;
+  cfg.numAttrs = pair ? 2 : 1;   // no cluster attribute at all for unclustered launches
+  int units = pair ? num_sms / 2 : num_sms;      // 2-CTA clusters pack the 148 SMs exactly (one pair per TPC)
+  if (units > p.total_super) units = p.total_super;
+  cfg.gridDim = dim3((unsigned)(pair ? 2 * units : units));
+  if (pair) {
+    if (f16) MOS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<true, true>, tmA, tmB, tmB1, tmL, p));
+    else MOS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<false, true>, tmA, tmB, tmB1, tmL, p));
+  } else {
+    if (f16) MOS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<true, false>, tmA, tmB, tmB1, tmL, p));
+    else MOS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<false, false>, tmA, tmB, tmB1, tmL, p));
   }
-  int clusters = max_clusters[csize];
-  if (clusters > p.total_super) clusters = p.total_super;
-  cfg.gridDim = dim3((unsigned)(clusters * csize));
-  cfg.dynamicSmemBytes = (size_t)smem_bytes;
-  cfg.numAttrs = csize > 1 ? 2 : 1;   // no cluster attribute at all for unclustered launches
-  if (f16) MOS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<true>, tmA, tmB, tmL, p));
-  else MOS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<false>, tmA, tmB, tmL, p));
   return MOS_OK;
 }
 

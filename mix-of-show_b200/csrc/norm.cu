@@ -5,6 +5,8 @@
 // BasicTransformerBlock (reached from mixofshow/pipelines/pipeline_edlora.py:277).
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.h"
 #include "tc.cuh"
 
@@ -223,155 +225,151 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long 
   }
 }
 
-// ---------------------------------------------------------------------------------------------- fused GroupNorm
-// Single-kernel GroupNorm(+SiLU): every block keeps its rows in registers, publishes per-chunk partial statistics,
-// passes a per-sample grid barrier (monotonic ticket counter, all blocks co-resident by construction: the host caps
-// the grid at the occupancy limit), reduces the partials in a fixed order and normalises from registers.  One read
-// of x, one write of y, one launch.
-constexpr int GN_MAXR = 8;   // rows per thread kept in registers
+// ---------------------------------------------------------------------------------------------- one-pass GroupNorm
+// GroupNorm(+SiLU) in ONE launch with ONE read of x: a thread-block cluster of k CTAs (k = 1, 2, 4, 8) owns one
+// (sample, group) pair.  Each CTA streams its rows of the group's channel slab (cpg = C / 32 channels, 20..160 bytes
+// per row) into shared memory while accumulating sum / sum of squares, the k partial pairs are exchanged through
+// distributed shared memory (every CTA stores its pair into every peer's table, one cluster barrier, everybody adds the
+// table in rank order: fixed order -> bitwise reproducible and identical in all CTAs), and the slab is normalised out of
+// shared memory.  Replaces gn_stats + gn_apply (two launches, two reads of x, a partial-statistics round trip through
+// global memory); those remain as the fallback for slabs that do not fit 8 x 200 KB.
+// Thread layout: thread = (row lane, VEC-element column word); blockDim = lanes * (cpg / VEC), so the column word - and
+// with it gamma / beta - is fixed per thread and no index division happens inside the loops; every thread re-reads only
+// the shared-memory words it wrote itself.
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32x2(uint32_t raddr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(raddr), "f"(a), "f"(b) : "memory");
+}
 
-template <bool F16>
-__global__ void __launch_bounds__(320, 2)
-gn_fused_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int HW, int C, int rows_per_chunk,
-                float* __restrict__ partial, unsigned int* __restrict__ counters, const float* __restrict__ gamma,
-                const float* __restrict__ beta, float eps, int silu_act, __nv_bfloat16* __restrict__ y, long long ldy) {
-  extern __shared__ float red[];  // [blockDim][16]
-  __shared__ float mean[GN_GROUPS], rstd[GN_GROUPS];
+template <bool F16, int VEC>   // VEC = 16-bit elements per load / store: 4 (cpg % 4 == 0) or 2
+__global__ void __launch_bounds__(256)
+gn_group_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int HW, int C, int rows_per_cta, int k, int lanes,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu_act,
+                __nv_bfloat16* __restrict__ y, long long ldy) {
+  extern __shared__ __align__(16) uint8_t gsm[];
+  __shared__ float wred[8][2];
+  __shared__ float2 table[8];       // per-CTA partial (sum, sumsq), filled by the peers through DSMEM
+  __shared__ float stat[2];
   pdl_wait();
   pdl_launch_dependents();
-  const int oct = C / 8;
-  const int b = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
-  const int lanes = blockDim.x / oct;
-  const int o = threadIdx.x % oct, rl = threadIdx.x / oct;
-  const int r0 = chunk * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
   const int cpg = C / GN_GROUPS;
-  uint4 rows[GN_MAXR];
-  float s[8], q[8];
+  const int vpr = cpg / VEC;                       // column words per row
+  // `lanes` row lanes (lanes * vpr <= blockDim.x; blockDim is rounded up to whole warps, the surplus threads only take
+  // part in the shuffles)
+  const int rank = k > 1 ? (int)cluster_ctarank() : 0;
+  const int bg = blockIdx.x / k;                   // (sample, group)
+  const int b = bg / GN_GROUPS, g = bg - b * GN_GROUPS;
+  const int v = threadIdx.x % vpr, rl = threadIdx.x / vpr;
+  const int r0 = rank * rows_per_cta, r1 = min(HW, r0 + rows_per_cta);
+  using word_t = typename std::conditional<VEC == 4, uint2, uint32_t>::type;
+  word_t* slab = reinterpret_cast<word_t*>(gsm);
+  const __nv_bfloat16* xb = x + ((long long)b * HW) * ldx + g * cpg + v * VEC;
+  float s = 0.f, q = 0.f;
+  if (rl < lanes) {
+    for (int r = r0 + rl; r < r1; r += 4 * lanes) {
+      word_t w[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
-  const __nv_bfloat16* base = x + ((long long)b * HW) * ldx + o * 8;
-#pragma unroll
-  for (int k = 0; k < GN_MAXR; ++k) {
-    const int r = r0 + rl + k * lanes;
-    if (r < r1) rows[k] = __ldg(reinterpret_cast<const uint4*>(base + (long long)r * ldx));
-  }
-#pragma unroll
-  for (int k = 0; k < GN_MAXR; ++k) {
-    const int r = r0 + rl + k * lanes;
-    if (r < r1) {
-      const uint32_t w[4] = {rows[k].x, rows[k].y, rows[k].z, rows[k].w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = unpack16x2<F16>(w[i]);
-        s[2 * i] += f.x;
-        q[2 * i] += f.x * f.x;
-        s[2 * i + 1] += f.y;
-        q[2 * i + 1] += f.y * f.y;
+      for (int j = 0; j < 4; ++j) {
+        const int rr = r + j * lanes;
+        if (rr < r1) w[j] = __ldg(reinterpret_cast<const word_t*>(xb + (long long)rr * ldx));
       }
-    }
-  }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    red[threadIdx.x * 16 + i] = s[i];
-    red[threadIdx.x * 16 + 8 + i] = q[i];
-  }
-  __syncthreads();
-  if (threadIdx.x < GN_GROUPS) {
-    const int g = threadIdx.x;
-    float gs = 0.f, gq = 0.f;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-      for (int l = 0; l < lanes; ++l) {
-        const float* t = red + (l * oct + (c >> 3)) * 16 + (c & 7);
-        gs += t[0];
-        gq += t[8];
-      }
-    }
-    float* dst = partial + (((long long)b * nchunks + chunk) * GN_GROUPS + g) * 2;
-    dst[0] = gs;
-    dst[1] = gq;
-    __threadfence();
-  }
-  __syncthreads();
-  // ---- per-sample grid barrier (sense reversal: count returns to 0, generation increments; zero-initialised once)
-  if (threadIdx.x == 0) {
-    unsigned int* count = counters + b;
-    unsigned int* gen = counters + 32 + b;
-    unsigned int my_gen, cur;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(my_gen) : "l"(gen) : "memory");
-    const unsigned int old = atomicAdd(count, 1u);
-    if (old == (unsigned)nchunks - 1u) {
-      *count = 0u;
-      __threadfence();
-      atomicAdd(gen, 1u);
-    } else {
-      long long t0 = clock64();
-      do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(gen) : "memory");
-        if (clock64() - t0 > 4000000000LL) {
-          printf("mos: groupnorm grid-barrier timeout\n");
-          __trap();
+      for (int j = 0; j < 4; ++j) {
+        const int rr = r + j * lanes;
+        if (rr < r1) {
+          slab[(rr - r0) * vpr + v] = w[j];
+          float2 f0, f1 = make_float2(0.f, 0.f);
+          if constexpr (VEC == 4) {
+            f0 = unpack16x2<F16>(w[j].x);
+            f1 = unpack16x2<F16>(w[j].y);
+          } else {
+            f0 = unpack16x2<F16>(w[j]);
+          }
+          s += (f0.x + f0.y) + (f1.x + f1.y);
+          q += (f0.x * f0.x + f0.y * f0.y) + (f1.x * f1.x + f1.y * f1.y);
         }
-      } while (cur == my_gen);
+      }
     }
   }
-  __syncthreads();
-  if (threadIdx.x < GN_GROUPS * 4) {
-    const int g = threadIdx.x >> 2, sub = threadIdx.x & 3;
-    float ss = 0.f, qq = 0.f;
-    for (int c = sub; c < nchunks; c += 4) {
-      const float* src = partial + (((long long)b * nchunks + c) * GN_GROUPS + g) * 2;
-      float a0, a1;
-      asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(a0) : "l"(src) : "memory");   // bypass stale L1
-      asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(a1) : "l"(src + 1) : "memory");
-      ss += a0;
-      qq += a1;
-    }
 #pragma unroll
-    for (int d = 2; d > 0; d >>= 1) {
-      ss += __shfl_xor_sync(0xffffffffu, ss, d);
-      qq += __shfl_xor_sync(0xffffffffu, qq, d);
-    }
-    if (sub == 0) {
-      const float n = (float)HW * (float)cpg;
-      const float m = ss / n;
-      const float var = fmaxf(qq / n - m * m, 0.f);
-      mean[g] = m;
-      rstd[g] = rsqrtf(var + eps);
-    }
+  for (int d = 16; d > 0; d >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, d);
+    q += __shfl_xor_sync(0xffffffffu, q, d);
+  }
+  const int warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+  if ((threadIdx.x & 31) == 0) {
+    wred[warp][0] = s;
+    wred[warp][1] = q;
   }
   __syncthreads();
-  float sc[8], sh[8];
+  if (threadIdx.x == 0) {
+    float ts = 0.f, tq = 0.f;
+    for (int w = 0; w < nwarps; ++w) {
+      ts += wred[w][0];
+      tq += wred[w][1];
+    }
+    if (k > 1) {
+      const uint32_t slot = smem_u32(&table[rank]);
+      for (int peer = 0; peer < k; ++peer) st_cluster_f32x2(mapa_u32(slot, (uint32_t)peer), ts, tq);
+    } else {
+      table[0] = make_float2(ts, tq);
+    }
+  }
+  if (k > 1) cluster_sync_all();     // release / acquire at cluster scope: the peers' table stores are visible
+  else __syncthreads();
+  if (threadIdx.x == 0) {
+    float ts = 0.f, tq = 0.f;
+    for (int i = 0; i < k; ++i) {
+      ts += table[i].x;
+      tq += table[i].y;
+    }
+    const float n = (float)HW * (float)cpg;
+    const float m = ts / n;
+    stat[0] = m;
+    stat[1] = rsqrtf(fmaxf(tq / n - m * m, 0.f) + eps);
+  }
+  __syncthreads();
+  if (rl >= lanes) return;
+  const float mean = stat[0], rstd = stat[1];
+  float sc[VEC], sh[VEC];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int c = o * 8 + i, g = c / cpg;
-    const float ga = __ldg(gamma + c) * rstd[g];
+  for (int i = 0; i < VEC; ++i) {
+    const int c = g * cpg + v * VEC + i;
+    const float ga = __ldg(gamma + c) * rstd;
     sc[i] = ga;
-    sh[i] = __ldg(beta + c) - mean[g] * ga;
+    sh[i] = __ldg(beta + c) - mean * ga;
   }
-  __nv_bfloat16* yb = y + ((long long)b * HW) * ldy + o * 8;
-#pragma unroll
-  for (int k = 0; k < GN_MAXR; ++k) {
-    const int r = r0 + rl + k * lanes;
-    if (r < r1) {
-      const uint32_t w[4] = {rows[k].x, rows[k].y, rows[k].z, rows[k].w};
-      float v[8];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = unpack16x2<F16>(w[i]);
-        v[2 * i] = f.x * sc[2 * i] + sh[2 * i];
-        v[2 * i + 1] = f.y * sc[2 * i + 1] + sh[2 * i + 1];
-      }
-      if (silu_act) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = silu(v[i]);
-      }
-      uint4 out;
-      out.x = pack16x2<F16>(v[0], v[1]);
-      out.y = pack16x2<F16>(v[2], v[3]);
-      out.z = pack16x2<F16>(v[4], v[5]);
-      out.w = pack16x2<F16>(v[6], v[7]);
-      *reinterpret_cast<uint4*>(yb + (long long)r * ldy) = out;
+  __nv_bfloat16* yb = y + ((long long)b * HW) * ldy + g * cpg + v * VEC;
+  for (int r = r0 + rl; r < r1; r += lanes) {
+    const word_t w = slab[(r - r0) * vpr + v];
+    float o[VEC];
+    if constexpr (VEC == 4) {
+      const float2 f0 = unpack16x2<F16>(w.x), f1 = unpack16x2<F16>(w.y);
+      o[0] = f0.x * sc[0] + sh[0];
+      o[1] = f0.y * sc[1] + sh[1];
+      o[2] = f1.x * sc[2] + sh[2];
+      o[3] = f1.y * sc[3] + sh[3];
+    } else {
+      const float2 f0 = unpack16x2<F16>(w);
+      o[0] = f0.x * sc[0] + sh[0];
+      o[1] = f0.y * sc[1] + sh[1];
     }
+    if (silu_act) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) o[i] = silu(o[i]);
+    }
+    word_t out;
+    if constexpr (VEC == 4) {
+      out.x = pack16x2<F16>(o[0], o[1]);
+      out.y = pack16x2<F16>(o[2], o[3]);
+    } else {
+      out = pack16x2<F16>(o[0], o[1]);
+    }
+    *reinterpret_cast<word_t*>(yb + (long long)r * ldy) = out;
   }
 }
 
@@ -688,34 +686,53 @@ extern "C" int mos_groupnorm_fwd(const void* x, int64_t ldx, int32_t B, int32_t 
   MOS_CHECK_ARG(C % 32 == 0 && C % 8 == 0 && C <= 2560 && ldx % 8 == 0 && ldy % 8 == 0 && ldx >= C && ldy >= C,
                 "mos_groupnorm_fwd: bad C=%d ldx=%lld ldy=%lld", C, (long long)ldx, (long long)ldy);
   const int threads = gn_block_threads(C);
-  const int lanes = threads / (C / 8);
-  // ---- fused single-launch path: grid capped at the co-resident capacity (the kernel contains a grid barrier)
-  static int capacity = 0, use_fused = -1;
-  if (use_fused < 0) {
-    // measured slower than the two-launch path on B200 (grid barrier + 2 blocks/SM): opt-in only
-    const char* e = getenv("MOS_GN_FUSED");
-    use_fused = (e && e[0] == '1') ? 1 : 0;
+  // ---- one-pass path: a cluster of k CTAs per (sample, group) keeps the group's channel slab in shared memory
+  static int two_pass = -1;
+  if (two_pass < 0) {
+    const char* e = getenv("MOS_GN_TWOPASS");
+    two_pass = (e && e[0] == '1') ? 1 : 0;
   }
-  if (use_fused && capacity == 0) {
-    int dev = 0, sms = 0, per_sm = 0;
-    MOS_CHECK_CUDA(cudaGetDevice(&dev));
-    MOS_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    MOS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_fused_kernel<false>, 320, 320 * 16 * sizeof(float)));
-    capacity = sms * (per_sm > 0 ? per_sm : 1);
-  }
-  if (use_fused) {
-    int nchunks = capacity / B;
-    if (nchunks > (int)ceil_div(HW, lanes)) nchunks = (int)ceil_div(HW, lanes);
-    if (nchunks < 1) nchunks = 1;
-    int rows_per_chunk = (int)ceil_div(HW, nchunks);
-    nchunks = (int)ceil_div(HW, rows_per_chunk);
-    const long long need = (long long)B * nchunks * GN_GROUPS * 2 + 64;   // + per-sample ticket counters
-    if (rows_per_chunk <= GN_MAXR * lanes && B <= 32 && need <= partial_capacity_floats && B * nchunks <= capacity) {
-      unsigned int* counters = reinterpret_cast<unsigned int*>(partial + partial_capacity_floats - 64);
-      MOS_CHECK_CUDA(launch_pdl(f16 ? gn_fused_kernel<true> : gn_fused_kernel<false>, dim3(nchunks, B), dim3(threads), threads * 16 * sizeof(float), stream,
-                                reinterpret_cast<const __nv_bfloat16*>(x), (long long)ldx, (int)HW, (int)C,
-                                rows_per_chunk, partial, counters, gamma, beta, eps, (int)silu_act,
-                                reinterpret_cast<__nv_bfloat16*>(y), (long long)ldy));
+  if (!two_pass) {
+    const int cpg = C / GN_GROUPS;
+    const int vec = (cpg % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0) ? 4 : 2;
+    const long long slab = (long long)HW * cpg * 2;
+    int k = 1;
+    while (k < 8 && HW / (2 * k) >= 16 && (slab / k > 48 * 1024 || (long long)B * GN_GROUPS * k < 148)) k *= 2;
+    const int rows_per_cta = (int)ceil_div(HW, k);
+    const size_t smem = (size_t)rows_per_cta * cpg * 2;
+    if (smem <= 200 * 1024 && cpg % 2 == 0 && ldx % 2 == 0 && ldy % 2 == 0) {
+      const int vpr = cpg / vec;
+      const int lanes = 256 / vpr;
+      const int threads = ((lanes * vpr + 31) / 32) * 32;
+      static bool configured = false;
+      if (!configured) {
+        MOS_CHECK_CUDA(cudaFuncSetAttribute(gn_group_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        MOS_CHECK_CUDA(cudaFuncSetAttribute(gn_group_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        MOS_CHECK_CUDA(cudaFuncSetAttribute(gn_group_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        MOS_CHECK_CUDA(cudaFuncSetAttribute(gn_group_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+      }
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3((unsigned)(B * GN_GROUPS * k));
+      cfg.blockDim = dim3((unsigned)threads);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[2];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      attr[1].id = cudaLaunchAttributeClusterDimension;
+      attr[1].val.clusterDim.x = (unsigned)k;
+      attr[1].val.clusterDim.y = 1;
+      attr[1].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = k > 1 ? 2 : 1;
+      const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+      __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
+      auto kern = f16 ? (vec == 4 ? gn_group_kernel<true, 4> : gn_group_kernel<true, 2>)
+                      : (vec == 4 ? gn_group_kernel<false, 4> : gn_group_kernel<false, 2>);
+      MOS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, xp, (long long)ldx, (int)HW, (int)C, rows_per_cta, k, lanes, gamma, beta, eps,
+                                        (int)silu_act, yp, (long long)ldy));
       return MOS_OK;
     }
   }

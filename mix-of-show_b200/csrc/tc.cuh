@@ -271,12 +271,8 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int fmt) {
   return (1u << 4) | (uint32_t(fmt) << 7) | (uint32_t(fmt) << 10) | (uint32_t(N >> 3) << 17) |
          (uint32_t(M >> 4) << 24);
 }
-// same with separate A / B formats (kind::f16 takes f16 and bf16 operands in any combination: fp16 activations against
-// bf16 weights)
-__host__ __device__ constexpr uint32_t make_idesc_ab(int M, int N, int afmt, int bfmt) {
-  return (1u << 4) | (uint32_t(afmt) << 7) | (uint32_t(bfmt) << 10) | (uint32_t(N >> 3) << 17) |
-         (uint32_t(M >> 4) << 24);
-}
+// (The descriptor has separate A / B format fields, but B200 faults - illegal instruction - on a kind::f16 MMA whose two
+// formats differ, measured in round 2; both operands therefore always share `fmt`.)
 
 // ------------------------------------------------------------------ small math helpers
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -287,8 +283,8 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(t);
 }
-// 16-bit activation storage is bf16 (training) or fp16 (inference: 3 more mantissa bits, which is what keeps the
-// classifier-free-guidance difference c - u accurate; profiles/README.md "numerics, round 2"); F16 selects the codec.
+// 16-bit storage (activations and packed weights) is bf16 (training) or fp16 (sampling: 3 more mantissa bits, which is what
+// keeps the classifier-free-guidance difference c - u accurate; profiles/README.md "numerics, round 2"); F16 = the codec.
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   __half2 t = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);

@@ -481,6 +481,24 @@ TEMPLATE_SIMPLE = 'photo of a {}'                      # gradient_fusion.py:19
 NUM_CROSS_ATTENTION_LAYERS = 16
 
 
+_UNET_LORA_SUFFIXES = tuple(f'.{a}.{p}.lora_{d}.weight' for a in ('attn1', 'attn2')
+                            for p in ('to_q', 'to_k', 'to_v', 'to_out.0') for d in ('down', 'up'))
+_TEXT_LORA_SUFFIXES = tuple(f'.self_attn.{p}.lora_{d}.weight' for p in ('q_proj', 'k_proj', 'v_proj', 'out_proj')
+                            for d in ('down', 'up'))
+
+
+def _check_lora_targets(params, path):
+    """The fusion stages cover the reference's default LoRA placement (`where: Attention` / `where: CLIPAttention`, every
+    shipped options/train/EDLoRA/*.yml).  Checkpoints that also tune CLIP's mlp.fc1/fc2 (`where: CLIPEncoderLayer`) or the
+    UNet's ff.net / proj_in / proj_out (`where: Transformer2DModel`) are refused HERE, before any stage has run, instead
+    of failing with a KeyError half way through the fusion."""
+    bad = [k for k in (params.get('unet') or {}) if not k.endswith(_UNET_LORA_SUFFIXES)]
+    bad += [k for k in (params.get('text_encoder') or {}) if not k.endswith(_TEXT_LORA_SUFFIXES)]
+    if bad:
+        raise ValueError(f'{path}: unsupported LoRA target(s) {bad[:3]}{" ..." if len(bad) > 3 else ""}: gradient fusion on '
+                         'the B200 path handles attention-projection LoRA (where: Attention / CLIPAttention) only')
+
+
 def parse_new_concepts(concept_cfg):
     """gradient_fusion.py:262-322: split every concept's `.pth` into embedding / text-encoder / cross-K/V / spatial parts."""
     import json
@@ -493,6 +511,7 @@ def parse_new_concepts(concept_cfg):
     crosskv_matches = ['attn2.to_k.lora', 'attn2.to_v.lora']
     for concept in concept_list:
         model = torch.load(concept['lora_path'], map_location='cpu')['params']
+        _check_lora_targets(model, concept['lora_path'])
         emb = model.get('new_concept_embedding')
         embedding_list.append(emb if emb is not None and len(emb) != 0 else None)
         te = model.get('text_encoder')
@@ -572,8 +591,8 @@ def compose_concepts(concept_cfg, optimize_textenc_iters, optimize_unet_iters, p
                      device='cuda', tokenizer=None, log=print):
     """gradient_fusion.py:750-813 on the B200 path.  `pretrained_model_path`: diffusers-layout directory (unet/,
     text_encoder/, tokenizer/); the fused UNet / text encoder and new_concept_cfg.json are written to
-    `{save_path}/combined_model_{suffix}` (the VAE / scheduler / tokenizer folders of the base model are untouched by the
-    fusion and are not copied here)."""
+    `{save_path}/combined_model_{suffix}` together with the tokenizer that carries the added `<new{k}>` tokens (the VAE /
+    scheduler folders of the base model are untouched by the fusion and are not copied here)."""
     import os
     from mixofshow.pipelines.pipeline_edlora import bind_concept_prompt
     from mixofshow.utils import model_io
@@ -632,7 +651,7 @@ def compose_concepts(concept_cfg, optimize_textenc_iters, optimize_unet_iters, p
         sd.update(new_w)
         unet.load_state_dict(sd)
     out_dir = os.path.join(save_path, f'combined_model_{suffix}')
-    model_io.save_combined_model(out_dir, unet, text_encoder, new_concept_cfg)
+    model_io.save_combined_model(out_dir, unet, text_encoder, new_concept_cfg, tokenizer=tokenizer)
     return out_dir, new_concept_cfg
 
 

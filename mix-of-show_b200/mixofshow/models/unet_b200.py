@@ -180,6 +180,7 @@ class UNet2DConditionModel(nn.Module):
         self._checked = None
         self.merge_lora = False
         self.use_graph = True
+        self.act_dtype = torch.float16      # operand type of the engine (fp16 = the reference's sampling precision)
 
     @classmethod
     def from_pretrained(cls, pretrained_model_name_or_path, subfolder='unet', **unused):
@@ -261,7 +262,7 @@ class UNet2DConditionModel(nn.Module):
         return self._checked
 
     def _engine(self, B, H, W, device, emit_probs, fp):
-        key = (B, H, W, str(device), emit_probs)
+        key = (B, H, W, str(device), emit_probs, self.act_dtype)
         ent = self._engines.get(key)
         if ent is None or ent[0] != fp:
             lora, alpha = self._collect_lora()
@@ -269,7 +270,7 @@ class UNet2DConditionModel(nn.Module):
             eng = UNetEngine(self.state_dict(), B, H, W, lora=lora, lora_alpha=alpha, merge_lora=self.merge_lora,
                              device=device, block_out=tuple(c.block_out_channels), layers=c.layers_per_block,
                              heads=c.attention_head_dim, cross_dim=c.cross_attention_dim, emit_probs=emit_probs,
-                             use_graph=self.use_graph)
+                             use_graph=self.use_graph, act_dtype=self.act_dtype)
             self._engines = {k: v for k, v in self._engines.items() if v[0] == fp}
             self._engines[key] = ent = (fp, eng)
         return ent[1]

@@ -67,6 +67,11 @@ class EDLoRAPipeline:
             from transformers import CLIPTokenizer
             tokenizer = CLIPTokenizer.from_pretrained(pretrained_model_name_or_path, subfolder='tokenizer')
         pipe = cls(vae=vae, text_encoder=text_encoder, tokenizer=tokenizer, unet=unet, scheduler=scheduler)
+        import os
+        if os.path.exists(os.path.join(pretrained_model_name_or_path, 'new_concept_cfg.json')):   # a fused model
+            cfg = model_io.load_new_concept_cfg(pretrained_model_name_or_path)
+            model_io.ensure_concept_tokens(tokenizer, cfg)
+            pipe.set_new_concept_cfg(cfg)
         return pipe.to(device)
 
     def to(self, device):

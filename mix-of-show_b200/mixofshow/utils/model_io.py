@@ -136,13 +136,33 @@ def save_text_encoder(text_encoder, model_dir, subfolder='text_encoder', hf_conf
     _write_weights(folder, TEXT_WEIGHTS[0], sd)
 
 
-def save_combined_model(model_dir, unet, text_encoder, new_concept_cfg):
-    """What gradient_fusion.py:810-813 leaves on disk for the sampling scripts (the VAE / tokenizer / scheduler folders of
-    the base model are copied by the caller: they are untouched by the fusion)."""
+def save_combined_model(model_dir, unet, text_encoder, new_concept_cfg, tokenizer=None):
+    """What gradient_fusion.py:810-813 (`pipe.save_pretrained`) leaves on disk for the sampling scripts: unet/,
+    text_encoder/, new_concept_cfg.json AND the tokenizer that carries the added `<new{k}>` tokens — without it the
+    concept tokens would be BPE-split into ordinary sub-tokens on reload and the learned embedding rows never selected.
+    (The VAE / scheduler folders of the base model are untouched by the fusion; the caller copies them.)"""
     save_unet(unet, model_dir)
     save_text_encoder(text_encoder, model_dir)
+    if tokenizer is not None:
+        tokenizer.save_pretrained(os.path.join(model_dir, 'tokenizer'))
     with open(os.path.join(model_dir, 'new_concept_cfg.json'), 'w') as f:
         json.dump(new_concept_cfg, f)
+
+
+def ensure_concept_tokens(tokenizer, new_concept_cfg):
+    """Loader-side guard for fused models: every `concept_token_names[k]` must map to `concept_token_ids[k]`.  A tokenizer
+    folder copied from the BASE model lacks the added tokens: they are re-added here in id order and the resulting ids
+    are checked against the cfg (raises instead of silently sampling without the concepts)."""
+    pairs = sorted({(i, n) for c in new_concept_cfg.values()
+                    for i, n in zip(c['concept_token_ids'], c['concept_token_names'])})
+    missing = [n for i, n in pairs if tokenizer.convert_tokens_to_ids(n) != i]
+    if missing:
+        tokenizer.add_tokens([n for _, n in pairs if n in set(missing)])
+    bad = [(n, i, tokenizer.convert_tokens_to_ids(n)) for i, n in pairs if tokenizer.convert_tokens_to_ids(n) != i]
+    if bad:
+        raise ValueError(f'tokenizer does not match new_concept_cfg.json (token, expected id, actual id): {bad[:4]} ... '
+                         'load the tokenizer saved next to the fused model')
+    return tokenizer
 
 
 def load_new_concept_cfg(model_dir):

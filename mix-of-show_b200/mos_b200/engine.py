@@ -51,10 +51,11 @@ class UNetEngine:
         """state_dict: diffusers-named fp32 tensors of the UNet.  lora: {f'{module}.lora_down.weight': [r,in],
         f'{module}.lora_up.weight': [out,r]} exactly as EDLoRATrainer.delta_state_dict()['unet'] stores it
         (trainer_edlora.py:371-378); rank <= 4.  batch includes the CFG duplication.  height/width: latent size.
-        act_dtype: 16-bit storage type of every activation.  Sampling uses fp16 against bf16 weights: with classifier-free
-        guidance the scheduler consumes u + g (c - u), so the rounding noise of the two (nearly equal) halves is amplified
-        by g while weight rounding cancels; fp16's 3 extra mantissa bits bring the CFG-7.5 latents from 2.8e-3 to 4.6e-4
-        rel-L2 (tests/numerics_emulation.py, profiles/README.md).  Training keeps bf16 (gradient range)."""
+        act_dtype: 16-bit type of every activation AND of the packed GEMM weights (tcgen05 kind::f16 takes one operand
+        format per MMA).  Sampling uses fp16 - the reference's own sampling precision (README.md:146 torch_dtype=float16):
+        with classifier-free guidance the scheduler consumes u + g (c - u), so the activation rounding noise of the two
+        (nearly equal) halves is amplified by g; fp16's 3 extra mantissa bits bring the CFG-7.5 latents from 2.8e-3 (bf16,
+        round 1) to < 5e-4 rel-L2 (tests/numerics_emulation.py, profiles/README.md).  Training keeps bf16 (gradient range)."""
         assert act_dtype in (F16, BF16)
         self.ACT = act_dtype
         self.dev = torch.device(device)
@@ -133,7 +134,7 @@ class UNetEngine:
                               for t in range(half // 80)]).to(self.dev)
             W = W[perm]
             bias = bias[perm] if bias is not None else None
-        ent['W'] = W.to(BF16).contiguous()
+        ent['W'] = W.to(self.ACT).contiguous()
         ent['bias'] = bias.contiguous() if bias is not None else None
         if any_lora:
             assert len(modules) <= 4
@@ -149,7 +150,7 @@ class UNetEngine:
                 off += w_.shape[0]
             if perm is not None:
                 up = up[perm]
-            ent['lora_down'] = down16.to(BF16).contiguous()
+            ent['lora_down'] = down16.to(self.ACT).contiguous()
             ent['lora_up'] = up.contiguous()
             ent['lora_seg'] = Ws[0].shape[0] if len(modules) > 1 else N
         self.w[key] = ent
@@ -305,7 +306,7 @@ class UNetEngine:
             return
         ops.groupnorm(x, g, b, y, self.gn_partial, B=self.B, HW=HW, C=C, eps=eps, silu=silu, ldx=x.stride(0),
                       ldy=y.stride(0))
-        self.launches += 2
+        self.launches += 1          # one-pass cluster kernel (two launches only on the large-slab fallback)
 
     def layernorm(self, x, key, y, *, M, C):
         g, b = self.w[key]

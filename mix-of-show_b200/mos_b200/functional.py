@@ -8,8 +8,7 @@ import torch
 from . import ops
 from ._lib import MOS_SEG_ROWS, MOS_SEG_TRANSPOSED
 
-BF16 = torch.bfloat16      # weights
-ACT = torch.float16        # activations of the (inference-only) operator path: see mos_b200/engine.py
+ACT = torch.float16        # operand type of the (inference-only) operator path, weights and activations: mos_b200/engine.py
 
 
 def _r(x, m):
@@ -46,7 +45,7 @@ def pack_linears(modules, device):
     N, K = W.shape
     if N % 160 != 0 or K % 64 != 0:
         raise ValueError(f'unsupported projection shape [{N}, {K}]: the sm_100a GEMM needs N % 160 == 0 and K % 64 == 0')
-    ent = {'N': N, 'K': K, 'W': W.to(BF16).contiguous(), 'bias': None}
+    ent = {'N': N, 'K': K, 'W': W.to(ACT).contiguous(), 'bias': None}
     if any(b is not None for b in bs):
         ent['bias'] = torch.cat([b if b is not None else torch.zeros(w.shape[0], device=device)
                                  for b, w in zip(bs, Ws)]).contiguous()
@@ -62,7 +61,7 @@ def pack_linears(modules, device):
                 down16[4 * s:4 * s + r] = d
                 up[off:off + w.shape[0], :r] = u * a
             off += w.shape[0]
-        ent['lora_down'] = down16.to(BF16).contiguous()
+        ent['lora_down'] = down16.to(ACT).contiguous()
         ent['lora_up'] = up.contiguous()
         ent['lora_seg'] = Ws[0].shape[0] if len(modules) > 1 else N
     return ent

@@ -300,13 +300,14 @@ def attention_train(Q, K, Vt, out, lse2, *, batch, heads, head_dim, nq, nk, scal
 
 
 def attention_bwd(Q, K, V, dO, Qt, Kt, dOt, lse2, delta, dq, dk, dv, *, batch, heads, head_dim, nq, nk, scale=None,
-                  gcols=None, pos=None, lddq=None, lddk=None, lddv=None):
+                  gcols=None, pos=None, lddq=None, lddk=None, lddv=None, causal=False):
     scale = head_dim ** -0.5 if scale is None else scale
     check(_lib.lib().mos_attention_bwd(
         ptr(Q), ptr(K), ptr(V), ptr(dO), ptr(Qt), ptr(Kt), ptr(dOt), ptr(lse2), ptr(delta), ptr(gcols), ptr(pos),
         ptr(dq), _i64(dq.stride(-2) if lddq is None else lddq), ptr(dk), _i64(dk.stride(-2) if lddk is None else lddk),
         ptr(dv), _i64(dv.stride(-2) if lddv is None else lddv), _i32(batch), _i32(heads), _i32(head_dim), _i32(nq),
-        _i32(nk), _i32(Qt.shape[-1]), _i32(Kt.shape[-1]), ctypes.c_float(scale), _s()), 'mos_attention_bwd')
+        _i32(nk), _i32(Qt.shape[-1]), _i32(Kt.shape[-1]), ctypes.c_float(scale), _i32(1 if causal else 0), _s()),
+        'mos_attention_bwd')
 
 
 def heads_transpose(src, dst):
@@ -419,11 +420,33 @@ def lora_pack(table_dev, n_modules, alpha):
 
 
 # ----------------------------------------------------------------------------------------------- CLIP text encoder
-def attention_causal(Q, K, Vt, out, *, batch, heads, head_dim, n, scale, ldo=None):
-    """Causal self-attention over one key tile (n <= 128); layouts as `attention`."""
+def attention_causal(Q, K, Vt, out, *, batch, heads, head_dim, n, scale, ldo=None, lse2=None):
+    """Causal self-attention over one key tile (n <= 128); layouts as `attention`; lse2 (optional) is saved for the
+    backward pass."""
     check(_lib.lib().mos_attention_fwd_causal(
         ptr(Q), ptr(K), ptr(Vt), ptr(out), _i64(out.stride(-2) if ldo is None else ldo), _i32(batch), _i32(heads),
-        _i32(head_dim), _i32(n), _i32(Vt.shape[-1]), ctypes.c_float(scale), _s()), 'mos_attention_fwd_causal')
+        _i32(head_dim), _i32(n), _i32(Vt.shape[-1]), ctypes.c_float(scale), ptr(lse2), _s()), 'mos_attention_fwd_causal')
+    return out
+
+
+def quick_gelu_fwd(x, y, *, M, C):
+    check(_lib.lib().mos_quick_gelu_fwd(ptr(x), _i64(x.stride(0)), _i64(M), _i32(C), ptr(y), _i64(y.stride(0)), _s()),
+          'mos_quick_gelu_fwd')
+    return y
+
+
+def quick_gelu_bwd(x, dy, dx, *, M, C):
+    check(_lib.lib().mos_quick_gelu_bwd(ptr(x), _i64(x.stride(0)), ptr(dy), _i64(dy.stride(0)), _i64(M), _i32(C), ptr(dx),
+                                        _i64(dx.stride(0)), _s()), 'mos_quick_gelu_bwd')
+    return dx
+
+
+def clip_embed_bwd(ids, dx, rows, out, *, C, accumulate=False):
+    """out[r, :C] (+)= sum of dx[m, :C] over the positions m whose token id is rows[r] (fp32 [n_rows, C])."""
+    assert ids.dtype == torch.int32 and rows.dtype == torch.int32 and out.dtype == torch.float32
+    check(_lib.lib().mos_clip_embed_bwd(ptr(ids), ptr(dx), _i64(dx.stride(0)), _i64(ids.numel()), _i32(C), ptr(rows),
+                                        _i32(rows.numel()), _i32(1 if accumulate else 0), ptr(out), _s()),
+          'mos_clip_embed_bwd')
     return out
 
 

@@ -46,8 +46,10 @@ def build_model(pretrained_model, device='cuda', tokenizer=None):
     if tokenizer is None:
         from transformers import CLIPTokenizer
         tokenizer = CLIPTokenizer.from_pretrained(pretrained_model, subfolder='tokenizer')
+    new_concept_cfg = model_io.load_new_concept_cfg(pretrained_model)
+    model_io.ensure_concept_tokens(tokenizer, new_concept_cfg)      # the fused model's added `<new{k}>` tokens
     pipe = RegionallyT2IAdapterPipeline(text_encoder=text_encoder, tokenizer=tokenizer, unet=unet).to(device)
-    pipe.set_new_concept_cfg(model_io.load_new_concept_cfg(pretrained_model))
+    pipe.set_new_concept_cfg(new_concept_cfg)
     return pipe
 
 

@@ -32,10 +32,21 @@ class WordTokenizer:
         return added
 
     def convert_tokens_to_ids(self, name):
-        return self.vocab[name]
+        return self.vocab.get(name, 0)         # unknown -> 0 (the unk id), as transformers tokenizers do
 
     def _ids(self, text):
         return [self.BOS] + [self.vocab.get(w, 1 + (sum(map(ord, w)) % 40000)) for w in text.split()] + [self.EOS]
+
+    def save_pretrained(self, path):
+        os.makedirs(path, exist_ok=True)
+        json.dump({'added': sorted(self.vocab, key=self.vocab.get)}, open(os.path.join(path, 'word_tokenizer.json'), 'w'))
+
+    @classmethod
+    def from_pretrained(cls, path):
+        t = cls()
+        for w in json.load(open(os.path.join(path, 'word_tokenizer.json')))['added']:
+            t.add_tokens([w])
+        return t
 
     def __call__(self, text, padding='do_not_pad', max_length=77, truncation=True, return_tensors=None, **kw):
         from types import SimpleNamespace
@@ -132,3 +143,19 @@ def test_compose_concepts_wiring(tmp_path, monkeypatch):
     te = CLIPTextModel.from_pretrained(os.path.join(out_dir, 'text_encoder'))
     assert te.get_input_embeddings().weight.shape[0] == 49408 + 48
     assert json.load(open(os.path.join(out_dir, 'new_concept_cfg.json'))) == new_cfg
+    # ---- fuse -> reload -> tokenize round trip: the saved tokenizer knows the added tokens (a base tokenizer would split
+    # '<new17>' into ordinary sub-tokens and the fused concept would silently be lost at sampling)
+    tok = WordTokenizer.from_pretrained(os.path.join(out_dir, 'tokenizer'))
+    model_io.ensure_concept_tokens(tok, new_cfg)
+    from mixofshow.pipelines.pipeline_edlora import bind_concept_prompt
+    p0 = bind_concept_prompt('photo of a <cat1> <cat2>', new_cfg)
+    ids0 = tok(p0[3], padding='max_length', max_length=77, return_tensors='pt').input_ids[0].tolist()
+    assert new_cfg['<cat1>']['concept_token_ids'][3] in ids0 and new_cfg['<cat2>']['concept_token_ids'][3] in ids0
+    base_tok = WordTokenizer()                                   # the BASE tokenizer: tokens are re-added in id order
+    model_io.ensure_concept_tokens(base_tok, new_cfg)
+    assert base_tok.convert_tokens_to_ids('<new47>') == 49408 + 47
+    shifted = WordTokenizer()
+    shifted.add_tokens(['<other>'])                              # ids no longer line up -> loud failure
+    import pytest
+    with pytest.raises(ValueError):
+        model_io.ensure_concept_tokens(shifted, new_cfg)

@@ -5,7 +5,7 @@ The oracle (oracle/unet.py skeleton + oracle/inject.py RegionProcessor = restate
 the reference's own processor by tests/golden) is plain PyTorch and runs here in fp32 ON THE GPU (TF32 off, the
 attention through the MATH backend) so that the 11 TFLOP of one full-size CFG step take a second instead of a minute.
 
-Tolerances (rel-L2 = ||a-b|| / ||b||): eps <= 1e-2 (bf16 weights x fp16 activations, see tests/test_unet_gpu.py);
+Tolerances (rel-L2 = ||a-b|| / ||b||): eps <= 5e-3 (fp16 operands, see tests/test_unet_gpu.py);
 post-scheduler latents at guidance 7.5 <= 1e-3 (BASELINE.json); multi-step pipeline latents <= 5e-3 per 3 steps.
 """
 import math
@@ -90,7 +90,7 @@ def test_config4_full_size_step(cuda, tag):
     torch.cuda.synchronize()
     e_eps, e_lat = rel_l2(eps, eps_ref), rel_l2(latents, prev_ref)
     print(f'config 4 [{tag}] 768x1536, 3 regions + adapters: eps rel-L2 {e_eps:.3e}, latents (CFG 7.5) rel-L2 {e_lat:.3e}')
-    assert e_eps < 1e-2 and e_lat < 1e-3
+    assert e_eps < 5e-3 and e_lat < 1e-3
 
 
 def _oracle_spatial_weight(feat, base, spec, height, width):
