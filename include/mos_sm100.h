@@ -76,6 +76,8 @@ typedef struct mos_gemm_args {
                            * an activation (Gram products): every load waits for the dependency. */
   int32_t a_dtype;        /* MOS_DT_*: type of A, of the 16-bit outputs (rows, head-split) and of `residual` */
   int32_t w_dtype;        /* MOS_DT_*: type of W and lora_down; must equal a_dtype (one operand format per tcgen05 MMA) */
+  int32_t pair_mode;      /* 0 = library heuristic, 1 = force 2-CTA pair tiles (needs an even number of 128-row tiles),
+                           * 2 = force the 1-CTA kernel (benchmarking) */
 } mos_gemm_args;
 
 int mos_gemm_bf16(const mos_gemm_args* args, void* stream);

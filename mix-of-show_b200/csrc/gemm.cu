@@ -733,12 +733,22 @@ extern "C" int mos_gemm_bf16(const mos_gemm_args* a, void* stream_) {
   p.m_tiles = m_tiles;
   // ---- CTA pairs (tcgen05 cta_group::2): a work item is a 256 x 160 tile of a 2-CTA cluster; needs an even number of
   // 128-row tiles.  MOS_GEMM_PAIR=0 forces the 1-CTA kernel (A/B comparison, profiles/README.md).
-  static int use_pair = -1;
+  static int use_pair = -1, pair_min_kb = 16;
   if (use_pair < 0) {
     const char* e = getenv("MOS_GEMM_PAIR");
-    use_pair = (e && e[0] == '0') ? 0 : 1;
+    use_pair = (e && e[0] == '1') ? 1 : 0;
+    const char* m = getenv("MOS_GEMM_PAIR_MIN_KB");
+    if (m) pair_min_kb = atoi(m);
   }
-  const bool pair = use_pair && (m_tiles % 2 == 0);
+  // Measured on B200 (tools/gemm_shape_bench.py, profiles/README.md "round 2: CTA pairs"): parity-green on every layer shape
+  // of the step, but never faster than the 1-CTA kernel - 29.7 vs 31.7 us on the res-64 3x3 conv, 67.6 vs 66.5 us on the
+  // longest one, +2 us on every short-K projection (two cluster barriers, remote barrier hops) - i.e. the mainloop is not
+  // bound by the bytes a CTA pulls through its own L2 port.  The pair path is therefore OPT-IN (MOS_GEMM_PAIR=1 with at
+  // least MOS_GEMM_PAIR_MIN_KB k-blocks per work item, or mos_gemm_args.pair_mode = 1).
+  const int kb_per_item = (int)ceil_div(p.kb_total, splits);
+  bool pair = use_pair && (m_tiles % 2 == 0) && kb_per_item >= pair_min_kb;
+  if (a->pair_mode == 1) pair = (m_tiles % 2 == 0);
+  else if (a->pair_mode == 2) pair = false;
   p.pair = pair ? 1 : 0;
 
   // ---- tensor maps.  W box: the whole tile (160 rows), or a pair's half: 80 rows, with LoRA (N = 176 = 160 W rows + 16

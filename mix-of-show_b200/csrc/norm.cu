@@ -254,6 +254,9 @@ gn_group_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int HW, int 
   __shared__ float wred[8][2];
   __shared__ float2 table[8];       // per-CTA partial (sum, sumsq), filled by the peers through DSMEM
   __shared__ float stat[2];
+  // Distributed shared memory may only be touched once every CTA of the cluster is known to be running: arrive here, wait
+  // right before the first remote store (the loads and the local reduction in between hide the barrier latency).
+  if (k > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   pdl_wait();
   pdl_launch_dependents();
   const int cpg = C / GN_GROUPS;
@@ -306,6 +309,7 @@ gn_group_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int HW, int 
     wred[warp][1] = q;
   }
   __syncthreads();
+  if (k > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // all peers have started
   if (threadIdx.x == 0) {
     float ts = 0.f, tq = 0.f;
     for (int w = 0; w < nwarps; ++w) {

@@ -29,7 +29,7 @@ class GemmArgs(ctypes.Structure):
         ('seg_ptr', c_vp * 3), ('seg_kind', c_i32 * 3), ('seg_rows_pad', c_i64 * 3),
         ('heads', c_i32), ('head_dim', c_i32), ('dpad', c_i32), ('dv_pad', c_i32),
         ('tokens_per_batch', c_i64), ('accumulate', c_i32), ('w_static', c_i32),
-        ('a_dtype', c_i32), ('w_dtype', c_i32),
+        ('a_dtype', c_i32), ('w_dtype', c_i32), ('pair_mode', c_i32),
     ]
 
 

@@ -30,8 +30,13 @@ def _key(t):
 
 class TrainEngine(UNetEngine):
     def __init__(self, state_dict, batch, height, width, *, lora, lora_alpha=1.0, attn_reg_weight=0.01,
-                 reg_full_identity=True, lr=1e-4, **kw):
+                 reg_full_identity=True, lr=1e-4, state=None, state_offset=0, text_grad=False, **kw):
+        """state / state_offset: a shared dp.FlatTrainState (and the offset of the UNet-LoRA block in it) when the text
+        encoder is trained in the same step (clip_train_engine.CLIPTrainEngine); None = a private state.
+        text_grad: also produce d loss / d(text embeddings) into `self.d_ehs` (bf16 [16 * B * 77, 800], layer-major rows =
+        the layout of `in_ehs`; the first 768 columns are the gradient) for the text encoder's backward."""
         self.use_train_graph = bool(kw.pop('use_graph', True))
+        self._ext_state, self._state_off, self.text_grad = state, int(state_offset), bool(text_grad)
         self.tgraph = None
         self._tgraphs = {}
         self._accumulate = False
@@ -96,10 +101,14 @@ class TrainEngine(UNetEngine):
             N = lora[f'{m}.lora_up.weight'].shape[0]
             sizes.append((K, N))
         total = sum(4 * (k + n) for k, n in sizes)
-        self.state = FlatTrainState(0, self.cross_dim, 0, total, lrs=(1e-3, 1e-5, lr), device=self.dev)
+        if self._ext_state is not None:
+            self.state = self._ext_state
+            assert self._state_off + total <= self.state.n, 'shared flat state too small for the UNet LoRA block'
+        else:
+            self.state = FlatTrainState(0, self.cross_dim, 0, total, lrs=(1e-3, 1e-5, lr), device=self.dev)
         self.lora_views = {}
         rows = []
-        off = 0
+        off = self._state_off
         keep = []
         for m, (K, N) in zip(mods, sizes):
             D = self.state.params[off:off + 4 * K].view(4, K)
@@ -121,12 +130,16 @@ class TrainEngine(UNetEngine):
             fdown = ent['lora_down'].data_ptr() + 4 * seg * K * 2
             fup = ent['lora_up'].data_ptr() + row_off * 4 * 4
             bdown = bup = 0
-            if not (m.endswith('attn2.to_k') or m.endswith('attn2.to_v')):   # no d(text embedding) this round
+            is_kv = m.endswith('attn2.to_k') or m.endswith('attn2.to_v')
+            if not is_kv or self.text_grad:
+                # text K / V projections: their input gradient d(ehs) is only needed when the text encoder trains; its
+                # width 768 is padded to the GEMM's 160-column tiles (800, zero rows)
+                kp = _r(K, 160) if is_kv else K
                 bd = torch.zeros(16, N, device=self.dev, dtype=BF16)
-                bu = torch.zeros(K, 4, device=self.dev)
+                bu = torch.zeros(kp, 4, device=self.dev)
                 keep += [bd, bu]
                 bdown, bup = bd.data_ptr(), bu.data_ptr()
-                self.wb[m] = {'N': K, 'K': N, 'bias': None, 'lora_down': bd, 'lora_up': bu, 'lora_seg': K}
+                self.wb[m] = {'N': kp, 'K': N, 'bias': None, 'lora_down': bd, 'lora_up': bu, 'lora_seg': kp}
             rows.append([D.data_ptr(), U.data_ptr(), K, N, fdown, fup, bdown, bup])
         self._lora_keep = keep
         self.lora_table = torch.tensor(rows, dtype=torch.int64, device=self.dev)
@@ -171,7 +184,16 @@ class TrainEngine(UNetEngine):
             key, seg = self._fwd_slot(m)
             W = self.w[key]['W']
             N = self.lora_views[m][5]
-            self.wb[m]['W'] = W[seg * N:(seg + 1) * N].t().contiguous()
+            Wt = W[seg * N:(seg + 1) * N].t()
+            if self.wb[m]['N'] != Wt.shape[0]:                 # padded output width (text K / V: 768 -> 800)
+                Wp = torch.zeros(self.wb[m]['N'], N, device=self.dev, dtype=W.dtype)
+                Wp[:Wt.shape[0]] = Wt
+                Wt = Wp
+            self.wb[m]['W'] = Wt.contiguous()
+        self.d_ehs = None
+        if self.text_grad:
+            self.d_ehs = torch.zeros(len(self.xattn_names) * self.B * self.n_text, _r(self.cross_dim, 160), device=self.dev,
+                                     dtype=BF16)
 
     # ------------------------------------------------------------------------------------------ buffers
     def tb(self, tag, shape, dtype=BF16, zero=False):
@@ -361,6 +383,10 @@ class TrainEngine(UNetEngine):
         self._lora_grad(a2 + 'to_q', S['ln2'], dq, M)
         self._lora_grad(a2 + 'to_k', ehs, dkv[:, :C], B * T, lddy=2 * C)
         self._lora_grad(a2 + 'to_v', ehs, dkv[:, C:], B * T, lddy=2 * C)
+        if self.d_ehs is not None:      # d(text embedding of layer xidx) = dK (W_k + a U_k D_k) + dV (W_v + a U_v D_v)
+            dst = self.d_ehs[xidx * B * T:(xidx + 1) * B * T]
+            self.gemm(dkv[:, :C], self.wb[a2 + 'to_k'], dst, M=B * T, lda=2 * C)
+            self.gemm(dkv[:, C:], self.wb[a2 + 'to_v'], dst, M=B * T, lda=2 * C, residual=dst)
         self.gemm(dq, self.wb[a2 + 'to_q'], d_ln, M=M)
         d_t1 = self.buf('g_t1', (M, C))
         ops.layernorm_bwd(S['t1'], d_ln, self.w[tbn + '.norm2'][0], d_t1, M=M, C=C, add=d_t2)
@@ -560,14 +586,25 @@ class TrainEngine(UNetEngine):
         self._leftover = grads      # only the conv_in output gradient remains (the latents need no gradient)
 
     # ------------------------------------------------------------------------------------------ public API
+    def attach_text_engine(self, text_engine):
+        """Train the text encoder in the same (captured) step: `text_engine` (clip_train_engine.CLIPTrainEngine over
+        16 * B layer-major sequences) writes its last hidden state straight into `in_ehs` before the UNet forward and
+        consumes `d_ehs` after the UNet backward.  Needs text_grad=True."""
+        assert self.text_grad and text_engine.n_seq == len(self.xattn_names) * self.B
+        self.text = text_engine
+        self._tgraphs = {}
+
     def forward_backward(self, latents, noise, timesteps, ehs_layers, masks, loss_mask=None, token_pos=None,
-                         accumulate=False):
+                         accumulate=False, text_ids=None):
         """One forward + loss + backward.  latents (x0) / noise fp32 [B,4,H,W]; timesteps int [B]; ehs_layers bf16
         [16,B,77,768]; masks / loss_mask [B,1,H,W] (trainer_edlora.py:246-252); token_pos: B pairs of concept-token
         positions (:270-279).  Returns the device tensor [total loss, attention loss]."""
         self.t_i32.copy_(timesteps.to(self.dev, torch.int32))
         self.in_t.copy_(timesteps.to(self.dev, F32))
-        self.in_ehs.copy_(ehs_layers)
+        if getattr(self, 'text', None) is not None:
+            self.text.set_ids(text_ids)                              # layer-major [16 * B, 77] token ids
+        else:
+            self.in_ehs.copy_(ehs_layers)
         self.target.copy_(noise)                                     # prediction_type 'epsilon' (:241-242)
         self.masks.copy_(masks)
         self.loss_mask.copy_(masks if loss_mask is None else loss_mask)
@@ -600,10 +637,15 @@ class TrainEngine(UNetEngine):
         return self.loss_out
 
     def _step(self):
+        text = getattr(self, 'text', None)
+        if text is not None:          # text encoder forward: last hidden states -> in_ehs (same layout, no copy)
+            text.forward_train(out=self.in_ehs.view(-1, self.cross_dim))
         ops.add_noise(self.x0, self.target, self.t_i32, self.alphas_cumprod, self.in_latents)
         self._run_train()
         self._loss()
         self._backward()
+        if text is not None:          # ... and its backward from d(in_ehs)
+            text.backward(self.d_ehs, accumulate=self._accumulate)
 
     def optimizer_step(self, grad_scale=1.0):
         from .dp import optimizer_step

@@ -135,7 +135,7 @@ def region_rewrite(global_out, query, region_kv, boxes, height, width, scale):
     Returns the rewritten hidden state (regional :32-86 with replace_ratio = 1.0)."""
     n = query.shape[1]
     fh, fw = region_feat_size(height, width, n)
-    count = torch.from_numpy(region_count_mask(boxes, fh, fw))
+    count = torch.from_numpy(region_count_mask(boxes, fh, fw)).to(query.device)   # (device placement only)
     q = query.reshape(query.shape[0], fh, fw, -1)
     out = global_out.reshape(global_out.shape[0], fh, fw, -1).clone()
     out[:, count != 0, :] = 0

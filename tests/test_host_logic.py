@@ -33,22 +33,22 @@ def test_engine_packing_on_cpu():
     assert ent['lora_seg'] == 320
     # fused q|k|v weight rows and LoRA rows land in the right segments
     wq = sd[tb + '.attn1.to_q.weight']
-    assert torch.equal(ent['W'][:320].float(), wq.to(torch.bfloat16).float())
+    assert torch.equal(ent['W'][:320].float(), wq.to(eng.ACT).float())
     dv = lora[tb + '.attn1.to_v.lora_down.weight']
-    assert torch.equal(ent['lora_down'][8:12].float(), dv.to(torch.bfloat16).float())
+    assert torch.equal(ent['lora_down'][8:12].float(), dv.to(eng.ACT).float())
     assert torch.all(ent['lora_down'][12:] == 0)
     uk = lora[tb + '.attn1.to_k.lora_up.weight']
     assert torch.allclose(ent['lora_up'][320:640], uk * 0.5)
     # GEGLU interleave: tile t = [a rows 80t.. | gate rows 1280+80t..]
     ff = eng.w[tb + '.ff1']
     w = sd[tb + '.ff.net.0.proj.weight']
-    assert torch.equal(ff['W'][0:80].float(), w[0:80].to(torch.bfloat16).float())
-    assert torch.equal(ff['W'][80:160].float(), w[1280:1360].to(torch.bfloat16).float())
-    assert torch.equal(ff['W'][160:240].float(), w[80:160].to(torch.bfloat16).float())
+    assert torch.equal(ff['W'][0:80].float(), w[0:80].to(eng.ACT).float())
+    assert torch.equal(ff['W'][80:160].float(), w[1280:1360].to(eng.ACT).float())
+    assert torch.equal(ff['W'][160:240].float(), w[80:160].to(eng.ACT).float())
     # conv weights are tap-major [Cout, (kh, kw, cin)]
     c1 = eng.w['down_blocks.0.resnets.0.conv1']['W']
     wc = sd['down_blocks.0.resnets.0.conv1.weight']
-    assert torch.equal(c1[:, 320:640].float(), wc[:, :, 0, 1].to(torch.bfloat16).float())
+    assert torch.equal(c1[:, 320:640].float(), wc[:, :, 0, 1].to(eng.ACT).float())
     # merged mode == W + alpha * up @ down (convert_edlora_to_diffusers.py:67-73)
     eng_m = UNetEngine(sd, 2, 16, 16, lora=lora, lora_alpha=0.5, merge_lora=True, device='cpu',
                        block_out=ou.TINY['block_out_channels'], layers=1)
@@ -56,7 +56,7 @@ def test_engine_packing_on_cpu():
     assert 'lora_down' not in em
     ref = er.merge_lora_weight(sd[tb + '.attn2.to_q.weight'], lora[tb + '.attn2.to_q.lora_down.weight'],
                                lora[tb + '.attn2.to_q.lora_up.weight'], 0.5)
-    assert torch.equal(em['W'].float(), ref.to(torch.bfloat16).float())
+    assert torch.equal(em['W'].float(), ref.to(eng.ACT).float())
 
 
 def test_concat_slots_cover_the_unet_skip_wiring():
@@ -120,13 +120,13 @@ def test_train_loop_host_logic():
     assert te.linear_lr(1e-4, 0, 250) == 1e-4
     assert te.linear_lr(1e-4, 125, 250) == pytest.approx(5e-5)
     assert te.linear_lr(1e-4, 250, 250) == 0.0 and te.linear_lr(1e-4, 300, 250) == 0.0
-    from mixofshow.pipelines.trainer_edlora import EDLoRATrainer
+    from mixofshow.pipelines.trainer_edlora import UNetLoRATrainer
     cfg = {'text_embedding': {'enable_tuning': True, 'lr': 1e-3}, 'text_encoder': {'enable_tuning': False},
            'unet': {'enable_tuning': True, 'lr': 1e-4, 'lora_cfg': {'rank': 4, 'alpha': 1.0, 'where': 'Attention'}}}
     with pytest.raises(NotImplementedError):
-        EDLoRATrainer({}, 2, finetune_cfg=cfg)
+        UNetLoRATrainer({}, 2, finetune_cfg=cfg)
     with pytest.raises(ValueError):
-        EDLoRATrainer({}, 2, finetune_cfg=None)
+        UNetLoRATrainer({}, 2, finetune_cfg=None)
 
 
 def test_clip_engine_packing_on_cpu():

@@ -33,7 +33,7 @@ def _setup(reg_weight, full_identity, seed=0):
     x0 = torch.randn(B, 4, H, H, generator=g)
     noise = torch.randn(B, 4, H, H, generator=g)
     t = torch.tensor([130, 811])
-    ehs = torch.randn(B, n_layers, 77, 768, generator=g).to(torch.bfloat16).float()
+    ehs = torch.randn(B, n_layers, 77, 768, generator=g).to(torch.bfloat16).float().requires_grad_(True)
     masks = (torch.rand(B, 1, H, H, generator=g) > 0.5).float()
     masks[:, :, 4:9, 4:9] = 1.0
     masks[:, :, 0, 0] = 0.0
@@ -42,7 +42,9 @@ def _setup(reg_weight, full_identity, seed=0):
     loss, pred, attn = train_ref.train_loss(ref, ctl, noisy, t, ehs, noise, masks, masks, pos,
                                             reg_full_identity=full_identity, attn_reg_weight=reg_weight)
     loss.backward()
+    ehs_grad, ehs = ehs.grad.detach(), ehs.detach()
     return dict(ref=ref, lora=lora, leaves=leaves, alpha=alpha, n_layers=n_layers, x0=x0, noise=noise, t=t, ehs=ehs,
+                ehs_grad=ehs_grad,
                 masks=masks, pos=pos, loss=loss.detach(), pred=pred.detach(), attn=attn)
 
 
@@ -177,14 +179,14 @@ def test_train_step_full_sd15_topology(cuda):
 
 
 def _tiny_trainer(reg=0.01, lr=1e-3, seed=0, lora_state=None):
-    from mixofshow.pipelines.trainer_edlora import EDLoRATrainer
+    from mixofshow.pipelines.trainer_edlora import UNetLoRATrainer
     from oracle import unet as ou
     ref = ou.build_unet(0, ou.TINY)
     cfg = {'text_embedding': {'enable_tuning': False}, 'text_encoder': {'enable_tuning': False},
            'unet': {'enable_tuning': True, 'lr': lr, 'lora_cfg': {'rank': 4, 'alpha': 1.0, 'where': 'Attention'}}}
     concept = {'<TOK>': {'concept_token_ids': list(range(49408, 49440)),
                          'concept_token_names': [f'<new{i}>' for i in range(32)]}}
-    tr = EDLoRATrainer({k: v.detach() for k, v in ref.state_dict().items()}, 2, new_concept_cfg=concept,
+    tr = UNetLoRATrainer({k: v.detach() for k, v in ref.state_dict().items()}, 2, new_concept_cfg=concept,
                        finetune_cfg=cfg, attn_reg_weight=reg, latent_size=(16, 16), seed=seed, lora_state=lora_state,
                        unet_topology=dict(block_out=ou.TINY['block_out_channels'], layers=ou.TINY['layers_per_block']))
     return tr, ref
@@ -256,3 +258,29 @@ def test_gradient_accumulation(cuda):
     tr(b1['latents'], b1['encoder_hidden_states'], b1['masks'], b1['img_masks'], **kw)
     tr(b2['latents'], b2['encoder_hidden_states'], b2['masks'], b2['img_masks'], accumulate=True, **kw)   # graph replay
     assert rel_l2(tr.engine.state.grads[:n], g1 + g2) < 1e-6
+
+
+@pytest.mark.parametrize('reg_weight', [None, 0.05])
+def test_text_embedding_gradient(cuda, reg_weight):
+    """d loss / d(encoder_hidden_states) out of the UNet backward ("ehs ... with grad"): the input
+    gradient of the 16 text K / V projections (incl. their LoRA term), laid out like `in_ehs` so that it is the text
+    encoder's output gradient.  vs autograd on the fp32 oracle; bf16 operands: rel-L2 <= 3e-2, cosine >= 0.999."""
+    from mos_b200.engine import ehs_to_layer_major
+    from mos_b200.train_engine import TrainEngine
+    from oracle import unet as ou
+    S = _setup(reg_weight, True)
+    eng = TrainEngine({k: v.detach() for k, v in S['ref'].state_dict().items()}, 2, 16, 16, lora=S['lora'],
+                      lora_alpha=S['alpha'], attn_reg_weight=reg_weight, reg_full_identity=True, text_grad=True,
+                      block_out=ou.TINY['block_out_channels'], layers=ou.TINY['layers_per_block'])
+    eng.forward_backward(S['x0'].cuda(), S['noise'].cuda(), S['t'].cuda(),
+                         ehs_to_layer_major(S['ehs'].cuda(), S['n_layers'], torch.bfloat16), S['masks'].cuda(),
+                         token_pos=S['pos'])
+    torch.cuda.synchronize()
+    nl = S['n_layers']
+    got = eng.d_ehs[:, :768].float().view(nl, 2, 77, 768).cpu()
+    ref = S['ehs_grad'].permute(1, 0, 2, 3)
+    e = rel_l2(got, ref)
+    cos = torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0).item()
+    print(f'[reg={reg_weight}] d(ehs): rel-L2 {e:.3e}, cosine {cos:.5f}')
+    assert eng.d_ehs[:, 768:].abs().max().item() == 0.0
+    assert e < 3e-2 and cos > 0.999

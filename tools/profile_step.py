@@ -22,7 +22,7 @@ ap.add_argument('--width', type=int, default=64)
 args = ap.parse_args()
 from mos_b200.engine import UNetEngine, ehs_to_layer_major  # noqa: E402
 
-unet, sd, lora, lat, ehs, cfg = bench.build_workload(args.tiny)
+sd, lora, lat, ehs, cfg = bench.build_workload(args.tiny)
 kw = dict(block_out=cfg['block_out_channels'], layers=cfg['layers_per_block']) if cfg else {}
 eng = UNetEngine(sd, 2, args.height, args.width, lora=lora, merge_lora=args.merged, use_graph=False, **kw)
 nx = len(eng.xattn_names)
