@@ -141,8 +141,10 @@ int mos_conv_out(const void* x, int32_t B, int32_t H, int32_t W, int32_t C, cons
 
 /* Upsample2D nearest x2: NHWC bf16 [B, H, W, ldx] -> contiguous [B, 2H, 2W, C]. */
 int mos_upsample2x(const void* x, int64_t ldx, int32_t B, int32_t H, int32_t W, int32_t C, void* y, void* stream);
-/* Downsample2D (3x3, stride 2, pad 1) im2col: NHWC bf16 -> [B*H/2*W/2, 9*C] for mos_gemm_bf16. */
-int mos_im2col_s2(const void* x, int64_t ldx, int32_t B, int32_t H, int32_t W, int32_t C, void* col, void* stream);
+/* Downsample2D (3x3, stride 2) im2col: NHWC 16-bit -> [B*H/2*W/2, 9*C] for mos_gemm_bf16.  pad = 1: symmetric padding 1
+ * (UNet Downsample2D); pad = 0: the VAE encoder's variant (F.pad (0,1,0,1) then no padding: taps start at 2*ho). */
+int mos_im2col_s2(const void* x, int64_t ldx, int32_t B, int32_t H, int32_t W, int32_t C, int32_t pad, void* col,
+                  void* stream);
 /* x[m, :C] += r[m, :C] (T2I-Adapter residuals, pipeline_regionally_t2iadapter.py:565). */
 int mos_add_rows(void* x, int64_t ldx, const void* r, int64_t ldr, int64_t M, int32_t C, int32_t act_dtype,
                  void* stream);
@@ -167,6 +169,22 @@ int mos_quick_gelu_bwd(const void* x, int64_t ldx, const void* dy, int64_t lddy,
                        int64_t lddx, void* stream);
 int mos_clip_embed_bwd(const int32_t* ids, const void* dx, int64_t ld, int64_t M, int32_t C, const int32_t* rows,
                        int32_t n_rows, int32_t accumulate, float* out, void* stream);
+
+/* ---- VAE (AutoencoderKL; SURVEY.md 8f rank 2: `vae.encode(images).latent_dist.sample() * 0.18215` trainer_edlora.py:203-204,
+ * `vae.decode(latents / 0.18215)` pipeline_edlora.py:303-313).  Convolutions / projections / GroupNorm reuse mos_gemm_bf16,
+ * mos_groupnorm_fwd, mos_conv_in / mos_conv_out, mos_upsample2x, mos_im2col_s2(pad = 0); the single-head d = 512 attention
+ * of the mid block is two GEMMs around mos_softmax_rows. */
+/* out[r, :cols] = softmax(scale * S[r, :cols]) as 16-bit; S fp32 [rows, lds]. */
+int mos_softmax_rows(const float* S, int64_t lds, int64_t rows, int32_t cols, float scale, void* out, int64_t ldo,
+                     int32_t act_dtype, void* stream);
+/* fp32 NCHW 1x1 convolution with <= 8 channels (post_quant_conv): y[b,o,p] = bias[o] + sum_c w[o,c] x[b,c,p]. */
+int mos_conv1x1_nchw(const float* x, int32_t B, int32_t Cin, int64_t HW, const float* w, const float* bias, int32_t Cout,
+                     float* y, void* stream);
+/* encoder tail: h 16-bit NHWC [B*HW, ldh] (2L moment channels) -> quant_conv (w [2L,2L], bias) -> mean, logvar (clamped to
+ * [-30, 20]) fp32 NCHW [B, L, HW]; with `noise` (standard normal, same layout): latents = scaling (mean + exp(logvar/2) noise). */
+int mos_vae_moments(const void* h, int64_t ldh, int32_t B, int64_t HW, int32_t L, const float* w, const float* bias,
+                    float* mean, float* logvar, const float* noise, float scaling, float* latents, int32_t act_dtype,
+                    void* stream);
 
 /* One fused kernel for mixofshow/pipelines/pipeline_edlora.py:273-290: classifier-free-guidance combine,
  * DPM-Solver++(2M) data-prediction update and re-duplication of the latents for the next UNet call.

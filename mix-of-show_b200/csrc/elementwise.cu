@@ -184,7 +184,7 @@ __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, long long
 }
 
 // col[(b,ho,wo), tap*C + c] = x[b, 2ho+kh-1, 2wo+kw-1, c] (zero outside): Downsample2D conv 3x3 / stride 2 / pad 1
-__global__ void im2col_s2_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int B, int H, int W, int C,
+__global__ void im2col_s2_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int B, int H, int W, int C, int pad,
                                  __nv_bfloat16* __restrict__ col) {
   pdl_wait();
   pdl_launch_dependents();
@@ -199,7 +199,7 @@ __global__ void im2col_s2_kernel(const __nv_bfloat16* __restrict__ x, long long 
   const int wo = (int)(pix % Wo);
   const int ho = (int)((pix / Wo) % Ho);
   const int b = (int)(pix / ((long long)Wo * Ho));
-  const int hh = 2 * ho + tap / 3 - 1, ww = 2 * wo + tap % 3 - 1;
+  const int hh = 2 * ho + tap / 3 - pad, ww = 2 * wo + tap % 3 - pad;   // pad 1: UNet Downsample2D; 0: VAE (pad right / bottom)
   uint4 u = make_uint4(0, 0, 0, 0);
   if (hh >= 0 && hh < H && ww >= 0 && ww < W)
     u = __ldg(reinterpret_cast<const uint4*>(x + (((long long)b * H + hh) * W + ww) * ldx + o * 8));
@@ -330,6 +330,94 @@ __global__ void clip_embed_bwd_kernel(const int* __restrict__ ids, const __nv_bf
     for (long long m = 0; m < M; ++m)
       if (__ldg(ids + m) == tok) acc += __bfloat162float(dx[m * ld + c]);
     out[(long long)blockIdx.x * C + c] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------- VAE glue (AutoencoderKL)
+// Row softmax of fp32 logits (single-head d = 512 attention of the VAE mid block, computed as two tcgen05 GEMMs around this
+// kernel): out[r, c] = softmax_c(scale * S[r, c]) for c < cols, as 16-bit.  One warp per row, two passes over the row
+// (it is L2 resident: the producing GEMM has just written it).
+template <bool F16>
+__global__ void softmax_rows_kernel(const float* __restrict__ S, long long lds, long long rows, int cols, float scale_log2,
+                                    __nv_bfloat16* __restrict__ out, long long ldo) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float* row = S + r * lds;
+  float m = -INFINITY;
+  for (int c = lane * 4; c < cols; c += 128) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(row + c));
+    m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+  const float mm = m * scale_log2;
+  float sum = 0.f;
+  for (int c = lane * 4; c < cols; c += 128) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(row + c));
+    sum += exp2f(v.x * scale_log2 - mm) + exp2f(v.y * scale_log2 - mm) + exp2f(v.z * scale_log2 - mm) +
+           exp2f(v.w * scale_log2 - mm);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+  const float inv = 1.0f / sum;
+  __nv_bfloat16* orow = out + r * ldo;
+  for (int c = lane * 4; c < cols; c += 128) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(row + c));
+    uint2 o;
+    o.x = pack16x2<F16>(exp2f(v.x * scale_log2 - mm) * inv, exp2f(v.y * scale_log2 - mm) * inv);
+    o.y = pack16x2<F16>(exp2f(v.z * scale_log2 - mm) * inv, exp2f(v.w * scale_log2 - mm) * inv);
+    *reinterpret_cast<uint2*>(orow + c) = o;
+  }
+}
+
+// out[b, o, p] = bias[o] + sum_c W[o, c] x[b, c, p]   (fp32 NCHW, <= 8 channels: post_quant_conv of the VAE decoder)
+__global__ void conv1x1_nchw_kernel(const float* __restrict__ x, int B, int Cin, long long HW, const float* __restrict__ w,
+                                    const float* __restrict__ bias, int Cout, float* __restrict__ y) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * HW) return;
+  const int b = (int)(idx / HW);
+  const long long p = idx - (long long)b * HW;
+  float xv[8];
+  for (int c = 0; c < Cin; ++c) xv[c] = __ldg(x + ((long long)b * Cin + c) * HW + p);
+  for (int o = 0; o < Cout; ++o) {
+    float acc = __ldg(bias + o);
+    for (int c = 0; c < Cin; ++c) acc += __ldg(w + o * Cin + c) * xv[c];
+    y[((long long)b * Cout + o) * HW + p] = acc;
+  }
+}
+
+// Encoder tail: h = 16-bit NHWC [B*HW, ldh] holding the 2L "moments" channels of encoder.conv_out; quant_conv (1x1, 2L x 2L)
+// is applied here, then mean / logvar (clamped to [-30, 20]) are written as fp32 NCHW [B, L, HW] and, when a standard
+// normal draw `noise` is given, latents = scaling * (mean + exp(0.5 logvar) * noise)   (trainer_edlora.py:203-204).
+template <bool F16>
+__global__ void vae_moments_kernel(const __nv_bfloat16* __restrict__ h, long long ldh, int B, long long HW, int L,
+                                   const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ mean,
+                                   float* __restrict__ logvar, const float* __restrict__ noise, float scaling,
+                                   float* __restrict__ latents) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * HW) return;
+  const int b = (int)(idx / HW);
+  const long long p = idx - (long long)b * HW;
+  float xv[8], mo[8];
+  for (int c = 0; c < 2 * L; ++c) xv[c] = ld16<F16>(h + idx * ldh + c);
+  for (int o = 0; o < 2 * L; ++o) {
+    float acc = __ldg(bias + o);
+    for (int c = 0; c < 2 * L; ++c) acc += __ldg(w + o * 2 * L + c) * xv[c];
+    mo[o] = acc;
+  }
+  for (int c = 0; c < L; ++c) {
+    const float mu = mo[c], lv = fminf(fmaxf(mo[L + c], -30.0f), 20.0f);
+    const long long off = ((long long)b * L + c) * HW + p;
+    mean[off] = mu;
+    logvar[off] = lv;
+    if (noise != nullptr) latents[off] = scaling * (mu + __expf(0.5f * lv) * __ldg(noise + off));
   }
 }
 
@@ -474,12 +562,13 @@ extern "C" int mos_upsample2x(const void* x, int64_t ldx, int32_t B, int32_t H, 
   return MOS_OK;
 }
 
-extern "C" int mos_im2col_s2(const void* x, int64_t ldx, int32_t B, int32_t H, int32_t W, int32_t C, void* col,
+extern "C" int mos_im2col_s2(const void* x, int64_t ldx, int32_t B, int32_t H, int32_t W, int32_t C, int32_t pad, void* col,
                              void* stream) {
-  MOS_CHECK_ARG(x && col && C % 8 == 0 && ldx % 8 == 0 && H % 2 == 0 && W % 2 == 0, "mos_im2col_s2: bad arguments");
+  MOS_CHECK_ARG(x && col && C % 8 == 0 && ldx % 8 == 0 && H % 2 == 0 && W % 2 == 0 && (pad == 0 || pad == 1),
+                "mos_im2col_s2: bad arguments");
   long long total = (long long)B * (H / 2) * (W / 2) * 9 * (C / 8);
   MOS_CHECK_CUDA(launch_pdl(im2col_s2_kernel, dim3(nblk(total, 256)), dim3(256), 0, STREAM(stream), reinterpret_cast<const __nv_bfloat16*>(x), ldx, B, H,
-                                                                 W, C, reinterpret_cast<__nv_bfloat16*>(col)));
+                                                                 W, C, (int)pad, reinterpret_cast<__nv_bfloat16*>(col)));
   return MOS_OK;
 }
 
@@ -538,6 +627,40 @@ extern "C" int mos_clip_embed_bwd(const int32_t* ids, const void* dx, int64_t ld
   MOS_CHECK_CUDA(launch_pdl(clip_embed_bwd_kernel, dim3((unsigned)n_rows), dim3(256), 0, STREAM(stream),
                             reinterpret_cast<const int*>(ids), reinterpret_cast<const __nv_bfloat16*>(dx), (long long)ld,
                             (long long)M, (int)C, reinterpret_cast<const int*>(rows), (int)accumulate, out));
+  return MOS_OK;
+}
+
+extern "C" int mos_softmax_rows(const float* S, int64_t lds, int64_t rows, int32_t cols, float scale, void* out, int64_t ldo,
+                                int32_t act_dtype, void* stream) {
+  MOS_CHECK_ARG(S && out && rows > 0 && cols > 0 && cols % 4 == 0 && lds % 4 == 0 && lds >= cols && ldo % 4 == 0 && ldo >= cols,
+                "mos_softmax_rows: bad arguments (cols, lds, ldo must be multiples of 4)");
+  MOS_CHECK_DTYPE(act_dtype, "mos_softmax_rows");
+  const int warps = 8;
+  MOS_CHECK_CUDA(launch_pdl(act_dtype ? softmax_rows_kernel<true> : softmax_rows_kernel<false>, dim3(nblk(rows, warps)),
+                            dim3(warps * 32), 0, STREAM(stream), S, (long long)lds, (long long)rows, (int)cols,
+                            scale * 1.4426950408889634f, reinterpret_cast<__nv_bfloat16*>(out), (long long)ldo));
+  return MOS_OK;
+}
+
+extern "C" int mos_conv1x1_nchw(const float* x, int32_t B, int32_t Cin, int64_t HW, const float* w, const float* bias,
+                                int32_t Cout, float* y, void* stream) {
+  MOS_CHECK_ARG(x && w && bias && y && B > 0 && HW > 0 && Cin >= 1 && Cin <= 8 && Cout >= 1 && Cout <= 8,
+                "mos_conv1x1_nchw: bad arguments (at most 8 channels)");
+  MOS_CHECK_CUDA(launch_pdl(conv1x1_nchw_kernel, dim3(nblk((long long)B * HW, 256)), dim3(256), 0, STREAM(stream), x, (int)B,
+                            (int)Cin, (long long)HW, w, bias, (int)Cout, y));
+  return MOS_OK;
+}
+
+extern "C" int mos_vae_moments(const void* h, int64_t ldh, int32_t B, int64_t HW, int32_t L, const float* w, const float* bias,
+                               float* mean, float* logvar, const float* noise, float scaling, float* latents,
+                               int32_t act_dtype, void* stream) {
+  MOS_CHECK_ARG(h && w && bias && mean && logvar && B > 0 && HW > 0 && L >= 1 && L <= 4 && ldh >= 2 * L && (!noise == !latents),
+                "mos_vae_moments: bad arguments");
+  MOS_CHECK_DTYPE(act_dtype, "mos_vae_moments");
+  MOS_CHECK_CUDA(launch_pdl(act_dtype ? vae_moments_kernel<true> : vae_moments_kernel<false>,
+                            dim3(nblk((long long)B * HW, 256)), dim3(256), 0, STREAM(stream),
+                            reinterpret_cast<const __nv_bfloat16*>(h), (long long)ldh, (int)B, (long long)HW, (int)L, w, bias,
+                            mean, logvar, noise, scaling, latents));
   return MOS_OK;
 }
 

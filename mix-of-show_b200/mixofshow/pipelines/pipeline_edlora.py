@@ -3,8 +3,8 @@ with the same constructor / `set_new_concept_cfg` / `set_controller` / `__call__
 
 The denoise loop (reference :271-301) runs on the B200 engine: per step one captured UNet graph (CFG batch 2) and
 ONE fused kernel for CFG combine + DPM-Solver++(2M) update + re-duplication of the latents (`mos_cfg_dpmpp_step`).
-Prompt encoding (CLIP) and VAE decode are adjacent components: when `text_encoder` / `vae` torch
-modules are supplied they are used as-is; otherwise pass `prompt_embeds` and request `output_type='latent'`.
+Prompt encoding and image decoding run on the B200 CLIP / VAE engines (mixofshow/models/clip_b200.py, vae_b200.py) when
+`from_pretrained` finds `text_encoder/` and `vae/`; without them pass `prompt_embeds` and request `output_type='latent'`.
 """
 from types import SimpleNamespace
 from typing import List, Optional, Union
@@ -58,16 +58,17 @@ class EDLoRAPipeline:
                         **unused):
         """diffusers call shape (`EDLoRAPipeline.from_pretrained(path, scheduler=..., torch_dtype=...)`, test_edlora.py /
         README.md:146): loads `unet/` and `text_encoder/` of a diffusers-layout directory into the B200 containers
-        (mixofshow/utils/model_io.py) and `tokenizer/` through transformers.  The VAE is §8f "next": pass one, or sample
-        with output_type='latent'."""
+        (mixofshow/utils/model_io.py), `vae/` (when present) into the B200 VAE and `tokenizer/` through transformers."""
+        import os
         from mixofshow.utils import model_io
         unet = model_io.load_unet(pretrained_model_name_or_path)
         text_encoder = model_io.load_text_encoder(pretrained_model_name_or_path, device=device)
+        if vae is None and os.path.isdir(os.path.join(pretrained_model_name_or_path, 'vae')):
+            vae = model_io.load_vae(pretrained_model_name_or_path, device=device)
         if tokenizer is None:
             from transformers import CLIPTokenizer
             tokenizer = CLIPTokenizer.from_pretrained(pretrained_model_name_or_path, subfolder='tokenizer')
         pipe = cls(vae=vae, text_encoder=text_encoder, tokenizer=tokenizer, unet=unet, scheduler=scheduler)
-        import os
         if os.path.exists(os.path.join(pretrained_model_name_or_path, 'new_concept_cfg.json')):   # a fused model
             cfg = model_io.load_new_concept_cfg(pretrained_model_name_or_path)
             model_io.ensure_concept_tokens(tokenizer, cfg)

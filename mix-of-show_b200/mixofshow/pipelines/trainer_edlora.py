@@ -7,8 +7,8 @@ keys f'{module}.lora_down.weight' / '.lora_up.weight', :371-378), and trains all
 new-concept embedding rows, the CLIPAttention LoRA and the UNet Attention LoRA — in one captured CUDA graph: text encoder
 forward -> UNet forward -> masked MSE + attention regulariser -> UNet backward -> text encoder backward
 (mos_b200/train_engine.py + mos_b200/clip_train_engine.py).  The gradients land in ONE flat fp32 buffer (the payload of the
-step's single NCCL all-reduce); there is no autograd graph to call `.backward()` on.  `forward` takes what the VAE
-produces - latents (already x 0.18215, :204) - where the reference takes images (the VAE encoder is SURVEY.md 8f-2).
+step's single NCCL all-reduce); there is no autograd graph to call `.backward()` on.  `forward` takes images (encoded by
+the B200 VAE engine, :203-204) or already encoded latents.
 
 `UNetLoRATrainer` is the latents-and-embeddings level trainer of the UNet LoRA group alone (text encoder frozen and run
 upstream)."""
@@ -191,7 +191,9 @@ class EDLoRATrainer:
             from transformers import CLIPTokenizer
             tokenizer = CLIPTokenizer.from_pretrained(pretrained_path, subfolder='tokenizer')   # :40
         self.tokenizer = tokenizer
-        self.vae = None                     # forward() takes latents
+        import os
+        self.vae = model_io.load_vae(pretrained_path, device=device) if os.path.isdir(os.path.join(pretrained_path, 'vae')) \
+            else None                                                                     # :39
         self._gen = torch.Generator(device='cpu').manual_seed(seed)
         self.new_concept_cfg = self.init_new_concept(new_concept_token, initializer_token, enable_edlora=True)   # :55
         self.attn_reg_weight = attn_reg_weight
@@ -330,12 +332,16 @@ class EDLoRATrainer:
         return ids, ids.view(b, n_x, -1).permute(1, 0, 2).reshape(n_x * b, -1).contiguous()
 
     def forward(self, images, prompts, masks, img_masks, noise=None, timesteps=None, accumulate=False):
-        """trainer_edlora.py:202-261 with `images` = VAE latents [b,4,h,w] (already x 0.18215).  Runs forward + loss +
-        backward of the whole step (text encoder and UNet) and returns the loss as a device scalar."""
-        if images.shape[1] != 4:
-            raise NotImplementedError('EDLoRATrainer.forward takes VAE latents [b,4,h,w] (x 0.18215): the VAE encoder is not '
-                                      'part of the B200 hot path yet (SURVEY.md 8f-2)')
-        latents = images
+        """trainer_edlora.py:202-261.  `images`: [b,3,H,W] in [-1,1] (encoded by the B200 VAE, :203-204) or already encoded
+        latents [b,4,h,w] (x 0.18215).  Runs forward + loss + backward of the whole step (text encoder and UNet) and returns
+        the loss as a device scalar."""
+        if images.shape[1] == 3:                  # :203-204: latents = vae.encode(images).latent_dist.sample() * 0.18215
+            if self.vae is None:
+                raise ValueError(f'images were given but the model directory has no vae/: pass latents [b,4,h,w] (x 0.18215)')
+            dist = self.vae.encode(images.to(self.device)).latent_dist
+            latents = (dist.mean + dist.std * torch.randn(dist.mean.shape, generator=self._gen).to(self.device)) * 0.18215
+        else:
+            latents = images
         b = latents.shape[0]
         if self.engine is None:
             self._build(b)

@@ -136,6 +136,42 @@ def save_text_encoder(text_encoder, model_dir, subfolder='text_encoder', hf_conf
     _write_weights(folder, TEXT_WEIGHTS[0], sd)
 
 
+VAE_WEIGHTS = ('diffusion_pytorch_model.safetensors', 'diffusion_pytorch_model.bin')
+_VAE_REQUIRED = {'act_fn': 'silu', 'norm_num_groups': 32, 'in_channels': 3, 'out_channels': 3}
+
+
+def load_vae(model_dir, subfolder='vae', device='cuda'):
+    """diffusers-layout `vae/` directory (config.json + weights) -> mixofshow.models.vae_b200.AutoencoderKL."""
+    from mixofshow.models.vae_b200 import AutoencoderKL
+    folder = os.path.join(model_dir, subfolder) if subfolder else model_dir
+    with open(os.path.join(folder, 'config.json')) as f:
+        cfg = json.load(f)
+    for k, want in _VAE_REQUIRED.items():
+        if k in cfg and cfg[k] != want:
+            raise ValueError(f'vae/config.json: {k}={cfg[k]!r} is not supported on the B200 path (needs {want!r})')
+    down = cfg.get('down_block_types')
+    if down is not None and any(t != 'DownEncoderBlock2D' for t in down):
+        raise ValueError(f'unsupported VAE block layout {down}')
+    return AutoencoderKL(_read_weights(folder, VAE_WEIGHTS), block_out_channels=tuple(cfg.get('block_out_channels', (128, 256, 512, 512))),
+                         layers_per_block=cfg.get('layers_per_block', 2), latent_channels=cfg.get('latent_channels', 4),
+                         scaling_factor=cfg.get('scaling_factor', 0.18215), device=device)
+
+
+def save_vae(vae, model_dir, subfolder='vae'):
+    folder = os.path.join(model_dir, subfolder) if subfolder else model_dir
+    c = vae.config
+    nb = len(c.block_out_channels)
+    cfg = {'_class_name': 'AutoencoderKL', '_diffusers_version': '0.19.3', 'act_fn': 'silu',
+           'block_out_channels': list(c.block_out_channels), 'down_block_types': ['DownEncoderBlock2D'] * nb,
+           'up_block_types': ['UpDecoderBlock2D'] * nb, 'in_channels': 3, 'out_channels': 3,
+           'latent_channels': c.latent_channels, 'layers_per_block': c.layers_per_block, 'norm_num_groups': 32,
+           'sample_size': 512, 'scaling_factor': c.scaling_factor}
+    os.makedirs(folder, exist_ok=True)
+    with open(os.path.join(folder, 'config.json'), 'w') as f:
+        json.dump(cfg, f, indent=2, sort_keys=True)
+    _write_weights(folder, VAE_WEIGHTS[0], vae.state_dict())
+
+
 def save_combined_model(model_dir, unet, text_encoder, new_concept_cfg, tokenizer=None):
     """What gradient_fusion.py:810-813 (`pipe.save_pretrained`) leaves on disk for the sampling scripts: unet/,
     text_encoder/, new_concept_cfg.json AND the tokenizer that carries the added `<new{k}>` tokens — without it the

@@ -161,11 +161,33 @@ def upsample2x(x, y, *, B, H, W, C, ldx=None):
     return y
 
 
-def im2col_s2(x, col, *, B, H, W, C, ldx=None):
+def im2col_s2(x, col, *, B, H, W, C, ldx=None, pad=1):
     check(_lib.lib().mos_im2col_s2(ptr(x), ctypes.c_int64(C if ldx is None else ldx), ctypes.c_int32(B),
-                                   ctypes.c_int32(H), ctypes.c_int32(W), ctypes.c_int32(C), ptr(col), _s()),
-          'mos_im2col_s2')
+                                   ctypes.c_int32(H), ctypes.c_int32(W), ctypes.c_int32(C), ctypes.c_int32(pad), ptr(col),
+                                   _s()), 'mos_im2col_s2')
     return col
+
+
+# ----------------------------------------------------------------------------------------------- VAE glue
+def softmax_rows(S, out, *, rows, cols, scale):
+    assert S.dtype == torch.float32
+    check(_lib.lib().mos_softmax_rows(ptr(S), ctypes.c_int64(S.stride(0)), ctypes.c_int64(rows), ctypes.c_int32(cols),
+                                      ctypes.c_float(scale), ptr(out), ctypes.c_int64(out.stride(0)), _dt(out), _s()),
+          'mos_softmax_rows')
+    return out
+
+
+def conv1x1_nchw(x, w, bias, y):
+    B, Cin = x.shape[0], x.shape[1]
+    check(_lib.lib().mos_conv1x1_nchw(ptr(x), ctypes.c_int32(B), ctypes.c_int32(Cin), ctypes.c_int64(x[0, 0].numel()), ptr(w),
+                                      ptr(bias), ctypes.c_int32(w.shape[0]), ptr(y), _s()), 'mos_conv1x1_nchw')
+    return y
+
+
+def vae_moments(h, w, bias, mean, logvar, *, B, HW, L, noise=None, scaling=1.0, latents=None):
+    check(_lib.lib().mos_vae_moments(ptr(h), ctypes.c_int64(h.stride(0)), ctypes.c_int32(B), ctypes.c_int64(HW),
+                                     ctypes.c_int32(L), ptr(w), ptr(bias), ptr(mean), ptr(logvar), ptr(noise),
+                                     ctypes.c_float(scaling), ptr(latents), _dt(h), _s()), 'mos_vae_moments')
 
 
 def add_rows(x, r, *, M, C, ldx, ldr):
