@@ -120,6 +120,10 @@ int mos_groupnorm_fwd(const void* x, int64_t ldx, int32_t B, int32_t HW, int32_t
                       const float* beta, float eps, int32_t silu_act, float* partial,
                       int32_t partial_capacity_floats, void* y, int64_t ldy, int32_t act_dtype, void* stream);
 
+/* Debug / benchmarking switch: 1 forces the two-launch GroupNorm (statistics kernel + apply kernel), 0 the one-pass cluster
+ * kernel (default; environment MOS_GN_TWOPASS=1 has the same effect). */
+int mos_debug_set_gn_twopass(int32_t on);
+
 /* LayerNorm over rows of bf16 [M, ldx] -> [M, ldy], C <= 1280 (BasicTransformerBlock.norm1/2/3). */
 int mos_layernorm_fwd(const void* x, int64_t ldx, int64_t M, int32_t C, const float* gamma, const float* beta,
                       float eps, void* y, int64_t ldy, int32_t act_dtype, void* stream);

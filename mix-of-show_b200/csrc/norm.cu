@@ -676,6 +676,12 @@ static int gn_block_threads(int C) {
 
 using namespace mos;
 
+static int g_gn_two_pass = -1;     // -1: read MOS_GN_TWOPASS on first use
+extern "C" int mos_debug_set_gn_twopass(int32_t on) {   // A/B switch for tools/gn_debug.py
+  g_gn_two_pass = on ? 1 : 0;
+  return MOS_OK;
+}
+
 // GroupNorm(32) + optional SiLU:  y[b, r, c] = act((x - mean_bg) * rstd_bg * gamma_c + beta_c)
 // x: bf16 [B, HW, ldx] (first C channels), y: bf16 [B, HW, ldy]; partial: fp32 workspace [B, nchunks, 32, 2],
 // nchunks = *nchunks_io (0 = choose; the chosen value is returned through the pointer).
@@ -691,12 +697,11 @@ extern "C" int mos_groupnorm_fwd(const void* x, int64_t ldx, int32_t B, int32_t 
                 "mos_groupnorm_fwd: bad C=%d ldx=%lld ldy=%lld", C, (long long)ldx, (long long)ldy);
   const int threads = gn_block_threads(C);
   // ---- one-pass path: a cluster of k CTAs per (sample, group) keeps the group's channel slab in shared memory
-  static int two_pass = -1;
-  if (two_pass < 0) {
+  if (g_gn_two_pass < 0) {
     const char* e = getenv("MOS_GN_TWOPASS");
-    two_pass = (e && e[0] == '1') ? 1 : 0;
+    g_gn_two_pass = (e && e[0] == '1') ? 1 : 0;
   }
-  if (!two_pass) {
+  if (!g_gn_two_pass) {
     const int cpg = C / GN_GROUPS;
     const int vec = (cpg % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0) ? 4 : 2;
     const long long slab = (long long)HW * cpg * 2;

@@ -433,7 +433,7 @@ class UNetEngine:
         assert fh == h and fw == w
         outs, boxes = [], []
         for r, (ehs_layers, box) in enumerate(self.regions):
-            Kr, Vr = self._cross_kv(tb, ehs_layers[xidx], C, f'_r{r}')
+            Kr, Vr = self.rkv[(r, xidx)]                  # step-invariant: projected once per prompt (update_text)
             o = self.buf(f'tr_ao_r{r}', (B * N, C))
             ops.attention(Q, Kr, Vr, o.view(B, N, C), batch=B, heads=Hh, head_dim=d, nq=N, nk=self.n_text)
             self.launches += 1
@@ -475,12 +475,30 @@ class UNetEngine:
             ch += [rev[i]] * (self.layers + 1)
         return ch
 
+    def update_text(self):
+        """Text K / V projections (+ LoRA) of the 16 cross-attention layers, and of every region's embeddings: they depend on
+        the prompt only, not on the denoise step (the reference recomputes them every step, edlora.py:143-145,
+        pipeline_regionally_t2iadapter.py:120-129), so they are projected ONCE per prompt, outside the captured step.
+        `run()` calls this whenever `in_ehs` / the region embeddings have been written since (tensor version counters)."""
+        launches = self.launches
+        self.kv, self.rkv = {}, {}
+        for xidx, (an, C) in enumerate(zip(self.xattn_names, self._xattn_channels())):
+            tbn = an[:-len('.attn2')]
+            self.kv[xidx] = self._cross_kv(tbn, self.in_ehs[xidx], C, f'_x{xidx}')
+            for r, (ehs_layers, _) in enumerate(self.regions or []):
+                self.rkv[(r, xidx)] = self._cross_kv(tbn, ehs_layers[xidx], C, f'_r{r}_{xidx}')
+        self.text_launches = self.launches - launches
+        self.launches = launches
+        self._text_version = self._text_state()
+
+    def _text_state(self):
+        return (self.in_ehs._version,) + tuple(e._version for e, _ in (self.regions or []))
+
     def _run(self):
         B, H, W = self.B, self.H, self.W
         nb = len(self.block_out)
         self.launches = 0
-        # side stream: timestep MLP + all 22 time_emb_proj, then the 16 text K/V projections (they depend only on the
-        # prompt embeddings), concurrently with conv_in and the first blocks on the main stream
+        # side stream: timestep MLP + all 22 time_emb_proj, concurrently with conv_in on the main stream
         main = torch.cuda.current_stream()
         if self.side is None:
             self.side = torch.cuda.Stream(device=self.dev)
@@ -489,11 +507,7 @@ class UNetEngine:
         with torch.cuda.stream(self.side):
             self._time()
             self.ev_time.record(self.side)
-            self.kv = {}
-            for xidx, (an, C) in enumerate(zip(self.xattn_names, self._xattn_channels())):
-                tbn = an[:-len('.attn2')]
-                self.kv[xidx] = self._cross_kv(tbn, self.in_ehs[xidx], C, f'_x{xidx}')
-        self._kv_joined = False
+        self._kv_joined = True
         si = 0
         x = self._skip_slot(si)
         ops.conv_in(self.in_latents, self.w['conv_in'][0], self.w['conv_in'][1], x, ldy=x.stride(0))
@@ -622,6 +636,8 @@ class UNetEngine:
         return self.out_eps
 
     def run(self):
+        if getattr(self, '_text_version', None) != self._text_state():
+            self.update_text()
         if not self.use_graph or self.emit_probs:
             self._run()
             return

@@ -180,3 +180,35 @@ def test_regional_script_prepare_text_matches_reference_golden():
     assert rcs.prepare_text('p', '', 512, 512) == ('p', [])
     a = rcs.parse_args(['--pretrained_model', 'x', '--prompt_rewrite', 'r', '--seed', '3'])
     assert a.seed == 3 and a.height == 768 and a.width == 1536 and a.keypose_adaptor_weight == 1.0
+
+
+def test_latent_dataset_and_yml_options(tmp_path):
+    """`train_edlora.py -opt <yml>` host side: LatentDataset (replace_mapping, dataset_enlarge_ratio, per-rank sharding of one
+    shared permutation, drop_last) and the shipped reference yml parsing (`!!float` tags, models block = EDLoRATrainer
+    keyword arguments)."""
+    import inspect
+    import os
+
+    import yaml
+
+    import train_edlora as te
+    from mixofshow.pipelines.trainer_edlora import EDLoRATrainer
+    blob = {'latents': torch.arange(6 * 4 * 2 * 2, dtype=torch.float32).view(6, 4, 2, 2), 'prompts': [f'a <TOK> {i}' for i in range(6)],
+            'masks': torch.ones(6, 1, 2, 2)}
+    path = str(tmp_path / 'set.pt')
+    torch.save(blob, path)
+    ds = te.LatentDataset({'path': path, 'replace_mapping': {'<TOK>': '<c1> <c2>'}, 'dataset_enlarge_ratio': 5})
+    assert len(ds) == 30 and ds.prompts[3] == 'a <c1> <c2> 3'
+    it0, it1 = ds.batches(2, rank=0, world=2, seed=1), ds.batches(2, rank=1, world=2, seed=1)
+    seen = []
+    for _ in range(7):                       # 30 // 4 = 7 steps per epoch, disjoint shards of one permutation
+        b0, b1 = next(it0), next(it1)
+        assert b0['images'].shape == (2, 4, 2, 2) and len(b0['prompts']) == 2 and b0['masks'].shape == (2, 1, 2, 2)
+        seen += [int(x[0, 0, 0]) // 16 for x in list(b0['images']) + list(b1['images'])]
+    assert len(seen) == 28 and max(seen.count(i) for i in range(6)) <= 5
+    ref_yml = '/root/reference/options/train/EDLoRA/real/8101_EDLoRA_potter_Cmix_B4_Repeat500.yml'
+    if os.path.exists(ref_yml):
+        opt = yaml.safe_load(open(ref_yml))
+        assert opt['models']['finetune_cfg']['text_embedding']['lr'] == 1e-3 and opt['train']['emb_norm_threshold'] == 0.55
+        params = inspect.signature(EDLoRATrainer.__init__).parameters
+        assert all(k in params for k in opt['models']), 'EDLoRATrainer(**opt["models"]) must accept every key of the yml'
