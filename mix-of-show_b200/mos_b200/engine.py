@@ -497,6 +497,8 @@ class UNetEngine:
     def _run(self):
         B, H, W = self.B, self.H, self.W
         nb = len(self.block_out)
+        if getattr(self, '_text_version', None) != self._text_state() and not torch.cuda.is_current_stream_capturing():
+            self.update_text()
         self.launches = 0
         # side stream: timestep MLP + all 22 time_emb_proj, concurrently with conv_in on the main stream
         main = torch.cuda.current_stream()

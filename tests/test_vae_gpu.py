@@ -73,3 +73,35 @@ def test_vae_container_call_shapes(cuda, tmp_path):
     assert tuple(s.shape) == (1, 4, 32, 32) and torch.isfinite(s).all()
     out = vae2.decode(s / 0.18215 * 0.18215).sample
     assert tuple(out.shape) == (1, 3, 64, 64)
+
+
+def test_pipeline_decodes_to_pil(cuda):
+    """EDLoRAPipeline.__call__ with output_type='pil' (the reference default, pipeline_edlora.py:303-313): latents / 0.18215
+    -> B200 VAE decode -> [0,1] clamp -> PIL, so that `.images[0].save(...)` works as in the reference's scripts."""
+    from mixofshow.models.unet_b200 import UNet2DConditionModel
+    from mixofshow.models.vae_b200 import AutoencoderKL
+    from mixofshow.pipelines.pipeline_edlora import EDLoRAPipeline
+    from oracle import unet as ou
+    from oracle import vae as ov
+    ref = ou.build_unet(0, ou.TINY)
+    unet = UNet2DConditionModel(block_out_channels=ou.TINY['block_out_channels'], layers_per_block=ou.TINY['layers_per_block'])
+    unet.load_state_dict(ref.state_dict())
+    vref = ov.build_vae(0, ov.TINY_VAE)
+    vae = AutoencoderKL({k: v.detach() for k, v in vref.state_dict().items()},
+                        block_out_channels=ov.TINY_VAE['block_out_channels'], layers_per_block=1)
+    pipe = EDLoRAPipeline(vae=vae, unet=unet).to('cuda')
+    pipe.set_new_concept_cfg({})
+    g = torch.Generator().manual_seed(3)
+    lat = torch.randn(1, 4, 16, 16, generator=g)
+    pe, ne = torch.randn(1, 16, 77, 768, generator=g), torch.randn(1, 77, 768, generator=g)
+    kw = dict(prompt_embeds=pe.cuda(), negative_prompt_embeds=ne.cuda(), height=128, width=128, num_inference_steps=3,
+              guidance_scale=3.0)
+    lat_out = pipe(latents=lat.clone(), output_type='latent', **kw).images
+    imgs = pipe(latents=lat.clone(), output_type='pil', **kw).images
+    assert isinstance(imgs, list) and imgs[0].size == (32, 32)            # TINY_VAE upsamples x2
+    with torch.no_grad():
+        dec = vref.decode(lat_out.cpu() / 0.18215)
+    want = ((dec / 2 + 0.5).clamp(0, 1)[0].permute(1, 2, 0) * 255).round()
+    import numpy as np
+    got = torch.from_numpy(np.asarray(imgs[0]).astype('float32'))
+    assert (got - want).abs().max().item() <= 2.0                         # 8-bit levels
