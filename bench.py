@@ -404,11 +404,7 @@ def main():
     if roof is not None:
         frac = roof['achieved'] / peaks['tflops']
         out['roofline'] = {'bound': 'tensor', 'achieved': roof['achieved'], 'peak': peaks['tflops'], 'unit': 'TFLOP/s',
-                           'frac': frac, 'traffic': 15.9e6,
-                           'traffic_note': 'mean dram__bytes_read+write per launch over the first 40 gemm launches of one '
-                                           'step (profiles/r1_gemm_full_v4_summary.csv, ncu --set full): 1.3-170 MB, e.g. '
-                                           '7.2-12.4 MB for the res-64 3x3 conv whose algorithmic operand bytes are 7.0 MB '
-                                           '(DRAM traffic ~ algorithmic; the re-reads are L2->SM: 212 MB for that launch)',
+                           'frac': frac, **gemm_traffic(),
                            'method': 'T(graph step) - T(graph step without gemm launches), CUDA events',
                            'peak_source': peaks['src'] + ' (bf16_tflops_sustained)',
                            'kernel': 'mos::gemm_kernel (tcgen05 GEMM + implicit-GEMM conv3x3)',
@@ -504,6 +500,26 @@ def train_leg(args, rank, world, dev, sd, lora, cfg):
             'params_bit_identical_across_ranks': identical, 'mean_loss': loss,
             'step_tflops_per_gpu': (per_sample_tflop * B / (ms * 1e-3)) if per_sample_tflop else None,
             'data': 'synthetic (per-rank seeds), latents in, VAE / CLIP upstream not included'}
+
+
+def gemm_traffic():
+    """`roofline.traffic`: dram__bytes_read.sum + dram__bytes_write.sum per launch of mos::gemm_kernel, read from the
+    committed summary of the round's `ncu --set full` capture (profiles/r2_kernels_summary.json, written by
+    tools/ncu_summary.py from the .ncu-rep) - not a literal in this file.  null when the summary is absent."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r2_kernels_summary.json')) as f:
+            rows = [r for r in json.load(f)['kernels'] if 'gemm_kernel' in r['kernel']]
+        vals = [r['dram_bytes'] for r in rows if r.get('dram_bytes') is not None]
+        if not vals:
+            return {'traffic': None}
+        return {'traffic': sum(vals) / len(vals),
+                'traffic_note': f'mean dram__bytes_read+write over the {len(vals)} gemm_kernel launches of the ncu --set full '
+                                'capture of tools/ncu_targets.py (conv3x3 8192x320x2880, 8192x320x320 +LoRA, GEGLU, split-K '
+                                'conv): profiles/r2_kernels_summary.json; algorithmic operand bytes of those launches: '
+                                + ', '.join(f"{r['dram_bytes'] / 1e6:.1f} MB measured / {r.get('algorithmic_mb', float('nan')):.1f} MB"
+                                            for r in rows if r.get('dram_bytes') is not None)}
+    except Exception:
+        return {'traffic': None}
 
 
 def gemm_roofline(eng, ops, torch):

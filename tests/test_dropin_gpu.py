@@ -267,3 +267,40 @@ def test_control_processor_head_dim_160(cuda):
     o = (p @ v).transpose(1, 2).reshape(2, 64, 1280) @ w['to_out.0.weight'].T + w['to_out.0.bias']
     assert rel_l2(seen['probs'], p.reshape(16, 64, 77)) < 1.5e-2
     assert rel_l2(out, o) < 1.5e-2
+
+
+def test_pipeline_loop_has_no_host_sync(cuda):
+    """The denoise loop of EDLoRAPipeline.__call__ must not synchronise the host with the device (the per-step
+    fingerprint walk did 128 device reads): from the first callback to the last, torch's sync debug mode is 'error', which
+    raises on any implicit synchronisation (.item(), float(cuda_tensor), blocking copies, ...)."""
+    from mixofshow.models.edlora import LoRALinearLayer
+    from mixofshow.pipelines.pipeline_edlora import EDLoRAPipeline
+    unet = _tiny_b200_unet(0)
+    for name, module in list(unet.named_modules()):
+        if module.__class__.__name__ == 'Attention':
+            for child_name, child in module.named_modules():
+                if child.__class__.__name__ == 'Linear':
+                    LoRALinearLayer(name + '.' + child_name, child, rank=4, alpha=1.0).lora_up.weight.data.normal_(0, 0.02)
+    pipe = EDLoRAPipeline(unet=unet).to('cuda')
+    pipe.set_new_concept_cfg({})
+    g = torch.Generator().manual_seed(3)
+    lat = torch.randn(1, 4, 16, 16, generator=g).cuda()
+    pe, ne = torch.randn(1, 16, 77, 768, generator=g).cuda(), torch.randn(1, 77, 768, generator=g).cuda()
+    steps = 6
+    seen = []
+
+    def cb(i, t, latents):
+        seen.append(i)
+        if i == 0:
+            torch.cuda.set_sync_debug_mode('error')
+        if i == steps - 1:
+            torch.cuda.set_sync_debug_mode('default')
+
+    kw = dict(prompt_embeds=pe, negative_prompt_embeds=ne, height=128, width=128, num_inference_steps=steps, guidance_scale=7.5,
+              output_type='latent')
+    pipe(latents=lat.clone(), **kw)                       # first call builds / captures (synchronises, by design)
+    try:
+        out = pipe(latents=lat.clone(), callback=cb, **kw).images
+    finally:
+        torch.cuda.set_sync_debug_mode('default')
+    assert seen == list(range(steps)) and torch.isfinite(out).all()
