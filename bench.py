@@ -28,7 +28,8 @@ for p in (ROOT, PKG):
 METRIC = 'SD1.5 UNet+ED-LoRA denoise steps/sec @512x512 bf16'
 UNIT = 'denoise_steps/s'
 WORKLOAD = ('EDLoRAPipeline denoise step: SD1.5 UNet 512x512 (latent 64x64), CFG batch 2, un-merged rank-4 ED-LoRA on '
-            '128 attention linears, 16 layer-wise text embeddings [2,16,77,768], DPM-Solver++(2M) update')
+            '128 attention linears, 16 layer-wise text embeddings [2,16,77,768] (their K/V projections computed once per '
+            'prompt, not per step), DPM-Solver++(2M) update')
 CPU_THREADS = None
 FLOPS_PER_STEP = 2 * 0.8044e12  # algorithmic FLOPs of one CFG denoise step
 
@@ -364,7 +365,12 @@ def main():
     if not args.no_train:
         del pipe, unet, sess, eng
         torch.cuda.empty_cache()
-        train = train_leg(args, rank, world, dev, sd, lora, cfg)
+        try:
+            train = train_leg(args, rank, world, dev, sd, lora, cfg)
+        except Exception as exc:                     # the headline line must still print; the failure is reported, not hidden
+            import traceback
+            traceback.print_exc()
+            train = {'error': f'{type(exc).__name__}: {exc}'[:400]}
 
     if world > 1:
         tt = torch.tensor([ms, e2e_ms], device=dev)
@@ -388,7 +394,7 @@ def main():
                                  'kind::f16 rate as bf16.  bf16 operands (--act-dtype bf16) run at the same speed but miss the '
                                  '1e-3 latent tolerance at guidance 7.5 (2.8e-3)') if args.act_dtype == 'fp16' else
                                 'bf16 operands, fp32 accumulation', 'parallelism': f'replicas x{world} (independent images per GPU, no data-path '
-                   'collective; SURVEY.md 8e)', 'l2': 'inputs larger than L2: 1.72 GB of bf16 weights streamed per '
+                   'collective; SURVEY.md 8e)', 'l2': 'inputs larger than L2: 1.72 GB of 16-bit weights streamed per '
                    'step vs 126 MB L2, no explicit flush', 'cuda_graph': bool(used_graph), 'images_per_step': n_img},
         'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
@@ -421,36 +427,84 @@ def main():
         dist.destroy_process_group()
 
 
+def synthetic_clip_state(n_new_tokens=32, seed=11):
+    """Random-init CLIP text encoder at the SD1.5 sizes (12 layers, width 768, 12 heads, 49408 tokens + the new-concept rows),
+    transformers parameter names; init scales of transformers' CLIPTextModel (N(0, 0.02) embeddings / projections)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    C, I, L = 768, 3072, 12
+    sd = {'text_model.embeddings.token_embedding.weight': torch.randn(49408 + n_new_tokens, C, generator=g) * 0.02,
+          'text_model.embeddings.position_embedding.weight': torch.randn(77, C, generator=g) * 0.02,
+          'text_model.final_layer_norm.weight': torch.ones(C), 'text_model.final_layer_norm.bias': torch.zeros(C)}
+    for i in range(L):
+        p = f'text_model.encoder.layers.{i}.'
+        for n in ('layer_norm1', 'layer_norm2'):
+            sd[p + n + '.weight'], sd[p + n + '.bias'] = torch.ones(C), torch.zeros(C)
+        for n in ('q_proj', 'k_proj', 'v_proj', 'out_proj'):
+            sd[p + f'self_attn.{n}.weight'] = torch.randn(C, C, generator=g) * C ** -0.5 * 0.6
+            sd[p + f'self_attn.{n}.bias'] = torch.zeros(C)
+        sd[p + 'mlp.fc1.weight'], sd[p + 'mlp.fc1.bias'] = torch.randn(I, C, generator=g) * C ** -0.5 * 0.6, torch.zeros(I)
+        sd[p + 'mlp.fc2.weight'], sd[p + 'mlp.fc2.bias'] = torch.randn(C, I, generator=g) * I ** -0.5 * 0.6, torch.zeros(C)
+    return sd
+
+
 def train_leg(args, rank, world, dev, sd, lora, cfg):
-    """BASELINE config 5 (config 2 at N = 1): data-parallel ED-LoRA training of the UNet-LoRA group.  Every rank runs the
-    captured forward + masked-MSE + attention-regulariser + backward graph on ITS shard of the global batch (per-GPU batch
-    fixed: weak scaling), then the step's ONE collective - an NCCL all-reduce (sum) of the flat fp32 gradient buffer
-    [797 184 LoRA gradients | loss | Norm_mean] - then the fused flat AdamW + LoRA re-pack (train_edlora.py:105-158;
-    SURVEY.md 8e).  Timed with CUDA events, max over ranks; the all-reduce alone is timed separately."""
+    """BASELINE config 5 (config 2 at N = 1): data-parallel ED-LoRA training, the path that actually shards.  Every rank runs
+    the captured step of `EDLoRATrainer.forward` + `loss.backward()` (trainer_edlora.py:218-261, train_edlora.py:120-123) on
+    ITS shard of the global batch (per-GPU batch fixed: weak scaling): CLIP text encoder forward (16 layer-wise prompts per
+    sample, CLIPAttention LoRA) -> UNet forward (Attention LoRA) -> masked MSE + attention regulariser -> UNet backward ->
+    CLIP backward; then the step's ONE collective - an NCCL all-reduce (sum, fp32) of the flat gradient buffer [32 concept
+    embedding rows | CLIP LoRA | UNet LoRA | loss, Norm_mean] - then the fused flat AdamW on the three learning-rate groups
+    and the LoRA re-pack (train_edlora.py:57,105-158).  The VAE encoder runs upstream (latents in).  Timed
+    with CUDA events, max over ranks; the all-reduce alone is timed separately."""
+    import math
+
     import torch
     import torch.distributed as dist
     from mos_b200 import dp
-    from mos_b200.engine import ehs_to_layer_major
+    from mos_b200.clip_train_engine import CLIPTrainEngine
     from mos_b200.train_engine import TrainEngine
     kw = dict(block_out=cfg['block_out_channels'], layers=cfg['layers_per_block']) if cfg else {}
     B = args.train_batch
-    eng = TrainEngine(sd, B, 64, 64, lora=lora, attn_reg_weight=0.01, device=dev, **kw)
+    tsd = synthetic_clip_state()
+    g0 = torch.Generator().manual_seed(12)
+    tlora = {}
+    for i in range(12):
+        for pj in ('q_proj', 'k_proj', 'v_proj', 'out_proj'):
+            m = f'text_model.encoder.layers.{i}.self_attn.{pj}'
+            tlora[m + '.lora_down.weight'] = (torch.rand(4, 768, generator=g0) * 2 - 1) / math.sqrt(768)
+            tlora[m + '.lora_up.weight'] = torch.randn(768, 4, generator=g0) * 0.02
+    concept_ids = list(range(49408, 49408 + 32))
+    n_text = CLIPTrainEngine.lora_param_count(12, 768, 960)
+    n_unet = sum(v.numel() for v in lora.values())
+    state = dp.FlatTrainState(len(concept_ids), 768, n_text, n_unet, lrs=(1e-3, 1e-5, 1e-4), device=dev)
+    eng = TrainEngine(sd, B, 64, 64, lora=lora, attn_reg_weight=0.01, reg_full_identity=False, state=state,
+                      state_offset=state.group_end[1], text_grad=True, device=dev, **kw)
+    nx = len(eng.xattn_names)
+    text = CLIPTrainEngine(tsd, nx * B, lora=tlora, lora_alpha=1.0, concept_token_ids=concept_ids, state=state, emb_offset=0,
+                           lora_offset=state.group_end[0], device=dev)
+    eng.attach_text_engine(text)
     g = torch.Generator().manual_seed(100 + rank)              # per-rank data (train_edlora.py:48,70)
     x0 = torch.randn(B, 4, 64, 64, generator=g).to(dev)
     noise = torch.randn(B, 4, 64, 64, generator=g).to(dev)
     t = torch.randint(0, 1000, (B,), generator=g).to(dev)
-    nx = len(eng.xattn_names)
-    ehs = ehs_to_layer_major(torch.randn(B, 16, 77, 768, generator=g)[:, :nx].to(dev), nx, torch.bfloat16)
+    ids = torch.randint(1000, 40000, (nx, B, 77), generator=g)    # layer-major [16, B, 77]: BOS, 8 words incl. the two
+    ids[:, :, 0] = 49406                                           # layer-wise concept tokens at positions 2 and 3, EOS padding
+    ids[:, :, 9:] = 49407
+    for l in range(nx):
+        ids[l, :, 2], ids[l, :, 3] = concept_ids[l % 16], concept_ids[16 + l % 16]
+    ids = ids.reshape(nx * B, 77)
     masks = torch.zeros(B, 1, 64, 64)
     masks[:, :, 8:56, 16:48] = 1.0                               # SURVEY.md 8d config 2
     masks = masks.to(dev)
     pos = [[2, 3]] * B
 
     def step():
-        out = eng.forward_backward(x0, noise, t, ehs, masks, token_pos=pos)
-        scale = dp.allreduce_flat_device(eng.state, out[0:1])
-        dp.optimizer_step(eng.state, scale)
+        out = eng.forward_backward(x0, noise, t, None, masks, token_pos=pos, text_ids=ids)
+        scale = dp.allreduce_flat_device(state, out[0:1])
+        dp.optimizer_step(state, scale)
         eng.refresh_lora()
+        text.refresh_lora()
 
     def sync():
         if world > 1:
@@ -468,9 +522,9 @@ def train_leg(args, rank, world, dev, sd, lora, cfg):
     e1.record()
     sync()
     ms = e0.elapsed_time(e1) / steps
-    # the collective alone (same buffer, back to back)
+    # the collective alone (same buffer size, back to back)
     a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    scratch = eng.state.grads.clone()
+    scratch = state.grads.clone()
     reps = 20
     a0.record()
     for _ in range(reps):
@@ -483,23 +537,27 @@ def train_leg(args, rank, world, dev, sd, lora, cfg):
     identical = True
     tt = torch.tensor([ms, ar_us], device=dev)
     if world > 1:
-        hi, lo = eng.state.params.clone(), eng.state.params.clone()
+        hi, lo = state.params.clone(), state.params.clone()
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         identical = bool(torch.equal(hi, lo))
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms, ar_us = tt[0].item(), tt[1].item()
-    loss = eng.state.grads[eng.state.n].item() / world
-    per_sample_tflop = 1.61 if not cfg else None             # UNet fwd + dX-only bwd + LoRA dW
-    return {'metric': 'ED-LoRA train samples/sec (SD1.5 UNet @512x512, bf16, UNet-LoRA group; forward + masked MSE + '
-                      'attention regulariser + backward + all-reduce + AdamW)',
+    loss = state.grads[state.n].item() / world
+    # UNet fwd + dX-only bwd + LoRA dW = 1.61 TFLOP, CLIP x16 sequences fwd + bwd = 0.42 TFLOP per sample
+    per_sample_tflop = 1.61 + 0.42 if not cfg else None
+    return {'metric': 'ED-LoRA train samples/sec (train_edlora step: CLIP text encoder x16 + SD1.5 UNet @512x512, bf16; text-'
+                      'embedding rows, CLIPAttention LoRA and UNet Attention LoRA trained; forward + masked MSE + attention '
+                      'regulariser + backward + all-reduce + AdamW)',
             'value': B * world / ms * 1e3, 'unit': 'samples/s', 'n_gpus': world, 'ms_per_step': ms, 'steps': steps,
             'warmup': warm, 'batch_per_gpu': B, 'global_batch': B * world, 'scaling': 'weak',
             'collective': 'ONE NCCL all-reduce (sum, fp32) of the flat gradient buffer per optimiser step',
-            'allreduce_bytes_per_step': (eng.state.n + 2) * 4, 'allreduce_us': ar_us, 'lora_params': eng.state.n,
+            'allreduce_bytes_per_step': (state.n + 2) * 4, 'allreduce_us': ar_us,
+            'trainable_params': {'embedding_rows': len(concept_ids) * 768, 'clip_lora_padded': n_text, 'unet_lora': n_unet},
             'params_bit_identical_across_ranks': identical, 'mean_loss': loss,
             'step_tflops_per_gpu': (per_sample_tflop * B / (ms * 1e-3)) if per_sample_tflop else None,
-            'data': 'synthetic (per-rank seeds), latents in, VAE / CLIP upstream not included'}
+            'kernel_launches_per_step': eng.launches + text.launches,
+            'data': 'synthetic (per-rank seeds): latents, token ids, masks; VAE encode upstream'}
 
 
 def gemm_traffic():

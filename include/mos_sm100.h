@@ -71,13 +71,18 @@ typedef struct mos_gemm_args {
   int32_t heads, head_dim, dpad, dv_pad;
   int64_t tokens_per_batch;
   int32_t accumulate;     /* MOS_OUT_F32 only: out += result (Gram accumulation, gradient fusion) */
-  int32_t w_static;       /* 1: W is not written by the kernels just ahead in the stream (model weights): its first tiles
-                           * are requested before griddepcontrol.wait, overlapping the predecessor's tail.  0 = W may be
-                           * an activation (Gram products): every load waits for the dependency. */
+  int32_t w_static;       /* reserved, ignored (round 1 requested the first W tiles ahead of griddepcontrol.wait when set; the
+                           * measurement was neutral and the path was removed) */
   int32_t a_dtype;        /* MOS_DT_*: type of A, of the 16-bit outputs (rows, head-split) and of `residual` */
   int32_t w_dtype;        /* MOS_DT_*: type of W and lora_down; must equal a_dtype (one operand format per tcgen05 MMA) */
   int32_t pair_mode;      /* 0 = library heuristic, 1 = force 2-CTA pair tiles (needs an even number of 128-row tiles),
                            * 2 = force the 1-CTA kernel (benchmarking) */
+  int32_t* tile_counters; /* split-K only, optional: int32 [tile_counters_len] device counters, ZERO on entry (the kernel
+                           * leaves them zero).  When given, the launch also finalizes: the `splits` CTAs of an output tile
+                           * sum the partials in split order and write bias / bias_batch / residual -> `out` themselves
+                           * (no mos_splitk_finalize launch).  One buffer per stream: launches that may overlap must not
+                           * share it. */
+  int32_t tile_counters_len;   /* >= (M tiles) x (N / 160) */
 } mos_gemm_args;
 
 int mos_gemm_bf16(const mos_gemm_args* args, void* stream);

@@ -68,7 +68,8 @@ struct GemmDev {
   long long tokens_per_batch;
   int accum;           // MOS_OUT_F32: out += result (Gram accumulation)
   unsigned long long* tl;   // optional timeline buffer (mos_debug_set_timeline)
-  int w_static;        // W tiles may be requested before griddepcontrol.wait
+  int w_static;        // reserved (round-1 weight-prefetch experiment: neutral, removed)
+  int* counters;       // split-K with in-kernel finalize: one arrival counter per output tile (zero between launches)
 };
 
 template <bool F16>
@@ -462,6 +463,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               for (int j = 0; j < 16; j += 4)
                 *reinterpret_cast<uint4*>(dst + c * 16 + j) = make_uint4(vv[c][j], vv[c][j + 1], vv[c][j + 2], vv[c][j + 3]);
             }
+            if (p.counters != nullptr) __threadfence();   // published by the release increment after the item
           }
         } else if (p.geglu) {
 #pragma unroll
@@ -581,8 +583,72 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       epi_bar();   // staging / bias tables are reused by the next item
       if (et == 0 && it == 0) stamp(7);
+      if (p.counters != nullptr) {
+        // split-K, in-kernel finalize: publish this item's partial tile (every thread fenced its own stores; the barrier
+        // above ordered them before this release increment)
+        if (et == 0) {
+          __threadfence();
+          atomicAdd(p.counters + ws / p.splits, 1);
+        }
+      }
     }
     tc_fence_before();
+    if (p.counters != nullptr) {
+      // ---- phase 2 (split-K only): the `splits` CTAs that hold the partials of one output tile each reduce 1/splits of
+      // its rows, in the fixed order split 0..S-1 (bitwise reproducible), and apply bias / per-batch bias / residual.
+      // Deadlock-free: the grid has at most one CTA per SM (all resident), and no CTA waits before ALL its own partials are
+      // published.  The counter runs 0 -> S (arrivals) -> 2S (slices done) and is reset by the last slice.
+      const int nthr = (int)blockDim.x - 64;
+      const int S = p.splits;
+      const int rows_per = (BM + S - 1) / S;
+      for (int ws = unit_id; ws < p.total_super; ws += num_units) {
+        const TileCoord t = item_coord(p, ws, rank);
+        int* ctr = p.counters + ws / S;
+        if (et == 0) {
+          int seen;
+          do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+          } while (seen < S);
+        }
+        epi_bar();
+        const int rlo = t.split * rows_per, rhi = min(BM, rlo + rows_per);
+        for (int i = et; i < (rhi - rlo) * (BN / 4); i += nthr) {
+          const int rr = rlo + i / (BN / 4), c4 = i % (BN / 4);
+          long long m;
+          int b;
+          if (!row_coord(p, t, rr, m, b)) continue;
+          const int n = t.n0 + c4 * 4;
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float* src = p.partial + m * p.N + n;
+          for (int sp = 0; sp < S; ++sp) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(src + (long long)sp * p.M * p.N));
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+          }
+          if (p.bias) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+            acc.x += bv.x; acc.y += bv.y; acc.z += bv.z; acc.w += bv.w;
+          }
+          if (p.bias_batch) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias_batch + (long long)b * p.bias_batch_ld + n));
+            acc.x += bv.x; acc.y += bv.y; acc.z += bv.z; acc.w += bv.w;
+          }
+          if (p.residual) {
+            const uint2 rv = *reinterpret_cast<const uint2*>(p.residual + m * p.ldr + n);
+            const float2 a = unpack16x2<F16>(rv.x), c = unpack16x2<F16>(rv.y);
+            acc.x += a.x; acc.y += a.y; acc.z += c.x; acc.w += c.y;
+          }
+          uint2 o;
+          o.x = pack16x2<F16>(acc.x, acc.y);
+          o.y = pack16x2<F16>(acc.z, acc.w);
+          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldc + n) = o;
+        }
+        epi_bar();
+        if (et == 0) {
+          const int old = atomicAdd(ctr, 1);
+          if (old == 2 * S - 1) atomicExch(ctr, 0);     // every slice of this tile is written: ready for the next launch
+        }
+      }
+    }
   }
 
   // a CTA of a pair may not exit while its peer can still read its shared memory (MMA operands), complete transactions or
@@ -668,6 +734,9 @@ extern "C" int mos_gemm_bf16(const mos_gemm_args* a, void* stream_) {
   const bool lora = a->lora_down != nullptr;
   if (splits > 1) {
     MOS_CHECK_ARG(a->partial != nullptr, "mos_gemm_bf16: split-K needs a partial workspace");
+    if (a->tile_counters != nullptr)
+      MOS_CHECK_ARG(a->out != nullptr && a->ldc >= a->N && a->ldc % 4 == 0 && a->N % 4 == 0 && a->pair_mode != 1,
+                    "mos_gemm_bf16: in-kernel split-K finalize needs `out` (16-bit rows, ldc %% 4 == 0) and the 1-CTA kernel");
     MOS_CHECK_ARG(!lora && !a->geglu && a->out_mode == MOS_OUT_BF16,
                   "mos_gemm_bf16: split-K cannot be combined with lora / geglu / head-split output");
   } else {
@@ -749,6 +818,7 @@ extern "C" int mos_gemm_bf16(const mos_gemm_args* a, void* stream_) {
   bool pair = use_pair && (m_tiles % 2 == 0) && kb_per_item >= pair_min_kb;
   if (a->pair_mode == 1) pair = (m_tiles % 2 == 0);
   else if (a->pair_mode == 2) pair = false;
+  if (splits > 1 && a->tile_counters != nullptr) pair = false;   // the in-kernel finalize is built for 1-CTA work items
   p.pair = pair ? 1 : 0;
 
   // ---- tensor maps.  W box: the whole tile (160 rows), or a pair's half: 80 rows, with LoRA (N = 176 = 160 W rows + 16
@@ -826,6 +896,12 @@ extern "C" int mos_gemm_bf16(const mos_gemm_args* a, void* stream_) {
   p.accum = a->accumulate;
   p.tl = g_timeline_host;
   p.w_static = a->w_static;
+  p.counters = (splits > 1) ? a->tile_counters : nullptr;
+  if (p.counters != nullptr) {
+    MOS_CHECK_ARG((long long)p.n_tiles * m_tiles <= a->tile_counters_len,
+                  "mos_gemm_bf16: tile_counters holds %d counters, the launch needs %lld", (int)a->tile_counters_len,
+                  (long long)p.n_tiles * m_tiles);
+  }
   if (a->bias_batch && !a->conv)
     MOS_CHECK_ARG(p.rows_per_batch >= 32, "mos_gemm_bf16: bias_batch needs rows_per_batch >= 32 in plain mode");
   p.total_super = p.n_tiles * (pair ? m_tiles / 2 : m_tiles) * splits;

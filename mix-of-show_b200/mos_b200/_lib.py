@@ -30,6 +30,7 @@ class GemmArgs(ctypes.Structure):
         ('heads', c_i32), ('head_dim', c_i32), ('dpad', c_i32), ('dv_pad', c_i32),
         ('tokens_per_batch', c_i64), ('accumulate', c_i32), ('w_static', c_i32),
         ('a_dtype', c_i32), ('w_dtype', c_i32), ('pair_mode', c_i32),
+        ('tile_counters', c_vp), ('tile_counters_len', c_i32),
     ]
 
 

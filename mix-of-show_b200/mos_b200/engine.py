@@ -22,7 +22,10 @@ BF16 = torch.bfloat16       # weights (and the training engine's activations)
 F16 = torch.float16
 # Experiment (opt-in, MOS_GEMM_PREFETCH_W=1): request the first weight tiles of every GEMM before griddepcontrol.wait.
 # Measured on B200 in round 1: no gain for the batch-2 denoise step (6.41 -> 6.55 ms together with a cheaper erf), so off.
-PREFETCH_W = os.environ.get('MOS_GEMM_PREFETCH_W') == '1'
+PREFETCH_W = os.environ.get('MOS_GEMM_PREFETCH_W') == '1'      # (kept for the bench history; the library ignores w_static)
+# split-K GEMMs finalize in-kernel (mos_gemm_args.tile_counters); MOS_SPLITK_FUSED=0 restores the separate
+# mos_splitk_finalize launch (A/B timing, profiles/README.md)
+FUSED_SPLITK = os.environ.get('MOS_SPLITK_FUSED', '1') != '0'
 SKIP_CH = [320, 320, 320, 320, 640, 640, 640, 1280, 1280, 1280, 1280, 1280]
 
 
@@ -283,9 +286,22 @@ class UNetEngine:
             splits = self._splits(M, ent['N'], kb_total)
         kw = dict(bias=ent['bias'], conv=conv, lda=lda)
         if splits > 1:
-            partial = self.buf('splitk', (16 * 1024 * 1280,), torch.float32)
+            # the side stream (1x1 shortcuts, timestep MLP) runs concurrently with the main stream: its split-K launches
+            # need a workspace and tile counters of their own
+            on_side = self.side is not None and torch.cuda.current_stream() == self.side
+            partial = (self.buf('splitk_side', (8 * 1024 * 1280,), torch.float32) if on_side
+                       else self.buf('splitk', (16 * 1024 * 1280,), torch.float32))
             assert splits * M * ent['N'] <= partial.numel()
-            ops.gemm(A, ent['W'], None, M=M, splits=splits, partial=partial, conv=conv, lda=lda, w_static=PREFETCH_W)
+            if FUSED_SPLITK:
+                # the `splits` CTAs of every output tile reduce the partials themselves (mos_gemm_args.tile_counters)
+                ops.gemm(A, ent['W'], out, M=M, splits=splits, partial=partial, conv=conv, lda=lda, bias=ent['bias'],
+                         bias_batch=bias_batch, rows_per_batch=rows_per_batch, residual=residual,
+                         bias_batch_ld=self.temb_total if bias_batch is not None else 0,
+                         counters=self.buf('splitk_counters_side' if on_side else 'splitk_counters', (1024,), torch.int32,
+                                           zero=True))
+                self.launches += 1
+                return out
+            ops.gemm(A, ent['W'], None, M=M, splits=splits, partial=partial, conv=conv, lda=lda)
             if 'splitk' not in self.skip:
               ops.splitk_finalize(partial, splits, M, ent['N'], out, bias=ent['bias'], bias_batch=bias_batch,
                                   rows_per_batch=rows_per_batch, residual=residual,
@@ -295,7 +311,7 @@ class UNetEngine:
         if lora:
             kw.update(lora_down=ent['lora_down'], lora_up=ent['lora_up'], lora_seg=ent['lora_seg'])
         ops.gemm(A, ent['W'], out, M=M, residual=residual, bias_batch=bias_batch, rows_per_batch=rows_per_batch,
-                 bias_batch_ld=self.temb_total if bias_batch is not None else 0, geglu=geglu, heads=heads, w_static=PREFETCH_W,
+                 bias_batch_ld=self.temb_total if bias_batch is not None else 0, geglu=geglu, heads=heads,
                  **kw)
         self.launches += 1
         return out

@@ -21,7 +21,7 @@ def _dt(*tensors):
 def gemm(A, W, out=None, *, bias=None, bias_batch=None, rows_per_batch=0, residual=None, geglu=False,
          lora_down=None, lora_up=None, lora_seg=0, conv=None, splits=1, partial=None, stages=0,
          out_f32=False, heads=None, M=None, lda=None, ldc=None, ldr=None, bias_batch_ld=0, accumulate=False,
-         w_static=False, pair_mode=0):
+         w_static=False, pair_mode=0, counters=None):
     """out = epilogue(A @ W^T [+ LoRA]).
 
     A: bf16 / fp16 [M, K] (row pitch lda) or, with conv=(B, H, Wd, C), the NHWC activation [B, H, Wd, C]; the 16-bit
@@ -57,8 +57,11 @@ def gemm(A, W, out=None, *, bias=None, bias_batch=None, rows_per_batch=0, residu
     if residual is not None:
         a.ldr = residual.stride(0) if ldr is None else ldr
     a.geglu = 1 if geglu else 0
-    a.w_static = 1 if w_static else 0      # W = model weights: prefetch ahead of the stream dependency
+    a.w_static = 1 if w_static else 0      # reserved (ignored by the library)
     a.pair_mode = pair_mode
+    if counters is not None:               # split-K with the in-kernel finalize (zeroed int32 counters, one per output tile)
+        assert splits > 1 and counters.dtype == torch.int32 and out is not None
+        a.tile_counters, a.tile_counters_len = ptr(counters), counters.numel()
     if lora_down is not None:
         assert lora_down.shape[0] == 16 and lora_up.dtype == torch.float32
         a.lora_down, a.lora_up = ptr(lora_down), ptr(lora_up)

@@ -161,6 +161,47 @@ def test_conv3x3_splitk(cuda, splits):
     assert rel_l2(out, ref) < 4e-3
 
 
+@pytest.mark.parametrize('case', [dict(conv=(2, 8, 8, 1280), N=1280, splits=15), dict(conv=(2, 16, 16, 1280), N=1280, splits=4),
+                                  dict(conv=(2, 12, 24, 320), N=320, splits=3), dict(M=512, K=2560, N=1280, splits=4),
+                                  dict(M=200, K=1280, N=640, splits=5), dict(conv=(2, 32, 32, 640), N=640, splits=2),
+                                  dict(conv=(2, 32, 32, 640), N=640, splits=4)])    # last: 256 work items > 148 CTAs
+@pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float16])
+def test_splitk_in_kernel_finalize(cuda, case, dtype):
+    """mos_gemm_args.tile_counters: the `splits` CTAs of every output tile reduce the partials themselves.  Same summation
+    order as mos_splitk_finalize, so the result must be BIT-identical to the two-launch path; three back-to-back launches
+    check that the counters return to zero (CUDA-graph replay relies on it)."""
+    from mos_b200 import ops
+    conv, N, S = case.get('conv'), case['N'], case['splits']
+    if conv is not None:
+        B, H, Wd, C = conv
+        M, K = B * H * Wd, 9 * C
+        x = mk((B, H, Wd, C), cuda, seed=1).to(dtype)
+        rows_per_batch = H * Wd
+    else:
+        M, K = case['M'], case['K']
+        x = mk((M, K), cuda, seed=1).to(dtype)
+        B, rows_per_batch = 2, M // 2
+    w = mk((N, K), cuda, K ** -0.5, seed=2).to(dtype)
+    bias = torch.randn(N, device=cuda) * 0.1
+    bias_batch = torch.randn(B, N + 40, device=cuda) * 0.1           # pitched like the engine's time-embedding table
+    res = mk((M, N + 8), cuda, seed=3).to(dtype)[:, :N]              # pitched residual
+    partial = torch.empty((S, M, N), device=cuda, dtype=torch.float32)
+    ref = torch.empty((M, N), device=cuda, dtype=dtype)
+    kw = dict(conv=conv, M=M)
+    ops.gemm(x, w, None, splits=S, partial=partial, **kw)
+    ops.splitk_finalize(partial, S, M, N, ref, bias=bias, bias_batch=bias_batch, rows_per_batch=rows_per_batch, residual=res,
+                        bias_batch_ld=N + 40)
+    counters = torch.zeros(256, device=cuda, dtype=torch.int32)
+    for rep in range(3):
+        out = torch.full((M, N), float('nan'), device=cuda, dtype=dtype)
+        partial.fill_(float('nan'))
+        ops.gemm(x, w, out, splits=S, partial=partial, bias=bias, bias_batch=bias_batch, rows_per_batch=rows_per_batch,
+                 bias_batch_ld=N + 40, residual=res, counters=counters, **kw)
+        torch.cuda.synchronize()
+        assert torch.equal(out.view(torch.int16), ref.view(torch.int16)), f'launch {rep}'
+        assert int(counters.abs().sum()) == 0, f'counters not reset after launch {rep}'
+
+
 def test_gemm_bad_args(cuda):
     """Error behaviour mirrors the reference's fail-fast asserts: ValueError, not a crash."""
     from mos_b200 import ops

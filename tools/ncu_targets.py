@@ -96,6 +96,7 @@ wc = rnd((320, 9 * 320), scale=(9 * 320) ** -0.5)
 oc = torch.empty(8192, 320, device=dev, dtype=torch.float16)
 bias = torch.randn(320, device=dev)
 run('gemm conv3x3 8192x320x2880', lambda: ops.gemm(xa, wc, oc, bias=bias, conv=(2, 64, 64, 320)))
+run('gemm conv3x3 8192x320x2880 cta_group::2 pair (opt-in mode)', lambda: ops.gemm(xa, wc, oc, bias=bias, conv=(2, 64, 64, 320), pair_mode=1))
 a2 = rnd((8192, 320))
 w2 = rnd((320, 320), scale=320 ** -0.5)
 d16 = torch.zeros(16, 320, device=dev, dtype=torch.float16)

@@ -11,7 +11,7 @@ import torch  # noqa: E402
 import bench  # noqa: E402
 from mos_b200.engine import UNetEngine, ehs_to_layer_major  # noqa: E402
 
-unet, sd, lora, lat, ehs, cfg = bench.build_workload(False)
+sd, lora, lat, ehs, cfg = bench.build_workload(False)
 eng = UNetEngine(sd, 2, 64, 64, lora=lora)
 eng.in_ehs.copy_(ehs_to_layer_major(ehs.cuda(), 16))
 eng.in_latents.normal_()
