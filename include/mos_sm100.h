@@ -83,6 +83,9 @@ typedef struct mos_gemm_args {
                            * (no mos_splitk_finalize launch).  One buffer per stream: launches that may overlap must not
                            * share it. */
   int32_t tile_counters_len;   /* >= (M tiles) x (N / 160) */
+  const void* prefetch_ptr;    /* optional: [prefetch_bytes] of STATIC device data (normally the next layer's weights) that the
+                                * launch pulls into L2 with cp.async.bulk.prefetch.L2 while it runs; semantically a no-op */
+  int64_t prefetch_bytes;
 } mos_gemm_args;
 
 int mos_gemm_bf16(const mos_gemm_args* args, void* stream);

@@ -70,6 +70,8 @@ struct GemmDev {
   unsigned long long* tl;   // optional timeline buffer (mos_debug_set_timeline)
   int w_static;        // reserved (round-1 weight-prefetch experiment: neutral, removed)
   int* counters;       // split-K with in-kernel finalize: one arrival counter per output tile (zero between launches)
+  const uint8_t* pf;   // optional: bytes to pull into L2 for a LATER launch (the next layer's weights), see mos_gemm_args
+  long long pf_bytes;
 };
 
 template <bool F16>
@@ -287,6 +289,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   // Everything above touched no global memory written by the previous kernel in the stream.
   if (threadIdx.x == 0) stamp(1);
+  if (p.pf != nullptr && warp == 0 && lane == 1) {
+    // L2 staging of a later launch's weights (static data: no dependency on the previous kernel, so ahead of the wait):
+    // this CTA's 1/gridDim slice, in 16 KB bulk prefetches.  HBM is idle for most of the step (the step streams 1.7 GB
+    // of weights in ~6 ms), the 126 MB L2 holds the next layer's whole weight matrix.
+    constexpr long long CH = 16384;
+    const long long per = ((p.pf_bytes + gridDim.x - 1) / gridDim.x + CH - 1) / CH * CH;
+    const long long lo = (long long)blockIdx.x * per, hi = min(p.pf_bytes, lo + per);
+    for (long long off = lo; off < hi; off += CH) {
+      const uint32_t n = (uint32_t)min(CH, hi - off) & ~15u;
+      if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.pf + off), "r"(n) : "memory");
+    }
+  }
   pdl_wait();
   pdl_launch_dependents();
 
@@ -896,6 +910,13 @@ extern "C" int mos_gemm_bf16(const mos_gemm_args* a, void* stream_) {
   p.accum = a->accumulate;
   p.tl = g_timeline_host;
   p.w_static = a->w_static;
+  p.pf = nullptr;
+  p.pf_bytes = 0;
+  if (a->prefetch_ptr != nullptr && a->prefetch_bytes >= 16) {
+    MOS_CHECK_ARG(is_aligned(a->prefetch_ptr, 16), "mos_gemm_bf16: prefetch_ptr must be 16-byte aligned");
+    p.pf = reinterpret_cast<const uint8_t*>(a->prefetch_ptr);
+    p.pf_bytes = a->prefetch_bytes;
+  }
   p.counters = (splits > 1) ? a->tile_counters : nullptr;
   if (p.counters != nullptr) {
     MOS_CHECK_ARG((long long)p.n_tiles * m_tiles <= a->tile_counters_len,

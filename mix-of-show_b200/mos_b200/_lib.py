@@ -31,6 +31,7 @@ class GemmArgs(ctypes.Structure):
         ('tokens_per_batch', c_i64), ('accumulate', c_i32), ('w_static', c_i32),
         ('a_dtype', c_i32), ('w_dtype', c_i32), ('pair_mode', c_i32),
         ('tile_counters', c_vp), ('tile_counters_len', c_i32),
+        ('prefetch_ptr', c_vp), ('prefetch_bytes', c_i64),
     ]
 
 

@@ -26,6 +26,10 @@ PREFETCH_W = os.environ.get('MOS_GEMM_PREFETCH_W') == '1'      # (kept for the b
 # split-K GEMMs finalize in-kernel (mos_gemm_args.tile_counters); MOS_SPLITK_FUSED=0 restores the separate
 # mos_splitk_finalize launch (A/B timing, profiles/README.md)
 FUSED_SPLITK = os.environ.get('MOS_SPLITK_FUSED', '1') != '0'
+# every GEMM of the step stages the NEXT GEMM's weight matrix in L2 while it runs (mos_gemm_args.prefetch_ptr): the step
+# streams 1.7 GB of weights through a mostly idle HBM, the 126 MB L2 holds any single layer.  MOS_L2_PREFETCH=0/1.
+L2_PREFETCH = os.environ.get('MOS_L2_PREFETCH', '0') == '1'
+L2_PREFETCH_MAX_BYTES = 48 << 20
 SKIP_CH = [320, 320, 320, 320, 640, 640, 640, 1280, 1280, 1280, 1280, 1280]
 
 
@@ -84,6 +88,7 @@ class UNetEngine:
         self.controller = None
         self.side = None        # side CUDA stream (created lazily on the device) for independent branches
         self.gram_rec = None    # gradient fusion: callable(key, A [M,C] bf16 view, M, C) fed with recorded GEMM inputs
+        self._in_run, self._w_idx, self._w_seq, self._w_rec = False, 0, [], None      # L2 weight prefetch (see gemm())
         self.skip = set()       # profiling aid: op families not launched ('gemm','splitk','attn','gn','ln','misc')
 
     # ------------------------------------------------------------------------------------------ packing
@@ -285,6 +290,17 @@ class UNetEngine:
         if not lora and not geglu and heads is None:
             splits = self._splits(M, ent['N'], kb_total)
         kw = dict(bias=ent['bias'], conv=conv, lda=lda)
+        if L2_PREFETCH and self._in_run:
+            # weight matrices in launch order: recorded on the first walk of the step, used by every later walk (the walk
+            # is deterministic for a given engine state; a walk of a different length re-records)
+            i = self._w_idx
+            self._w_idx += 1
+            if self._w_rec is not None:
+                self._w_rec.append(ent['W'])
+            elif i + 1 < len(self._w_seq) and self._w_seq[i] is ent['W']:
+                nxt = self._w_seq[i + 1]
+                if nxt.numel() * nxt.element_size() <= L2_PREFETCH_MAX_BYTES:
+                    kw['prefetch'] = nxt
         if splits > 1:
             # the side stream (1x1 shortcuts, timestep MLP) runs concurrently with the main stream: its split-K launches
             # need a workspace and tile counters of their own
@@ -294,14 +310,13 @@ class UNetEngine:
             assert splits * M * ent['N'] <= partial.numel()
             if FUSED_SPLITK:
                 # the `splits` CTAs of every output tile reduce the partials themselves (mos_gemm_args.tile_counters)
-                ops.gemm(A, ent['W'], out, M=M, splits=splits, partial=partial, conv=conv, lda=lda, bias=ent['bias'],
-                         bias_batch=bias_batch, rows_per_batch=rows_per_batch, residual=residual,
+                ops.gemm(A, ent['W'], out, M=M, splits=splits, partial=partial, bias_batch=bias_batch, rows_per_batch=rows_per_batch, residual=residual,
                          bias_batch_ld=self.temb_total if bias_batch is not None else 0,
                          counters=self.buf('splitk_counters_side' if on_side else 'splitk_counters', (1024,), torch.int32,
-                                           zero=True))
+                                           zero=True), **kw)
                 self.launches += 1
                 return out
-            ops.gemm(A, ent['W'], None, M=M, splits=splits, partial=partial, conv=conv, lda=lda)
+            ops.gemm(A, ent['W'], None, M=M, splits=splits, partial=partial, conv=conv, lda=lda, prefetch=kw.get('prefetch'))
             if 'splitk' not in self.skip:
               ops.splitk_finalize(partial, splits, M, ent['N'], out, bias=ent['bias'], bias_batch=bias_batch,
                                   rows_per_batch=rows_per_batch, residual=residual,
@@ -516,6 +531,8 @@ class UNetEngine:
         if getattr(self, '_text_version', None) != self._text_state() and not torch.cuda.is_current_stream_capturing():
             self.update_text()
         self.launches = 0
+        self._in_run, self._w_idx = True, 0
+        self._w_rec = [] if (L2_PREFETCH and not self._w_seq) else None
         # side stream: timestep MLP + all 22 time_emb_proj, concurrently with conv_in on the main stream
         main = torch.cuda.current_stream()
         if self.side is None:
@@ -612,6 +629,11 @@ class UNetEngine:
         ops.conv_out(fn, self.w['conv_out'][0], self.w['conv_out'][1], self.out_eps, B=B, H=h, W=w,
                      C=self.block_out[0])
         self.launches += 1
+        self._in_run = False
+        if self._w_rec is not None:
+            self._w_seq, self._w_rec = self._w_rec, None
+        elif L2_PREFETCH and self._w_idx != len(self._w_seq):
+            self._w_seq = []                 # the walk changed (regions / adapters switched): re-record on the next walk
 
     def set_regions(self, regions, region_hw):
         """regions: list of (ehs_layers bf16 [n_layers,B,77,768], (sh,sw,eh,ew) box fractions) or None.  The embeddings
@@ -665,6 +687,8 @@ class UNetEngine:
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
                 self._run()
+                if L2_PREFETCH and not self._w_seq:
+                    self._run()              # the walk changed since the weight order was recorded: record it again
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
             self.graph = torch.cuda.CUDAGraph()

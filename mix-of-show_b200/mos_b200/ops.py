@@ -21,7 +21,7 @@ def _dt(*tensors):
 def gemm(A, W, out=None, *, bias=None, bias_batch=None, rows_per_batch=0, residual=None, geglu=False,
          lora_down=None, lora_up=None, lora_seg=0, conv=None, splits=1, partial=None, stages=0,
          out_f32=False, heads=None, M=None, lda=None, ldc=None, ldr=None, bias_batch_ld=0, accumulate=False,
-         w_static=False, pair_mode=0, counters=None):
+         w_static=False, pair_mode=0, counters=None, prefetch=None):
     """out = epilogue(A @ W^T [+ LoRA]).
 
     A: bf16 / fp16 [M, K] (row pitch lda) or, with conv=(B, H, Wd, C), the NHWC activation [B, H, Wd, C]; the 16-bit
@@ -59,6 +59,8 @@ def gemm(A, W, out=None, *, bias=None, bias_batch=None, rows_per_batch=0, residu
     a.geglu = 1 if geglu else 0
     a.w_static = 1 if w_static else 0      # reserved (ignored by the library)
     a.pair_mode = pair_mode
+    if prefetch is not None:               # a later launch's weights: staged in L2 by this launch (no-op semantically)
+        a.prefetch_ptr, a.prefetch_bytes = ptr(prefetch), prefetch.numel() * prefetch.element_size()
     if counters is not None:               # split-K with the in-kernel finalize (zeroed int32 counters, one per output tile)
         assert splits > 1 and counters.dtype == torch.int32 and out is not None
         a.tile_counters, a.tile_counters_len = ptr(counters), counters.numel()

@@ -35,7 +35,7 @@ def regional(steps=30):
         regions.append((ehs_to_layer_major(emb.cuda()), (h0 / 768, w0 / 1536, h1 / 768, w1 / 1536)))
     eng.set_regions(regions, (768, 1536))
     shapes = [(320, 96, 192), (640, 48, 96), (1280, 24, 48), (1280, 12, 24)]
-    eng.set_adapters([(torch.randn(B * h * w, c, generator=g) * 0.1).to(torch.bfloat16).cuda() for c, h, w in shapes])
+    eng.set_adapters([(torch.randn(B * h * w, c, generator=g) * 0.1).to(eng.ACT).cuda() for c, h, w in shapes])
     eng.in_ehs.copy_(ehs_to_layer_major(ctx.cuda()))
     sched = DPMSolverPP2M()
     sched.set_timesteps(steps)
