@@ -477,7 +477,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               for (int j = 0; j < 16; j += 4)
                 *reinterpret_cast<uint4*>(dst + c * 16 + j) = make_uint4(vv[c][j], vv[c][j + 1], vv[c][j + 2], vv[c][j + 3]);
             }
-            if (p.counters != nullptr) __threadfence();   // published by the release increment after the item
           }
         } else if (p.geglu) {
 #pragma unroll
@@ -598,8 +597,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       epi_bar();   // staging / bias tables are reused by the next item
       if (et == 0 && it == 0) stamp(7);
       if (p.counters != nullptr) {
-        // split-K, in-kernel finalize: publish this item's partial tile (every thread fenced its own stores; the barrier
-        // above ordered them before this release increment)
+        // split-K, in-kernel finalize: publish this item's partial tile (bar.sync ordered every epilogue thread's stores
+        // before this thread; its gpu-scope fence is cumulative over them - the pattern of a cooperative grid sync)
         if (et == 0) {
           __threadfence();
           atomicAdd(p.counters + ws / p.splits, 1);
@@ -626,35 +625,64 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         epi_bar();
         const int rlo = t.split * rows_per, rhi = min(BM, rlo + rows_per);
-        for (int i = et; i < (rhi - rlo) * (BN / 4); i += nthr) {
-          const int rr = rlo + i / (BN / 4), c4 = i % (BN / 4);
-          long long m;
-          int b;
-          if (!row_coord(p, t, rr, m, b)) continue;
-          const int n = t.n0 + c4 * 4;
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          const float* src = p.partial + m * p.N + n;
-          for (int sp = 0; sp < S; ++sp) {
-            const float4 v = __ldcg(reinterpret_cast<const float4*>(src + (long long)sp * p.M * p.N));
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        const int total = (rhi - rlo) * (BN / 4);
+        const long long MN = (long long)p.M * p.N;
+        // two output quads per thread and four splits per round: 8 independent 16-byte L2 loads in flight per thread (the
+        // partials were written by other SMs: the reduction is L2-latency bound, not bandwidth bound)
+        for (int i0 = et; i0 < total; i0 += 2 * nthr) {
+          bool ok[2];
+          long long m[2];
+          int b[2], n[2];
+          const float* src[2];
+          float4 acc[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int i = i0 + e * nthr;
+            const int rr = rlo + i / (BN / 4), c4 = i % (BN / 4);
+            m[e] = 0;
+            b[e] = 0;
+            ok[e] = (i < total) && row_coord(p, t, rr, m[e], b[e]);
+            n[e] = t.n0 + c4 * 4;
+            src[e] = p.partial + m[e] * p.N + n[e];
+            acc[e] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
-          if (p.bias) {
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-            acc.x += bv.x; acc.y += bv.y; acc.z += bv.z; acc.w += bv.w;
+          for (int sp = 0; sp < S; sp += 4) {
+            float4 v[2][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+              for (int e = 0; e < 2; ++e)
+                if (ok[e] && sp + u < S) v[e][u] = __ldcg(reinterpret_cast<const float4*>(src[e] + (sp + u) * MN));
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+              for (int e = 0; e < 2; ++e)
+                if (ok[e] && sp + u < S) {     // split order 0..S-1: the summation order of mos_splitk_finalize
+                  acc[e].x += v[e][u].x; acc[e].y += v[e][u].y; acc[e].z += v[e][u].z; acc[e].w += v[e][u].w;
+                }
           }
-          if (p.bias_batch) {
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias_batch + (long long)b * p.bias_batch_ld + n));
-            acc.x += bv.x; acc.y += bv.y; acc.z += bv.z; acc.w += bv.w;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            if (!ok[e]) continue;
+            float4 a4 = acc[e];
+            if (p.bias) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n[e]));
+              a4.x += bv.x; a4.y += bv.y; a4.z += bv.z; a4.w += bv.w;
+            }
+            if (p.bias_batch) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias_batch + (long long)b[e] * p.bias_batch_ld + n[e]));
+              a4.x += bv.x; a4.y += bv.y; a4.z += bv.z; a4.w += bv.w;
+            }
+            if (p.residual) {
+              const uint2 rv = *reinterpret_cast<const uint2*>(p.residual + m[e] * p.ldr + n[e]);
+              const float2 r0 = unpack16x2<F16>(rv.x), r1 = unpack16x2<F16>(rv.y);
+              a4.x += r0.x; a4.y += r0.y; a4.z += r1.x; a4.w += r1.y;
+            }
+            uint2 o;
+            o.x = pack16x2<F16>(a4.x, a4.y);
+            o.y = pack16x2<F16>(a4.z, a4.w);
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + m[e] * p.ldc + n[e]) = o;
           }
-          if (p.residual) {
-            const uint2 rv = *reinterpret_cast<const uint2*>(p.residual + m * p.ldr + n);
-            const float2 a = unpack16x2<F16>(rv.x), c = unpack16x2<F16>(rv.y);
-            acc.x += a.x; acc.y += a.y; acc.z += c.x; acc.w += c.y;
-          }
-          uint2 o;
-          o.x = pack16x2<F16>(acc.x, acc.y);
-          o.y = pack16x2<F16>(acc.z, acc.w);
-          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldc + n) = o;
         }
         epi_bar();
         if (et == 0) {
