@@ -70,6 +70,7 @@ struct GemmDev {
   unsigned long long* tl;   // optional timeline buffer (mos_debug_set_timeline)
   int w_static;        // reserved (round-1 weight-prefetch experiment: neutral, removed)
   int* counters;       // split-K with in-kernel finalize: one arrival counter per output tile (zero between launches)
+  int stg_alias;       // the epilogue staging tile overlays pipeline stage 0.. (launches with <= 1 work item per CTA)
   const uint8_t* pf;   // optional: bytes to pull into L2 for a LATER launch (the next layer's weights), see mos_gemm_args
   long long pf_bytes;
 };
@@ -245,8 +246,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   // W rows held by one CTA per k-block: the whole tile (160, + 16 LoRA rows), or in a pair one half of N = 160 / 176
   const int b_rows = PAIR ? (p.lora ? (BN + LORA_N) / 2 : BN / 2) : (p.lora ? BN + LORA_N : BN);
   const int stage_bytes = A_STAGE_BYTES + b_rows * 128;
-  uint8_t* stg = smem + p.stages * stage_bytes;                    // epilogue staging tile [128][STG_PITCH]
-  float* cb_s = reinterpret_cast<float*>(stg + STG_BYTES);          // [4][BN] bias (+ per-batch bias)
+  // epilogue staging tile [128][STG_PITCH]: behind the pipeline stages, or - when every CTA has at most one work item, so
+  // that no load of a following item can be in flight during an epilogue - on top of stage 0.., which buys two more stages
+  uint8_t* tables = smem + p.stages * stage_bytes;
+  uint8_t* stg = p.stg_alias ? smem : tables;
+  float* cb_s = reinterpret_cast<float*>(p.stg_alias ? tables : tables + STG_BYTES);   // [4][BN] bias (+ per-batch bias)
   float4* up_s = reinterpret_cast<float4*>(cb_s + 4 * BN);          // [BN] LoRA up rows (pre-scaled by alpha)
 
   __shared__ uint64_t full_bar[MAX_STAGES];
@@ -411,7 +415,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         row_coord(p, t, 0, m_first, b_lo);
       }
       // ---- 1. residual tile -> staging (coalesced 16-byte cp.async, in flight while the bias tables are staged)
-      if (staged && p.residual) {
+      if (staged && p.residual && !p.stg_alias) {
         __nv_bfloat16* rbase = const_cast<__nv_bfloat16*>(p.residual);
         if (p.geglu) stage_copy<BN / 16, false>(p, t, stg, rbase, p.ldr, t.n0 / 2, et);
         else stage_copy<BN / 8, false>(p, t, stg, rbase, p.ldr, t.n0, et);
@@ -438,6 +442,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       __syncwarp();
       tc_fence_after();
       if (et == 0 && it == 0) stamp(5);
+      if (staged && p.residual && p.stg_alias) {
+        // every MMA of the (only) item has retired, so every TMA load has landed and been consumed: the pipeline stages
+        // are free to carry the staging tile
+        __nv_bfloat16* rbase = const_cast<__nv_bfloat16*>(p.residual);
+        if (p.geglu) stage_copy<BN / 16, false>(p, t, stg, rbase, p.ldr, t.n0 / 2, et);
+        else stage_copy<BN / 8, false>(p, t, stg, rbase, p.ldr, t.n0, et);
+        cp_async_wait_all();
+        epi_bar();
+      }
       const uint32_t trow = tmem_base + acc * ACC_STRIDE + (uint32_t(q * 32) << 16);
       const int bsel = min(max(b - b_lo, 0), 3);
       const float* cb = cb_s + bsel * BN;
@@ -956,20 +969,31 @@ extern "C" int mos_gemm_bf16(const mos_gemm_args* a, void* stream_) {
   p.total_super = p.n_tiles * (pair ? m_tiles / 2 : m_tiles) * splits;
   p.nbatch = a->conv ? a->B : (int)ceil_div(a->M, p.rows_per_batch);
 
-  const int b_rows = pair ? (int)wrows0 : (lora ? BN + LORA_N : BN);
-  const int stage_bytes = A_STAGE_BYTES + b_rows * 128;
-  int stages = a->stages > 0 ? a->stages : MAX_STAGES;
-  if (stages > MAX_STAGES) stages = MAX_STAGES;
-  while (stages * stage_bytes + EPI_SMEM_BYTES + 1024 > MAX_DYN_SMEM) --stages;
-  if (stages < 2) stages = 2;
-  p.stages = stages;
-  const int smem_bytes = stages * stage_bytes + EPI_SMEM_BYTES + 1024;
-
-  static int num_sms = 0;
+  static int num_sms = 0, stg_alias_env = -1;
+  if (stg_alias_env < 0) {
+    const char* e = getenv("MOS_GEMM_STG_ALIAS");
+    stg_alias_env = (e && e[0] == '0') ? 0 : 1;
+  }
   if (num_sms == 0) {
     int dev = 0;
     MOS_CHECK_CUDA(cudaGetDevice(&dev));
     MOS_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int b_rows = pair ? (int)wrows0 : (lora ? BN + LORA_N : BN);
+  const int stage_bytes = A_STAGE_BYTES + b_rows * 128;
+  // one work item per CTA at most (the common case of the batch-2 step): the staging tile overlays the pipeline stages
+  p.stg_alias = (stg_alias_env && !pair && p.total_super <= num_sms && 2 * stage_bytes >= STG_BYTES) ? 1 : 0;
+  const int epi_bytes = p.stg_alias ? EPI_SMEM_BYTES - STG_BYTES : EPI_SMEM_BYTES;
+  int stages = a->stages > 0 ? a->stages : MAX_STAGES;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  while (stages * stage_bytes + epi_bytes + 1024 > MAX_DYN_SMEM) --stages;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  const int smem_bytes = stages * stage_bytes + epi_bytes + 1024;
+
+  static bool configured = false;
+  if (!configured) {
+    configured = true;
     MOS_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM));
     MOS_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM));
     MOS_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM));

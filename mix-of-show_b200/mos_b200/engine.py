@@ -25,7 +25,7 @@ F16 = torch.float16
 PREFETCH_W = os.environ.get('MOS_GEMM_PREFETCH_W') == '1'      # (kept for the bench history; the library ignores w_static)
 # split-K GEMMs finalize in-kernel (mos_gemm_args.tile_counters); MOS_SPLITK_FUSED=0 restores the separate
 # mos_splitk_finalize launch (A/B timing, profiles/README.md)
-FUSED_SPLITK = os.environ.get('MOS_SPLITK_FUSED', '1') != '0'
+FUSED_SPLITK = os.environ.get('MOS_SPLITK_FUSED', '0') == '1'
 # every GEMM of the step stages the NEXT GEMM's weight matrix in L2 while it runs (mos_gemm_args.prefetch_ptr): the step
 # streams 1.7 GB of weights through a mostly idle HBM, the 126 MB L2 holds any single layer.  MOS_L2_PREFETCH=0/1.
 L2_PREFETCH = os.environ.get('MOS_L2_PREFETCH', '0') == '1'

@@ -32,3 +32,4 @@ python tools/ncu_summary.py /tmp/r2_kernels.ncu-rep gpurun_out/r2_kernels 2>&1 |
 echo "#### small report (GEMM conv, both tile modes, + d=40 attention) for the source view"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'attn_kernel|gemm_kernel' -c 8 -o gpurun_out/r2_top -f python tools/ncu_targets.py > /dev/null 2>&1; ls -la gpurun_out/*.ncu-rep
 du -sh gpurun_out
+echo "#### gemm stage sweep"; timeout 300 python tools/gemm_stage_sweep.py 2>&1 | tail -16
