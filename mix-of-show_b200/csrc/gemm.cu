@@ -969,10 +969,14 @@ extern "C" int mos_gemm_bf16(const mos_gemm_args* a, void* stream_) {
   p.total_super = p.n_tiles * (pair ? m_tiles / 2 : m_tiles) * splits;
   p.nbatch = a->conv ? a->B : (int)ceil_div(a->M, p.rows_per_batch);
 
-  static int num_sms = 0, stg_alias_env = -1;
+  // MOS_GEMM_STG_ALIAS=1: staging tile on top of the pipeline stages (measured slower: the residual prefetch moves behind the
+  // mainloop and more than 3 stages buy nothing, tools/gemm_stage_sweep.py).  MOS_GEMM_STAGES=n: default pipeline depth.
+  static int num_sms = 0, stg_alias_env = -1, stages_env = 0;
   if (stg_alias_env < 0) {
     const char* e = getenv("MOS_GEMM_STG_ALIAS");
-    stg_alias_env = (e && e[0] == '0') ? 0 : 1;
+    stg_alias_env = (e && e[0] == '1') ? 1 : 0;
+    const char* st = getenv("MOS_GEMM_STAGES");
+    if (st) stages_env = atoi(st);
   }
   if (num_sms == 0) {
     int dev = 0;
@@ -984,7 +988,7 @@ extern "C" int mos_gemm_bf16(const mos_gemm_args* a, void* stream_) {
   // one work item per CTA at most (the common case of the batch-2 step): the staging tile overlays the pipeline stages
   p.stg_alias = (stg_alias_env && !pair && p.total_super <= num_sms && 2 * stage_bytes >= STG_BYTES) ? 1 : 0;
   const int epi_bytes = p.stg_alias ? EPI_SMEM_BYTES - STG_BYTES : EPI_SMEM_BYTES;
-  int stages = a->stages > 0 ? a->stages : MAX_STAGES;
+  int stages = a->stages > 0 ? a->stages : (stages_env > 0 ? stages_env : MAX_STAGES);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   while (stages * stage_bytes + epi_bytes + 1024 > MAX_DYN_SMEM) --stages;
   if (stages < 2) stages = 2;
