@@ -100,17 +100,28 @@ def build_workload(tiny=False, images=1):
     `UNet2DConditionModel` container (PyTorch default inits under manual_seed(0), diffusers parameter names), a rank-4
     ED-LoRA on every attention projection (down ~ kaiming-uniform(a=sqrt(5)) as edlora.py:238, up ~ N(0, 0.02^2) so the
     low-rank path is exercised) and random latents / layer-wise text embeddings."""
-    import math
-
     import torch
     from mixofshow.models.unet_b200 import UNet2DConditionModel
-    from mos_b200.engine import cross_attention_names
     cfg = TINY if tiny else None
     torch.manual_seed(0)
     model = UNet2DConditionModel(**(cfg or {}))
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     del model
-    g = torch.Generator().manual_seed(10)
+    lora = random_unet_lora(sd, cfg, seed=10)
+    H = W = 64
+    lat = torch.randn(images, 4, H, W, generator=torch.Generator().manual_seed(1))
+    ehs = torch.randn(2 * images, 16, 77, 768, generator=torch.Generator().manual_seed(2))   # [uncond x n | cond x n]
+    return sd, lora, lat, ehs, cfg
+
+
+def random_unet_lora(sd, cfg=None, seed=10):
+    """A random rank-4 ED-LoRA on every attention projection of `sd` (reference key layout: <module>.lora_down.weight
+    [4, in], <module>.lora_up.weight [out, 4]); down ~ kaiming-uniform(a=sqrt(5)) (edlora.py:238), up ~ N(0, 0.02^2)."""
+    import math
+
+    import torch
+    from mos_b200.engine import cross_attention_names
+    g = torch.Generator().manual_seed(seed)
     names = cross_attention_names(cfg['block_out_channels'], cfg['layers_per_block']) if cfg else cross_attention_names()
     lora = {}
     for an in names:
@@ -121,10 +132,7 @@ def build_workload(tiny=False, images=1):
                 cout, cin = sd[m + '.weight'].shape
                 lora[m + '.lora_down.weight'] = (torch.rand(4, cin, generator=g) * 2 - 1) / math.sqrt(cin)
                 lora[m + '.lora_up.weight'] = torch.randn(cout, 4, generator=g) * 0.02
-    H = W = 64
-    lat = torch.randn(images, 4, H, W, generator=torch.Generator().manual_seed(1))
-    ehs = torch.randn(2 * images, 16, 77, 768, generator=torch.Generator().manual_seed(2))   # [uncond x n | cond x n]
-    return sd, lora, lat, ehs, cfg
+    return lora
 
 
 def build_pipeline(sd, lora, cfg, dev):

@@ -12,17 +12,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, 'mix-of-show_b200')]
 import torch  # noqa: E402
 
-from oracle import inject  # noqa: E402
-from oracle import unet as ou  # noqa: E402
+import bench  # noqa: E402  (synthetic SD1.5-topology weights / LoRAs; no oracle on this path)
 
 
 def regional(steps=30):
     from mos_b200 import ops
     from mos_b200.engine import UNetEngine, ehs_to_layer_major
     from mos_b200.scheduler import DPMSolverPP2M
-    ref = ou.build_unet(0)
-    sd = {k: v.detach() for k, v in ref.state_dict().items()}
-    del ref
+    sd = bench.build_workload(False)[0]
     H, W = 96, 192                      # latent size of 768 x 1536
     B = 2                               # CFG
     eng = UNetEngine(sd, B, H, W)       # fused checkpoint: LoRA already merged into the weights (regional :56-63)
@@ -72,10 +69,8 @@ def regional(steps=30):
 
 def fusion():
     import gradient_fusion as gf
-    ref = ou.build_unet(0)
-    sd = {k: v.detach().clone() for k, v in ref.state_dict().items()}
-    loras = [inject.random_lora_state(ref, seed=10 + c) for c in range(5)]
-    del ref
+    sd = bench.build_workload(False)[0]
+    loras = [bench.random_unet_lora(sd, None, seed=10 + c) for c in range(5)]
     spatial = [{k: v for k, v in l.items() if 'attn2.to_k' not in k and 'attn2.to_v' not in k} for l in loras]
     crosskv = [{k: v for k, v in l.items() if 'attn2.to_k' in k or 'attn2.to_v' in k} for l in loras]
     alphas = [1.0] * 5

@@ -34,12 +34,8 @@ def main():
     from mos_b200 import dp
     from mos_b200.engine import ehs_to_layer_major
     from mos_b200.train_engine import TrainEngine
-    from oracle import inject
-    from oracle import unet as ou
-    ref = ou.build_unet(0)
-    lora = inject.random_lora_state(ref, seed=10)
-    sd = {k: v.detach() for k, v in ref.state_dict().items()}
-    del ref
+    import bench
+    sd, lora = bench.build_workload(False)[:2]
     B = a.batch
     eng = TrainEngine(sd, B, 64, 64, lora=lora, attn_reg_weight=None if a.no_reg else 0.01)
     g = torch.Generator().manual_seed(100 + rank)

@@ -12,17 +12,13 @@ import torch  # noqa: E402
 from mos_b200 import ops  # noqa: E402
 from mos_b200.engine import ehs_to_layer_major  # noqa: E402
 from mos_b200.train_engine import TrainEngine  # noqa: E402
-from oracle import inject  # noqa: E402
-from oracle import unet as ou  # noqa: E402
+import bench  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument('--batch', type=int, default=4)
 a = ap.parse_args()
 B = a.batch
-ref = ou.build_unet(0)
-lora = inject.random_lora_state(ref, seed=10)
-sd = {k: v.detach() for k, v in ref.state_dict().items()}
-del ref
+sd, lora = bench.build_workload(False)[:2]
 eng = TrainEngine(sd, B, 64, 64, lora=lora, attn_reg_weight=0.01)
 g = torch.Generator().manual_seed(100)
 x0 = torch.randn(B, 4, 64, 64, generator=g).cuda()
