@@ -235,6 +235,13 @@ int mos_vec_dot(const float* a, const float* b, int64_t n, float* out, float* sc
 int mos_vec_asum(const float* a, int64_t n, float* out, float* scratch, void* stream);
 int mos_vec_absmax(const float* a, int64_t n, float scale, float* out, float* scratch, void* stream);
 int mos_vec_axpby(float* y, const float* x, float alpha, float beta, int64_t n, void* stream);
+/* L-BFGS direction d = -H g by the two-loop recursion (torch.optim.LBFGS as driven by gradient_fusion.py:76-85) over k
+ * curvature pairs, and gtd[0] = <g, d>, without host round trips: 2k + 1 launches, every coefficient stays in device memory.
+ * S, Y: HOST arrays of k device pointers (fp32 [n], oldest pair first); rho[i] = 1 / <y_i, s_i> and h_diag = <y, s> / <y, y>
+ * of the newest pair: host values.  Bit-identical to the same recursion driven from the host with mos_vec_dot /
+ * mos_vec_axpby.  work: >= k + 1 doubles; partial: >= 257 floats with partial[256] == 0 on entry (left zero). */
+int mos_lbfgs_direction(const void* const* S, const void* const* Y, const double* rho, int32_t k, const float* g,
+                        float h_diag, int64_t n, float* d, double* work, float* partial, float* gtd, void* stream);
 /* Batched W_l += alpha * up_l @ down_l (convert_edlora_to_diffusers.py:33-76, gradient_fusion.py:99-143).
  * table_dev: int64 [n_layers, 6] = {W fp32 ptr, down fp32 ptr, up fp32 ptr, out, in, rank}. */
 int mos_lora_merge(const int64_t* table_dev, int32_t n_layers, float alpha, void* stream);

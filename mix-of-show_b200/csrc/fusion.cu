@@ -105,42 +105,76 @@ sgemm_nn_kernel(const float* __restrict__ A, const float* __restrict__ B, float*
 // The Gram form squares the condition number of the least-squares problem; the product D G must therefore be carried
 // in fp64 for the solver to reach the residual the reference reaches with its direct fp32 MSE (measured: 2e-5 vs
 // 6e-7 relative residual on an exactly solvable problem with an fp32 product).  <= 4.2 GFLOP per closure.
+template <int TM>   // rows per CTA tile: 64 (4 x 4 per thread) or 32 (2 x 4 per thread, for grids that would not fill the chip)
 __global__ void __launch_bounds__(256)
 dgemm_mixed_kernel(const float* __restrict__ A, const double* __restrict__ B, double* __restrict__ C, int M, int N,
                    int K) {
-  __shared__ double As[16][64 + 2], Bs[16][64 + 2];
+  // every output element accumulates fma(a, b, acc) over k ascending, whatever the tiling: results do not depend on TM.
+  // Global loads of tile t + 1 are issued before the products of tile t (register prefetch, double-buffered smem).
+  constexpr int RI = TM / 16;                 // rows per thread
+  constexpr int AL = TM * 16 / 256;           // A elements per thread and tile (4 or 2)
+  __shared__ double As[2][16][TM + 2], Bs[2][16][64 + 2];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-  double acc[4][4];
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * 64;
+  double acc[RI][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < RI; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+  float ra[AL];
+  double rb[4];
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int u = 0; u < AL; ++u) {
+      const int i = threadIdx.x + u * 256;
       const int m = i >> 4, k = i & 15;
-      As[k][m] = (m0 + m < M && k0 + k < K) ? (double)A[(long long)(m0 + m) * K + k0 + k] : 0.0;
-      const int kk = i >> 6, n = i & 63;
-      Bs[kk][n] = (k0 + kk < K && n0 + n < N) ? B[(long long)(k0 + kk) * N + n0 + n] : 0.0;
+      ra[u] = (m0 + m < M && k0 + k < K) ? __ldg(A + (long long)(m0 + m) * K + k0 + k) : 0.f;
     }
-    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = threadIdx.x + u * 256;
+      const int kk = i >> 6, n = i & 63;
+      rb[u] = (k0 + kk < K && n0 + n < N) ? __ldg(B + (long long)(k0 + kk) * N + n0 + n) : 0.0;
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int u = 0; u < AL; ++u) {
+      const int i = threadIdx.x + u * 256;
+      As[buf][i & 15][i >> 4] = (double)ra[u];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = threadIdx.x + u * 256;
+      Bs[buf][i >> 6][i & 63] = rb[u];
+    }
+  };
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    const bool more = k0 + 16 < K;
+    if (more) gload(k0 + 16);
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      double a[4], b[4];
+      double a[RI], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+      for (int i = 0; i < RI; ++i) a[i] = As[buf][k][ty * RI + i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+      for (int j = 0; j < 4; ++j) b[j] = Bs[buf][k][tx * 4 + j];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < RI; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
     }
+    if (more) sstore(buf ^ 1);
     __syncthreads();
+    buf ^= 1;
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+  for (int i = 0; i < RI; ++i) {
+    const int m = m0 + ty * RI + i;
     if (m >= M) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -257,6 +291,67 @@ __global__ void vec_axpby_kernel(float* __restrict__ y, const float* __restrict_
     y[i] = alpha * x[i] + (beta != 0.f ? beta * y[i] : 0.f);
 }
 
+// ------------------------------------------------------------------ L-BFGS two-loop recursion without host round trips
+// One launch per history pair and loop: v <- v + c * upd (c = the coefficient the PREVIOUS launch left in device memory), then
+// the dot product of the updated v with the next history vector, reduced by the last-arriving block exactly like
+// vec_dot_kernel + reduce_partials_kernel (same grid, same partial layout, same final tree), so the direction equals the
+// host-driven recursion bit for bit.  mode 0: first loop (al_i = rho_i <s_i, q>, next coefficient -al_i); mode 1: second loop
+// (be_i = rho_i <y_i, r>, next coefficient al_i - be_i); mode 2: final update, dot with g -> gtd.
+struct LbfgsStep {
+  float* v;               // q / r, updated in place
+  const float* g;         // first step only: v = -g
+  const float* upd;       // vector added with the incoming coefficient (NULL: none)
+  const float* dotv;      // vector of the dot product
+  long long n;
+  double rho;             // rho_i of this step (modes 0, 1)
+  float h_diag;           // applied after the update when scale != 0 (transition q -> r = H0 q)
+  int first, scale, mode, idx;
+  double* al;             // [k] device: al_i
+  double* coef;           // [1] device: coefficient for the next launch
+  float* partial;         // [RED_BLOCKS]
+  unsigned* counter;      // [1], zero between launches
+  float* gtd;             // mode 2: <g, d>
+};
+__global__ void __launch_bounds__(256) lbfgs_step_kernel(const LbfgsStep p) {
+  __shared__ float sh[32];
+  __shared__ int last;
+  const float c = (p.upd != nullptr) ? (float)(*p.coef) : 0.f;
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
+    float v = p.first ? -1.0f * p.g[i] : p.v[i];
+    if (p.upd != nullptr) v = c * p.upd[i] + v;          // contracted to one fma, as vec_axpby_kernel's alpha * x + 1 * y
+    if (p.scale) v = p.h_diag * v;
+    p.v[i] = v;
+    acc += p.dotv[i] * v;                                // vec_dot_kernel's a[i] * b[i] with a = history vector
+  }
+  const float t = block_sum(acc, sh);
+  if (threadIdx.x == 0) {
+    p.partial[blockIdx.x] = t;
+    __threadfence();
+    last = (atomicAdd(p.counter, 1u) == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float vsum = 0.f;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) vsum += __ldcg(p.partial + i);
+  const float dot = block_sum(vsum, sh);
+  if (threadIdx.x == 0) {
+    const float d1 = 1.f * dot + 0.f;                    // reduce_partials_kernel: scale * t + add
+    if (p.mode == 0) {
+      const double al = (double)d1 * p.rho;
+      p.al[p.idx] = al;
+      *p.coef = -al;
+    } else if (p.mode == 1) {
+      const double be = (double)d1 * p.rho;
+      *p.coef = p.al[p.idx] - be;
+    } else {
+      *p.gtd = d1;
+    }
+    *p.counter = 0u;
+  }
+}
+
 // ------------------------------------------------------------------ batched LoRA merge: W_l += alpha * up_l @ down_l
 // table[l] = {W ptr, down ptr, up ptr, out, in, rank}; W fp32 [out, in] (4-D 1x1 conv weights have the same layout)
 __global__ void lora_merge_kernel(const long long* __restrict__ table, float alpha) {
@@ -320,8 +415,13 @@ extern "C" int mos_sgemm_nn(const float* A, const float* B, float* C, int32_t M,
 extern "C" int mos_dgemm_mixed(const float* A, const double* B, double* C, int32_t M, int32_t N, int32_t K,
                                void* stream) {
   MOS_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0, "mos_dgemm_mixed: bad arguments");
-  dim3 grid((unsigned)ceil_div(N, 64), (unsigned)ceil_div(M, 64));
-  dgemm_mixed_kernel<<<grid, 256, 0, STREAM(stream)>>>(A, B, C, M, N, K);
+  if (ceil_div(N, 64) * ceil_div(M, 64) < 148) {     // too few 64-row tiles for the chip: 32-row tiles
+    dim3 grid((unsigned)ceil_div(N, 64), (unsigned)ceil_div(M, 32));
+    dgemm_mixed_kernel<32><<<grid, 256, 0, STREAM(stream)>>>(A, B, C, M, N, K);
+  } else {
+    dim3 grid((unsigned)ceil_div(N, 64), (unsigned)ceil_div(M, 64));
+    dgemm_mixed_kernel<64><<<grid, 256, 0, STREAM(stream)>>>(A, B, C, M, N, K);
+  }
   MOS_CHECK_LAUNCH();
   return MOS_OK;
 }
@@ -368,6 +468,66 @@ extern "C" int mos_vec_axpby(float* y, const float* x, float alpha, float beta, 
   long long blocks = ceil_div(n, 256 * 4);
   if (blocks > 1184) blocks = 1184;
   vec_axpby_kernel<<<(unsigned)blocks, 256, 0, STREAM(stream)>>>(y, x, alpha, beta, n);
+  MOS_CHECK_LAUNCH();
+  return MOS_OK;
+}
+
+// d = -H g by the two-loop recursion over k curvature pairs (S[i], Y[i] host arrays of device pointers, oldest first; rho[i] =
+// 1 / <y_i, s_i> and h_diag host values) and gtd[0] = <g, d>; 2k + 1 launches, no host synchronisation.
+// work: >= k + 1 doubles, partial: >= 257 floats (device scratch; partial[256] is the block counter and must be zero on entry -
+// the launches leave it zero).
+extern "C" int mos_lbfgs_direction(const void* const* S, const void* const* Y, const double* rho, int32_t k, const float* g,
+                                   float h_diag, int64_t n, float* d, double* work, float* partial, float* gtd,
+                                   void* stream) {
+  MOS_CHECK_ARG(g && d && work && partial && gtd && n > 0 && k >= 0 && (k == 0 || (S && Y && rho)),
+                "mos_lbfgs_direction: bad arguments");
+  LbfgsStep p;
+  memset(&p, 0, sizeof(p));
+  p.v = d;
+  p.g = g;
+  p.n = n;
+  p.al = work;
+  p.coef = work + k;
+  p.partial = partial;
+  p.counter = reinterpret_cast<unsigned*>(partial + RED_BLOCKS);
+  p.gtd = gtd;
+  p.h_diag = h_diag;
+  bool first = true;
+  const float* pending = nullptr;      // vector whose update (with the coefficient in *coef) the next launch applies
+  for (int i = k - 1; i >= 0; --i) {   // first loop: q -= al_i y_i
+    p.first = first ? 1 : 0;
+    p.upd = pending;
+    p.scale = 0;
+    p.dotv = reinterpret_cast<const float*>(S[i]);
+    p.mode = 0;
+    p.idx = i;
+    p.rho = rho[i];
+    lbfgs_step_kernel<<<RED_BLOCKS, 256, 0, STREAM(stream)>>>(p);
+    MOS_CHECK_LAUNCH();
+    first = false;
+    pending = reinterpret_cast<const float*>(Y[i]);
+  }
+  bool scale = true;                   // r = h_diag * q, applied by the first launch after the first loop
+  for (int i = 0; i < k; ++i) {        // second loop: r += (al_i - be_i) s_i
+    p.first = first ? 1 : 0;
+    p.upd = pending;
+    p.scale = scale ? 1 : 0;
+    p.dotv = reinterpret_cast<const float*>(Y[i]);
+    p.mode = 1;
+    p.idx = i;
+    p.rho = rho[i];
+    lbfgs_step_kernel<<<RED_BLOCKS, 256, 0, STREAM(stream)>>>(p);
+    MOS_CHECK_LAUNCH();
+    first = false;
+    scale = false;
+    pending = reinterpret_cast<const float*>(S[i]);
+  }
+  p.first = first ? 1 : 0;
+  p.upd = pending;
+  p.scale = scale ? 1 : 0;
+  p.dotv = g;
+  p.mode = 2;
+  lbfgs_step_kernel<<<RED_BLOCKS, 256, 0, STREAM(stream)>>>(p);
   MOS_CHECK_LAUNCH();
   return MOS_OK;
 }

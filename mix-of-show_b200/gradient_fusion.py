@@ -55,10 +55,29 @@ class _GramProblem:
         self.scratch64 = torch.empty(256, device=dev, dtype=torch.float64)
         self.best_loss, self.best_D = float('inf'), None
         self.evals = 0
+        # mos_lbfgs_direction: device coefficients, partial sums + block counter (zero between launches), <g, d>
+        self.work = torch.zeros(64, device=dev, dtype=torch.float64)
+        self.partial = torch.zeros(260, device=dev, dtype=F32)
+        self.gtd = torch.zeros(1, device=dev, dtype=F32)
+        self.scal2 = torch.zeros(2, device=dev, dtype=F32)
 
     def dot(self, a, b):
         ops.vec_dot(a, b, self.scal, self.scratch)
         return self.scal.item()
+
+    def dot2(self, a, b, c, d):
+        """(<a, b>, <c, d>) with one host synchronisation"""
+        ops.vec_dot(a, b, self.scal2[0:1], self.scratch)
+        ops.vec_dot(c, d, self.scal2[1:2], self.scratch)
+        r = self.scal2.tolist()
+        return r[0], r[1]
+
+    def absmax2(self, a, b, scale_b):
+        """(max |a|, max |scale_b b|) with one host synchronisation"""
+        ops.vec_absmax(a, self.scal2[0:1], self.scratch, 1.0)
+        ops.vec_absmax(b, self.scal2[1:2], self.scratch, scale_b)
+        r = self.scal2.tolist()
+        return r[0], r[1]
 
     def absmax(self, a, scale=1.0):
         ops.vec_absmax(a, self.scal, self.scratch, scale)
@@ -159,6 +178,7 @@ def lbfgs_minimize(P, x0, max_iter, history=25, lr=1.0, tol_grad=1e-16, tol_chan
     n_iter = 0
     while n_iter < max_iter:
         n_iter += 1
+        dev_gtd = False
         if n_iter == 1:
             d = g.clone()
             ops.vec_axpby(d, g, -1.0, 0.0)                      # d = -g
@@ -167,31 +187,24 @@ def lbfgs_minimize(P, x0, max_iter, history=25, lr=1.0, tol_grad=1e-16, tol_chan
             ops.vec_axpby(y, prev_g, -1.0, 1.0)                 # y = g - prev_g
             s = torch.empty_like(d)
             ops.vec_axpby(s, d, t, 0.0)                         # s = t d
-            ys = P.dot(y, s)
+            ys, yy = P.dot2(y, s, y, y)
             if ys > 1e-10:
                 if len(S) == history:
                     S.pop(0), Y.pop(0), rho.pop(0)
                 S.append(s), Y.append(y), rho.append(1.0 / ys)
-                h_diag = ys / P.dot(y, y)
-            k = len(S)
-            al = [0.0] * k
-            q = torch.empty_like(g)
-            ops.vec_axpby(q, g, -1.0, 0.0)                      # two-loop recursion on q = -g
-            for i in range(k - 1, -1, -1):
-                al[i] = P.dot(S[i], q) * rho[i]
-                ops.vec_axpby(q, Y[i], -al[i], 1.0)
-            d = q
-            ops.vec_axpby(d, d, h_diag, 0.0)                    # r = H0 q
-            for i in range(k):
-                be = P.dot(Y[i], d) * rho[i]
-                ops.vec_axpby(d, S[i], al[i] - be, 1.0)
+                h_diag = ys / yy
+            # two-loop recursion on q = -g, r = H0 q (one C-ABI call, 2k + 1 launches, coefficients stay on the device;
+            # bit-identical to the recursion driven from here with vec_dot / vec_axpby), and <g, d> for the test below
+            d = torch.empty_like(g)
+            ops.lbfgs_direction(S, Y, rho, g, h_diag, d, P.work, P.partial, P.gtd)
+            dev_gtd = True
         prev_g, prev_loss = g.clone(), loss
         if n_iter == 1:
             ops.vec_asum(g, P.scal, P.scratch)                  # |g|_1
             t = min(1.0, 1.0 / P.scal.item()) * lr
         else:
             t = lr
-        gtd = P.dot(g, d)
+        gtd = P.gtd.item() if dev_gtd else P.dot(g, d)
         if gtd > -tol_change:
             break
         loss, g, t, ls_evals = _strong_wolfe(P, x, t, d, loss, g, gtd)
@@ -199,7 +212,8 @@ def lbfgs_minimize(P, x0, max_iter, history=25, lr=1.0, tol_grad=1e-16, tol_chan
         evals += ls_evals
         if n_iter == max_iter or evals >= max_eval:
             break
-        if P.absmax(g) <= tol_grad or P.absmax(d, t) <= tol_change or abs(loss - prev_loss) < tol_change:
+        g_max, step_max = P.absmax2(g, d, t)
+        if g_max <= tol_grad or step_max <= tol_change or abs(loss - prev_loss) < tol_change:
             break
     return x
 

@@ -286,6 +286,19 @@ def vec_absmax(a, out, scratch, scale=1.0):
                                     _s()), 'mos_vec_absmax')
 
 
+def lbfgs_direction(S, Y, rho, g, h_diag, d, work, partial, gtd):
+    """d = -H g (two-loop recursion over the pairs S[i], Y[i], oldest first) and gtd[0] = <g, d>; no host synchronisation."""
+    k = len(S)
+    PtrArr = ctypes.c_void_p * max(k, 1)
+    Sp, Yp = PtrArr(*[t.data_ptr() for t in S]), PtrArr(*[t.data_ptr() for t in Y])
+    rh = (ctypes.c_double * max(k, 1))(*[float(r) for r in rho])
+    assert work.dtype == torch.float64 and work.numel() >= k + 1 and partial.numel() >= 257
+    check(_lib.lib().mos_lbfgs_direction(Sp, Yp, rh, ctypes.c_int32(k), ptr(g), ctypes.c_float(h_diag),
+                                         ctypes.c_int64(g.numel()), ptr(d), ptr(work), ptr(partial), ptr(gtd), _s()),
+          'mos_lbfgs_direction')
+    return d
+
+
 def vec_axpby(y, x, alpha, beta=1.0):
     check(_lib.lib().mos_vec_axpby(ptr(y), ptr(x), ctypes.c_float(alpha), ctypes.c_float(beta),
                                    ctypes.c_int64(y.numel()), _s()), 'mos_vec_axpby')

@@ -49,6 +49,61 @@ def test_vector_primitives_and_sgemm(cuda):
     assert rel(g1, X.double().t() @ X.double()) < 1e-5 and rel(g2, X.double().t() @ Y.double()) < 1e-5
 
 
+@pytest.mark.parametrize('k', [0, 1, 7, 25])
+@pytest.mark.parametrize('n', [245760, 100003])
+def test_lbfgs_direction_bit_identical_to_host_recursion(cuda, k, n):
+    """mos_lbfgs_direction (2k + 1 launches, coefficients on the device) vs the two-loop recursion driven from the host with
+    vec_dot / vec_axpby exactly as gradient_fusion.lbfgs_minimize did before: same bits for d and <g, d>; twice in a row
+    (the block counter must return to zero)."""
+    from mos_b200 import ops
+    gen = torch.Generator().manual_seed(7 + k)
+    g = torch.randn(n, generator=gen).to(cuda)
+    S = [(torch.randn(n, generator=gen) * 0.1).to(cuda) for _ in range(k)]
+    Y = [(S[i] * (1.0 + 0.1 * i) + 0.05 * torch.randn(n, generator=gen).to(cuda)) for i in range(k)]
+    scal, scratch = torch.zeros(1, device=cuda), torch.empty(256, device=cuda)
+
+    def dot(a, b):
+        ops.vec_dot(a, b, scal, scratch)
+        return scal.item()
+
+    rho = [1.0 / dot(Y[i], S[i]) for i in range(k)]
+    h_diag = dot(Y[-1], S[-1]) / dot(Y[-1], Y[-1]) if k else 0.37
+    # host-driven reference (the former code of lbfgs_minimize)
+    al = [0.0] * k
+    q = torch.empty_like(g)
+    ops.vec_axpby(q, g, -1.0, 0.0)
+    for i in range(k - 1, -1, -1):
+        al[i] = dot(S[i], q) * rho[i]
+        ops.vec_axpby(q, Y[i], -al[i], 1.0)
+    ops.vec_axpby(q, q, h_diag, 0.0)
+    for i in range(k):
+        be = dot(Y[i], q) * rho[i]
+        ops.vec_axpby(q, S[i], al[i] - be, 1.0)
+    gtd_ref = dot(g, q)
+    work = torch.zeros(64, device=cuda, dtype=torch.float64)
+    partial = torch.zeros(260, device=cuda)
+    gtd = torch.zeros(1, device=cuda)
+    for rep in range(2):
+        d = torch.full_like(g, float('nan'))
+        ops.lbfgs_direction(S, Y, rho, g, h_diag, d, work, partial, gtd)
+        torch.cuda.synchronize()
+        assert torch.equal(d.view(torch.int32), q.view(torch.int32)), f'k={k} rep={rep}'
+        assert gtd.item() == gtd_ref
+        assert partial[256].item() == 0
+
+
+def test_dgemm_mixed_tilings(cuda):
+    """the fp64 closure product in both tilings (32- and 64-row CTA tiles) vs torch fp64"""
+    from mos_b200 import ops
+    for M, K, N in ((320, 768, 768), (1280, 1280, 1280), (100, 70, 130)):
+        A = torch.randn(M, K, device=cuda)
+        B = torch.randn(K, N, device=cuda, dtype=torch.float64)
+        C = torch.empty(M, N, device=cuda, dtype=torch.float64)
+        ops.dgemm_mixed(A, B, C)
+        ref = A.double() @ B
+        assert ((C - ref).norm() / ref.norm()).item() < 1e-13
+
+
 def test_gram_accumulate_tensor_core(cuda):
     from gradient_fusion import GramRecorder
     rec = GramRecorder(cuda)
