@@ -90,8 +90,17 @@ class CLIPTextModel:
             for eng in self._engines.values():
                 eng.set_token_embedding(self._sd[TOKEN_KEY])
             self._emb_dirty = False
-        n = input_ids.shape[0]
+        n, L = input_ids.shape
         eng = self._engines.get(n)
         if eng is None:
             eng = self._engines[n] = CLIPTextEngine(self._sd, n, **self._kw)
+        T = eng.T
+        if L > T:
+            raise ValueError(f'sequence length {L} exceeds max_position_embeddings {T}')
+        if L < T:
+            # un-padded prompts (gradient_fusion.py:190-199 feeds them one by one): the encoder is causal, so the hidden
+            # states of the first L positions do not depend on what follows - run the fixed-length engine on the sequence
+            # padded with its own last id and return the first L positions
+            pad = input_ids[:, -1:].expand(n, T - L)
+            return (eng(torch.cat([input_ids, pad], 1))[:, :L].clone(),)
         return (eng(input_ids).clone(),)

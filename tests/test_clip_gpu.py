@@ -88,3 +88,22 @@ def test_clip_text_engine_vs_transformers(cuda, layers, with_lora, merged):
     if with_lora and not merged:
         base = CLIPTextEngine(sd, n_seq)(ids)
         assert rel_l2(base, ref) > 2 * e
+
+
+@pytest.mark.gpu
+def test_clip_container_unpadded_ids(cuda):
+    """gradient_fusion.py:190-199 calls the text encoder with UN-padded prompts, one at a time: the container pads to the
+    engine's fixed length (the encoder is causal) and returns the first L positions - equal to transformers on the same
+    ids, and to the prefix of the padded call."""
+    from mixofshow.models.clip_b200 import CLIPTextModel as B200Clip
+    model = _clip(2)
+    enc = B200Clip({k: v.clone() for k, v in model.state_dict().items()})
+    ids = torch.tensor([[49406, 320, 1125, 539, 320, 49408 % 49407, 49407]])      # BOS, 5 words, EOS: L = 7
+    with torch.no_grad():
+        ref = model(ids)[0]
+    out = enc(ids.cuda())[0]
+    assert tuple(out.shape) == (1, 7, 768)
+    assert rel_l2(out, ref) < 2e-2
+    padded = torch.cat([ids, ids[:, -1:].expand(1, 70)], 1)
+    full = enc(padded.cuda())[0]
+    assert torch.equal(full[:, :7], out)
