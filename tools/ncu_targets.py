@@ -135,6 +135,18 @@ Gf = torch.randn(768, 768, device=dev, dtype=torch.float64)
 Yf = torch.empty(320, 768, device=dev, dtype=torch.float64)
 run('dgemm_mixed 320x768x768', lambda: ops.dgemm_mixed(Wf, Gf, Yf))
 
+# ---- L-BFGS direction (25 pairs, n = 320 x 768): 51 launches of lbfgs_step_kernel
+nv = 320 * 768
+Sv = [torch.randn(nv, device=dev) * 0.1 for _ in range(25)]
+Yv = [Sv[i] * 1.1 + 0.01 * torch.randn(nv, device=dev) for i in range(25)]
+gv = torch.randn(nv, device=dev)
+dv = torch.empty_like(gv)
+workv = torch.zeros(64, device=dev, dtype=torch.float64)
+partv = torch.zeros(260, device=dev)
+gtdv = torch.zeros(1, device=dev)
+rhov = [1.0 / float((Yv[i] * Sv[i]).sum()) for i in range(25)]
+run('lbfgs_direction k=25 n=245760', lambda: ops.lbfgs_direction(Sv, Yv, rhov, gv, 0.9, dv, workv, partv, gtdv))
+
 # ---- VAE attention softmax (4096 x 4096 fp32 logits)
 S = torch.randn(4096, 4160, device=dev)
 P = torch.empty(4096, 4096, device=dev, dtype=torch.float16)
