@@ -578,12 +578,17 @@ def gemm_traffic():
         vals = [r['dram_bytes'] for r in rows if r.get('dram_bytes') is not None]
         if not vals:
             return {'traffic': None}
+        # algorithmic operand bytes of the captured launches (tools/ncu_targets.py, in launch order, two launches each): unique
+        # A + W bytes read once; the 16-bit output tile normally stays in the 126 MB L2 within the capture window
+        algo = {'conv3x3 8192x320x2880 (1-CTA)': (8192 * 320 + 320 * 2880) * 2, 'conv3x3 8192x320x2880 (CTA pair)': (8192 * 320 + 320 * 2880) * 2,
+                '8192x320x320 +LoRA +residual': (8192 * 320 * 2 + 320 * 320 + 16 * 320) * 2, 'GEGLU 8192x2560x320': (8192 * 320 + 2560 * 320) * 2,
+                'conv3x3 split-K 512x1280x11520': (512 * 1280 + 1280 * 11520) * 2}
+        names = [n for n in algo for _ in range(2)]
+        per = ', '.join(f"{n}: {r['dram_bytes'] / 1e6:.1f} MB measured / {algo[n] / 1e6:.1f} MB algorithmic"
+                        for n, r in zip(names, rows) if r.get('dram_bytes') is not None) if len(rows) == len(names) else ''
         return {'traffic': sum(vals) / len(vals),
                 'traffic_note': f'mean dram__bytes_read+write over the {len(vals)} gemm_kernel launches of the ncu --set full '
-                                'capture of tools/ncu_targets.py (conv3x3 8192x320x2880, 8192x320x320 +LoRA, GEGLU, split-K '
-                                'conv): profiles/r2_kernels_summary.json; algorithmic operand bytes of those launches: '
-                                + ', '.join(f"{r['dram_bytes'] / 1e6:.1f} MB measured / {r.get('algorithmic_mb', float('nan')):.1f} MB"
-                                            for r in rows if r.get('dram_bytes') is not None)}
+                                'capture of tools/ncu_targets.py: profiles/r2_kernels_summary.json' + ('; ' + per if per else '')}
     except Exception:
         return {'traffic': None}
 
