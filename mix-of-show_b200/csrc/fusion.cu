@@ -106,14 +106,19 @@ sgemm_nn_kernel(const float* __restrict__ A, const float* __restrict__ B, float*
 // in fp64 for the solver to reach the residual the reference reaches with its direct fp32 MSE (measured: 2e-5 vs
 // 6e-7 relative residual on an exactly solvable problem with an fp32 product).  <= 4.2 GFLOP per closure.
 template <int TM>   // rows per CTA tile: 64 (4 x 4 per thread) or 32 (2 x 4 per thread, for grids that would not fill the chip)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 dgemm_mixed_kernel(const float* __restrict__ A, const double* __restrict__ B, double* __restrict__ C, int M, int N,
                    int K) {
-  // every output element accumulates fma(a, b, acc) over k ascending, whatever the tiling: results do not depend on TM.
-  // Global loads of tile t + 1 are issued before the products of tile t (register prefetch, double-buffered smem).
+  // every output element accumulates fma(a, b, acc) over k ascending, whatever the tiling: results do not depend on TM / DK.
+  // Global loads of k-tile t + 1 are issued before the products of tile t (register prefetch, double-buffered smem); 32-deep
+  // k-tiles and two CTAs per SM keep the DFMA pipe fed across the L2 round trip.
+  constexpr int DK = 32;
   constexpr int RI = TM / 16;                 // rows per thread
-  constexpr int AL = TM * 16 / 256;           // A elements per thread and tile (4 or 2)
-  __shared__ double As[2][16][TM + 2], Bs[2][16][64 + 2];
+  constexpr int AL = TM * DK / 256;           // A elements per thread and tile (8 or 4)
+  constexpr int BL = 64 * DK / 256;           // B elements per thread and tile (8)
+  extern __shared__ __align__(16) unsigned char dsm[];
+  double(*As)[DK][TM + 2] = reinterpret_cast<double(*)[DK][TM + 2]>(dsm);
+  double(*Bs)[DK][64 + 2] = reinterpret_cast<double(*)[DK][64 + 2]>(dsm + sizeof(double) * 2 * DK * (TM + 2));
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * 64;
   double acc[RI][4];
@@ -122,16 +127,16 @@ dgemm_mixed_kernel(const float* __restrict__ A, const double* __restrict__ B, do
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
   float ra[AL];
-  double rb[4];
+  double rb[BL];
   auto gload = [&](int k0) {
 #pragma unroll
     for (int u = 0; u < AL; ++u) {
       const int i = threadIdx.x + u * 256;
-      const int m = i >> 4, k = i & 15;
+      const int m = i / DK, k = i % DK;
       ra[u] = (m0 + m < M && k0 + k < K) ? __ldg(A + (long long)(m0 + m) * K + k0 + k) : 0.f;
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < BL; ++u) {
       const int i = threadIdx.x + u * 256;
       const int kk = i >> 6, n = i & 63;
       rb[u] = (k0 + kk < K && n0 + n < N) ? __ldg(B + (long long)(k0 + kk) * N + n0 + n) : 0.0;
@@ -141,10 +146,10 @@ dgemm_mixed_kernel(const float* __restrict__ A, const double* __restrict__ B, do
 #pragma unroll
     for (int u = 0; u < AL; ++u) {
       const int i = threadIdx.x + u * 256;
-      As[buf][i & 15][i >> 4] = (double)ra[u];
+      As[buf][i % DK][i / DK] = (double)ra[u];
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < BL; ++u) {
       const int i = threadIdx.x + u * 256;
       Bs[buf][i >> 6][i & 63] = rb[u];
     }
@@ -153,11 +158,11 @@ dgemm_mixed_kernel(const float* __restrict__ A, const double* __restrict__ B, do
   sstore(0);
   __syncthreads();
   int buf = 0;
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    const bool more = k0 + 16 < K;
-    if (more) gload(k0 + 16);
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
+  for (int k0 = 0; k0 < K; k0 += DK) {
+    const bool more = k0 + DK < K;
+    if (more) gload(k0 + DK);
+#pragma unroll 8
+    for (int k = 0; k < DK; ++k) {
       double a[RI], b[4];
 #pragma unroll
       for (int i = 0; i < RI; ++i) a[i] = As[buf][k][ty * RI + i];
@@ -415,12 +420,20 @@ extern "C" int mos_sgemm_nn(const float* A, const float* B, float* C, int32_t M,
 extern "C" int mos_dgemm_mixed(const float* A, const double* B, double* C, int32_t M, int32_t N, int32_t K,
                                void* stream) {
   MOS_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0, "mos_dgemm_mixed: bad arguments");
-  if (ceil_div(N, 64) * ceil_div(M, 64) < 148) {     // too few 64-row tiles for the chip: 32-row tiles
+  constexpr int DK = 32;
+  static bool configured = false;
+  const size_t sm32 = sizeof(double) * 2 * DK * ((32 + 2) + (64 + 2)), sm64 = sizeof(double) * 2 * DK * ((64 + 2) + (64 + 2));
+  if (!configured) {
+    MOS_CHECK_CUDA(cudaFuncSetAttribute(dgemm_mixed_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm32));
+    MOS_CHECK_CUDA(cudaFuncSetAttribute(dgemm_mixed_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm64));
+    configured = true;
+  }
+  if (ceil_div(N, 64) * ceil_div(M, 64) < 2 * 148) {     // too few 64-row tiles for two CTAs per SM: 32-row tiles
     dim3 grid((unsigned)ceil_div(N, 64), (unsigned)ceil_div(M, 32));
-    dgemm_mixed_kernel<32><<<grid, 256, 0, STREAM(stream)>>>(A, B, C, M, N, K);
+    dgemm_mixed_kernel<32><<<grid, 256, sm32, STREAM(stream)>>>(A, B, C, M, N, K);
   } else {
     dim3 grid((unsigned)ceil_div(N, 64), (unsigned)ceil_div(M, 64));
-    dgemm_mixed_kernel<64><<<grid, 256, 0, STREAM(stream)>>>(A, B, C, M, N, K);
+    dgemm_mixed_kernel<64><<<grid, 256, sm64, STREAM(stream)>>>(A, B, C, M, N, K);
   }
   MOS_CHECK_LAUNCH();
   return MOS_OK;

@@ -17,6 +17,7 @@ without the cancellation of the raw Gram form.  The text-encoder half (merge_tex
 compose_concepts and the CLI) is restated at the bottom of this file over those stages.
 """
 import math
+import os
 
 import torch
 
@@ -240,6 +241,60 @@ def solve_from_gram(G, Cm, vv, n_rows, W0, iters):
     return Wn
 
 
+FUSION_WORKERS = int(os.environ.get('MOS_FUSION_WORKERS', '4'))
+
+
+def solve_all(jobs, iters, workers=None):
+    """jobs: list of (name, G, Cm, vv, n_rows, W0, out_shape) - the independent per-layer problems of one fusion stage
+    (gradient_fusion.py solves them one after the other, :394-455 / :518-563 / :690-745).  One L-BFGS solve is a chain of
+    small kernels with a handful of host decisions per iteration and leaves the GPU mostly idle, so `workers` host threads
+    drive `workers` solves at a time, each on its own CUDA stream.  Every solve runs exactly the arithmetic of the
+    sequential code (results are bit-identical whatever the concurrency).  -> {name: fused weight (fp32, CPU)}."""
+    workers = FUSION_WORKERS if workers is None else workers
+    if not jobs:
+        return {}
+    dev = jobs[0][1].device
+    out = {}
+    if workers <= 1 or len(jobs) == 1 or dev.type != 'cuda':
+        for name, G, Cm, vv, n, W0, shape in jobs:
+            out[name] = solve_from_gram(G, Cm, vv, n, W0, iters).reshape(shape).cpu()
+        return out
+    import queue
+    import threading
+    torch.cuda.synchronize(dev)                 # the Gram matrices / right-hand sides were built on the caller's stream
+    # largest problems first: the tail of the schedule is then filled with short solves
+    order = sorted(range(len(jobs)), key=lambda i: -jobs[i][2].numel())
+    todo = queue.SimpleQueue()
+    for i in order:
+        todo.put(i)
+    errors, results = [], {}
+
+    def run():
+        stream = torch.cuda.Stream(device=dev)
+        try:
+            with torch.cuda.device(dev), torch.cuda.stream(stream):
+                while True:
+                    try:
+                        i = todo.get_nowait()
+                    except queue.Empty:
+                        break
+                    name, G, Cm, vv, n, W0, shape = jobs[i]
+                    results[name] = solve_from_gram(G, Cm, vv, n, W0, iters).reshape(shape)
+                stream.synchronize()
+        except BaseException as exc:            # re-raised in the caller's thread
+            errors.append(exc)
+
+    threads = [threading.Thread(target=run, daemon=True) for _ in range(min(workers, len(jobs)))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    torch.cuda.synchronize(dev)
+    return {job[0]: results[job[0]].cpu() for job in jobs}
+
+
 def update_quasi_newton(K_target, V_target, W, iters, device='cuda'):
     """Reference signature (gradient_fusion.py:38): K [n,in], V [n,out], W [out,in] (or 1x1-conv 4-D) -> Wnew."""
     shape = W.shape
@@ -306,7 +361,7 @@ def merge_kv_in_cross_attention(unet_state_dict, cross_kv_layer_names, text_feat
     """Cross-attention K/V fusion (gradient_fusion.py:325-457).  text_features[c][layer_idx] = CLIP features of
     concept c at its concept-token (+EOS) positions [n_pos, 768] (gradient_fusion.py:182-199; CLIP runs upstream).
     cross_kv_layer_names: [(layer_idx, 'down_blocks....attn2.to_k.weight'), ...] in the reference's order."""
-    new_w = {}
+    jobs = []
     for layer_idx, name in cross_kv_layer_names:
         W0 = unet_state_dict[name].to(device, F32)
         d_in = W0.shape[1]
@@ -325,8 +380,8 @@ def merge_kv_in_cross_attention(unet_state_dict, cross_kv_layer_names, text_feat
             ops.vec_axpby(Cm.view(-1), WG.view(-1), 1.0, 1.0)
             vv += float((Wc.double() * WG.double()).sum())
             n += X.shape[0]
-        new_w[name] = solve_from_gram(G, Cm, vv, n, W0, optimize_iters).cpu()
-    return new_w
+        jobs.append((name, G, Cm, vv, n, W0, tuple(W0.shape)))
+    return solve_all(jobs, optimize_iters)
 
 
 class _RowRecorder:
@@ -374,7 +429,7 @@ def merge_text_encoder(text_state_dict, text_encoder_list, alphas, prompt_ids, o
         eng.gram_rec = rec
         eng(ids)
         feats.append(rec.X)
-    new_w = {}
+    jobs = []
     for name in names:                                       # e.g. 'text_model.encoder.layers.0.self_attn.q_proj.weight'
         mod = name[:-len('.weight')]
         layer, leaf = mod.rsplit('.self_attn.', 1)
@@ -396,8 +451,8 @@ def merge_text_encoder(text_state_dict, text_encoder_list, alphas, prompt_ids, o
             ops.vec_axpby(Cm.view(-1), WG.view(-1), 1.0, 1.0)
             vv += float((Wc.double() * WG.double()).sum())
             n += X.shape[0]
-        new_w[name] = solve_from_gram(G, Cm, vv, n, W0, optimize_iters).cpu()
-    return new_w
+        jobs.append((name, G, Cm, vv, n, W0, tuple(W0.shape)))
+    return solve_all(jobs, optimize_iters)
 
 
 class GramRecorder:
@@ -462,7 +517,7 @@ def merge_spatial_attention(unet_state_dict, unet_spatial_attn_list, alphas, con
         merged_w.append(tuned)
         eng.gram_rec = None
     names = sorted({k.replace('.lora_down', '').replace('.lora_up', '') for t in unet_spatial_attn_list for k in t})
-    new_w = {}
+    jobs = []
     for name in names:                                          # e.g. '...attn1.to_q.weight'
         mod = name[:-len('.weight')]
         tb, leaf = mod.rsplit('.attn', 1)
@@ -483,8 +538,8 @@ def merge_spatial_attention(unet_state_dict, unet_spatial_attn_list, alphas, con
             ops.vec_axpby(Cm.view(-1), WG.view(-1), 1.0, 1.0)
             vv += float((Wc.double() * WG.double()).sum())
             n += grams[c].rows[rec_key]
-        new_w[name] = solve_from_gram(G, Cm, vv, n, W0, optimize_iters).reshape(unet_state_dict[name].shape).cpu()
-    return new_w
+        jobs.append((name, G, Cm, vv, n, W0, tuple(unet_state_dict[name].shape)))
+    return solve_all(jobs, optimize_iters)
 
 
 # ------------------------------------------------------------------------------------------------ orchestration (host)
