@@ -736,9 +736,12 @@ def parse_args(argv=None):
     return parser.parse_args(argv)
 
 
-if __name__ == '__main__':
-    import os
-    args = parse_args()
+def main(argv=None):
+    args = parse_args(argv)
     os.makedirs(args.save_path, exist_ok=True)
-    compose_concepts(args.concept_cfg, args.optimize_textenc_iters, args.optimize_unet_iters, args.pretrained_models,
-                     args.save_path, args.suffix, device='cuda')
+    return compose_concepts(args.concept_cfg, args.optimize_textenc_iters, args.optimize_unet_iters, args.pretrained_models,
+                            args.save_path, args.suffix, device='cuda')
+
+
+if __name__ == '__main__':
+    main()

@@ -49,7 +49,8 @@ class EDLoRAPipeline:
         revise_edlora_unet_attention_forward(unet)          # reference :93
         self.vae, self.text_encoder, self.tokenizer, self.unet = vae, text_encoder, tokenizer, unet
         self.scheduler = scheduler if scheduler is not None else DPMSolverPP2M()
-        self.vae_scale_factor = 8
+        # diffusers: 2 ** (len(vae.config.block_out_channels) - 1); 8 for SD1.5 (and when no VAE is attached)
+        self.vae_scale_factor = 2 ** (len(vae.config.block_out_channels) - 1) if vae is not None else 8
         self.new_concept_cfg = None
         self.device = torch.device('cuda')
 

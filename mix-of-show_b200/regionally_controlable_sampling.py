@@ -77,11 +77,12 @@ def parse_args(argv=None):
     parser.add_argument('--prompt_rewrite', default='', type=str)
     parser.add_argument('--seed', default=16141, type=int)
     parser.add_argument('--suffix', default='', type=str)
+    parser.add_argument('--num_inference_steps', default=50, type=int)       # the reference samples with 50 steps (:38)
     return parser.parse_args(argv)
 
 
-if __name__ == '__main__':
-    args = parse_args()
+def main(argv=None):
+    args = parse_args(argv)
     device = torch.device('cuda')
     pipe = build_model(args.pretrained_model, device)
     kwargs = {'height': args.height, 'width': args.width, 'output_type': 'latent'}
@@ -93,7 +94,8 @@ if __name__ == '__main__':
         kwargs[f'region_{kind}_adaptor_weight'] = getattr(args, f'region_{kind}_adaptor_weight')
     input_prompt = [prepare_text(args.prompt, args.prompt_rewrite, args.height, args.width)]
     latents = sample_image(pipe, input_prompt=input_prompt, input_neg_prompt=[args.negative_prompt],
-                           generator=torch.Generator('cpu').manual_seed(args.seed), **kwargs)
+                           generator=torch.Generator('cpu').manual_seed(args.seed),
+                           num_inference_steps=args.num_inference_steps, **kwargs)
     if args.save_dir is not None:
         os.makedirs(args.save_dir, exist_ok=True)
         out = os.path.join(args.save_dir, f'latents---{args.seed}{"---" + args.suffix if args.suffix else ""}.pt')
@@ -101,3 +103,8 @@ if __name__ == '__main__':
         with open(os.path.join(args.save_dir, 'config.json'), 'w') as f:
             json.dump(vars(args), f)
         print(f'save to: {out}')
+    return latents
+
+
+if __name__ == '__main__':
+    main()
