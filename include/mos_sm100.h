@@ -242,6 +242,29 @@ int mos_vec_axpby(float* y, const float* x, float alpha, float beta, int64_t n, 
  * mos_vec_axpby.  work: >= k + 1 doubles; partial: >= 257 floats with partial[256] == 0 on entry (left zero). */
 int mos_lbfgs_direction(const void* const* S, const void* const* Y, const double* rho, int32_t k, const float* g,
                         float h_diag, int64_t n, float* d, double* work, float* partial, float* gtd, void* stream);
+
+/* Native driver of one per-layer fusion solve: ONE torch.optim.LBFGS.step(closure) (strong-Wolfe line search, `history` pairs,
+ * at most `max_iter` iterations and max_iter * 5 / 4 closure evaluations, tolerances 1e-16 / 1e-16, lr 1: gradient_fusion.py:76-85)
+ * on f(D) = s <D, D G - 2 R> + f0 from D = 0; best_D receives the iterate with the lowest loss over all evaluations
+ * (gradient_fusion.py:72-74).  The loop runs on the host inside the library and issues the mos_vec_* / mos_lbfgs_direction /
+ * mos_dgemm_mixed / mos_ls_grad_loss launches on `stream` (results identical to driving the same launches from the caller).
+ * workspace: device memory of mos_lbfgs_workspace_bytes(out_f, in_f, history) bytes.  Blocking. */
+typedef struct mos_lbfgs_problem {
+  const double* G;      /* [in_f, in_f]  fp64, device */
+  const double* R;      /* [out_f, in_f] fp64, device: C - W0 G */
+  int32_t out_f, in_f;
+  double s, f0;
+  int32_t max_iter;
+  int32_t history;      /* 0 = 25 */
+  float* best_D;        /* out, device fp32 [out_f * in_f] */
+  double* best_loss;    /* out, host (may be NULL) */
+  int32_t* n_evals;     /* out, host (may be NULL) */
+} mos_lbfgs_problem;
+int64_t mos_lbfgs_workspace_bytes(int32_t out_f, int32_t in_f, int32_t history);
+int mos_lbfgs_solve(const mos_lbfgs_problem* problem, void* workspace, void* stream);
+/* The independent layers of a fusion stage: `workers` host threads, each with its own CUDA stream and workspace, take the
+ * problems largest first.  Synchronises the device on entry and exit. */
+int mos_lbfgs_solve_batch(const mos_lbfgs_problem* problems, int32_t n_problems, int32_t workers);
 /* Batched W_l += alpha * up_l @ down_l (convert_edlora_to_diffusers.py:33-76, gradient_fusion.py:99-143).
  * table_dev: int64 [n_layers, 6] = {W fp32 ptr, down fp32 ptr, up fp32 ptr, out, in, rank}. */
 int mos_lora_merge(const int64_t* table_dev, int32_t n_layers, float alpha, void* stream);

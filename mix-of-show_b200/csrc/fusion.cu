@@ -167,7 +167,7 @@ dgemm_mixed_kernel(const float* __restrict__ A, const double* __restrict__ B, do
 #pragma unroll
       for (int i = 0; i < RI; ++i) a[i] = As[buf][k][ty * RI + i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[buf][k][tx * 4 + j];
+      for (int j = 0; j < 4; ++j) b[j] = Bs[buf][k][tx + 16 * j];   // consecutive lanes -> consecutive doubles: no bank conflicts
 #pragma unroll
       for (int i = 0; i < RI; ++i)
 #pragma unroll
@@ -183,7 +183,7 @@ dgemm_mixed_kernel(const float* __restrict__ A, const double* __restrict__ B, do
     if (m >= M) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
+      const int n = n0 + tx + 16 * j;
       if (n < N) C[(long long)m * N + n] = acc[i][j];
     }
   }

@@ -220,24 +220,41 @@ def lbfgs_minimize(P, x0, max_iter, history=25, lr=1.0, tol_grad=1e-16, tol_chan
 
 
 # ------------------------------------------------------------------------------------------------ solver front ends
-def solve_from_gram(G, Cm, vv, n_rows, W0, iters):
-    """min_W (1/(n out)) (tr(W G W^T) - 2 tr(W C^T) + vv) by the reference's L-BFGS recipe, starting at W0.
-    G [in,in], Cm [out,in] fp32 on the device; returns the best W over all closure evaluations (fp32, device)."""
-    out_f, in_f = Cm.shape
+def _gram_setup(G, Cm, vv, n_rows, W0):
+    """one-time fp64 setup of a solve (like weight packing): residual right-hand side R = C - W0 G and f(W0); the Gram form
+    squares the condition number, so the closure product D G is carried in fp64 on the device (mos_dgemm_mixed)"""
+    out_f = Cm.shape[0]
     dev = Cm.device
     W0 = W0.to(dev, F32).contiguous()
     G = G.to(dev, F32).contiguous()
     s = 1.0 / (float(n_rows) * out_f)
-    # one-time fp64 setup (like weight packing): residual right-hand side R = C - W0 G and f(W0); the Gram form squares
-    # the condition number, so the closure product D G is carried in fp64 on the device (mos_dgemm_mixed)
     W0d, Gd, Cd = W0.double(), G.double().contiguous(), Cm.to(dev).double()
     Rd = (Cd - W0d @ Gd).contiguous()
     f0 = s * (float((W0d * (W0d @ Gd - 2.0 * Cd)).sum()) + float(vv))
-    P = _GramProblem(Gd, Rd, s, f0, W0)
-    D0 = torch.zeros(out_f * in_f, device=dev, dtype=F32)
-    lbfgs_minimize(P, D0, iters)
+    return W0, Gd, Rd, s, f0
+
+
+# the L-BFGS loop runs in the library (csrc/lbfgs.cu); MOS_FUSION_NATIVE=0 selects the Python driver below, which issues the
+# same launches in the same order (kept as the readable statement of the algorithm and as the yardstick of the tests)
+FUSION_NATIVE = os.environ.get('MOS_FUSION_NATIVE', '1') != '0'
+
+
+def solve_from_gram(G, Cm, vv, n_rows, W0, iters, native=None):
+    """min_W (1/(n out)) (tr(W G W^T) - 2 tr(W C^T) + vv) by the reference's L-BFGS recipe, starting at W0.
+    G [in,in], Cm [out,in] fp32 on the device; returns the best W over all closure evaluations (fp32, device)."""
+    out_f, in_f = Cm.shape
+    dev = Cm.device
+    W0, Gd, Rd, s, f0 = _gram_setup(G, Cm, vv, n_rows, W0)
+    if FUSION_NATIVE if native is None else native:
+        best_D = torch.empty(out_f * in_f, device=dev, dtype=F32)
+        ops.lbfgs_solve_batch([(Gd, Rd, s, f0, best_D)], iters, workers=1)
+    else:
+        P = _GramProblem(Gd, Rd, s, f0, W0)
+        D0 = torch.zeros(out_f * in_f, device=dev, dtype=F32)
+        lbfgs_minimize(P, D0, iters)
+        best_D = P.best_D
     Wn = W0.clone()
-    ops.vec_axpby(Wn.view(-1), P.best_D, 1.0, 1.0)
+    ops.vec_axpby(Wn.view(-1), best_D, 1.0, 1.0)
     return Wn
 
 
@@ -255,6 +272,16 @@ def solve_all(jobs, iters, workers=None):
         return {}
     dev = jobs[0][1].device
     out = {}
+    if FUSION_NATIVE and dev.type == 'cuda':
+        # host threads x CUDA streams inside the library (mos_lbfgs_solve_batch): no interpreter lock between the solves
+        setups = [_gram_setup(G, Cm, vv, n, W0) for _, G, Cm, vv, n, W0, _ in jobs]
+        bests = [torch.empty(W0.numel(), device=dev, dtype=F32) for W0, *_ in setups]
+        ops.lbfgs_solve_batch([(Gd, Rd, s, f0, b) for (W0, Gd, Rd, s, f0), b in zip(setups, bests)], iters, workers=workers)
+        for (name, *_, shape), (W0, *_), b in zip(jobs, setups, bests):
+            Wn = W0.clone()
+            ops.vec_axpby(Wn.view(-1), b, 1.0, 1.0)
+            out[name] = Wn.reshape(shape).cpu()
+        return out
     if workers <= 1 or len(jobs) == 1 or dev.type != 'cuda':
         for name, G, Cm, vv, n, W0, shape in jobs:
             out[name] = solve_from_gram(G, Cm, vv, n, W0, iters).reshape(shape).cpu()

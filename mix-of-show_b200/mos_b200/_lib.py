@@ -35,6 +35,13 @@ class GemmArgs(ctypes.Structure):
     ]
 
 
+class LbfgsProblem(ctypes.Structure):
+    """mos_lbfgs_problem (include/mos_sm100.h)"""
+    _fields_ = [('G', c_vp), ('R', c_vp), ('out_f', c_i32), ('in_f', c_i32), ('s', ctypes.c_double), ('f0', ctypes.c_double),
+                ('max_iter', c_i32), ('history', c_i32), ('best_D', c_vp), ('best_loss', ctypes.POINTER(ctypes.c_double)),
+                ('n_evals', ctypes.POINTER(c_i32))]
+
+
 class MosError(RuntimeError):
     pass
 

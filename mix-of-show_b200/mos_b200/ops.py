@@ -299,6 +299,27 @@ def lbfgs_direction(S, Y, rho, g, h_diag, d, work, partial, gtd):
     return d
 
 
+def lbfgs_solve_batch(problems, iters, workers=4, history=25):
+    """problems: list of (G fp64 [in,in], R fp64 [out,in], s, f0, best_D fp32 [out*in] (written)); runs the native L-BFGS
+    driver (mos_lbfgs_solve_batch: `workers` host threads x CUDA streams inside the library).  -> [(best_loss, n_evals)]."""
+    from ._lib import LbfgsProblem
+    n = len(problems)
+    arr = (LbfgsProblem * n)()
+    losses = (ctypes.c_double * n)()
+    evals = (ctypes.c_int32 * n)()
+    for i, (G, R, s, f0, best_D) in enumerate(problems):
+        assert G.dtype == torch.float64 and R.dtype == torch.float64 and best_D.dtype == torch.float32
+        assert G.is_contiguous() and R.is_contiguous() and best_D.is_contiguous() and best_D.numel() == R.numel()
+        p = arr[i]
+        p.G, p.R, p.best_D = ptr(G), ptr(R), ptr(best_D)
+        p.out_f, p.in_f = R.shape[0], R.shape[1]
+        p.s, p.f0, p.max_iter, p.history = float(s), float(f0), int(iters), int(history)
+        p.best_loss = ctypes.cast(ctypes.byref(losses, i * 8), ctypes.POINTER(ctypes.c_double))
+        p.n_evals = ctypes.cast(ctypes.byref(evals, i * 4), ctypes.POINTER(ctypes.c_int32))
+    check(_lib.lib().mos_lbfgs_solve_batch(arr, ctypes.c_int32(n), ctypes.c_int32(workers)), 'mos_lbfgs_solve_batch')
+    return [(losses[i], evals[i]) for i in range(n)]
+
+
 def vec_axpby(y, x, alpha, beta=1.0):
     check(_lib.lib().mos_vec_axpby(ptr(y), ptr(x), ctypes.c_float(alpha), ctypes.c_float(beta),
                                    ctypes.c_int64(y.numel()), _s()), 'mos_vec_axpby')

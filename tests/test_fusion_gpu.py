@@ -92,6 +92,32 @@ def test_lbfgs_direction_bit_identical_to_host_recursion(cuda, k, n):
         assert partial[256].item() == 0
 
 
+@pytest.mark.parametrize('out_f,in_f,n_rows,iters', [(64, 96, 40, 30), (320, 768, 30, 60), (200, 130, 500, 25)])
+def test_native_lbfgs_driver_bit_identical_to_python_driver(cuda, out_f, in_f, n_rows, iters):
+    """csrc/lbfgs.cu (mos_lbfgs_solve_batch) issues the launches of gradient_fusion.lbfgs_minimize in the same order: the
+    fused weight must be the same bits, for an under-determined (n < in) and an over-determined problem."""
+    import gradient_fusion as gf
+    g = torch.Generator().manual_seed(out_f + in_f)
+    K = torch.randn(n_rows, in_f, generator=g).to(cuda)
+    W0 = (torch.randn(out_f, in_f, generator=g) * in_f ** -0.5).to(cuda)
+    Wt = W0 + 0.05 * torch.randn(out_f, in_f, generator=g).to(cuda)
+    V = K @ Wt.t()
+    G = (K.t() @ K).contiguous()
+    Cm = (V.t() @ K).contiguous()
+    vv = float((V.double() ** 2).sum())
+    a = gf.solve_from_gram(G, Cm, vv, n_rows, W0, iters, native=False)
+    b = gf.solve_from_gram(G, Cm, vv, n_rows, W0, iters, native=True)
+    assert torch.equal(a.view(torch.int32), b.view(torch.int32))
+    r0 = ((K @ W0.t() - V) ** 2).mean().item()
+    r1 = ((K @ b.t() - V) ** 2).mean().item()
+    assert r1 < 0.2 * r0
+    # the batch entry with several workers: same bits again
+    jobs = [(f'l{i}', G, Cm, vv, n_rows, W0, (out_f, in_f)) for i in range(5)]
+    outs = gf.solve_all(jobs, iters, workers=3)
+    for v in outs.values():
+        assert torch.equal(v.view(torch.int32), a.cpu().view(torch.int32))
+
+
 def test_dgemm_mixed_tilings(cuda):
     """the fp64 closure product in both tilings (32- and 64-row CTA tiles) vs torch fp64"""
     from mos_b200 import ops
