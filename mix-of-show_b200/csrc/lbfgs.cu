@@ -80,7 +80,7 @@ struct Solver {
   static size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
   static size_t workspace_bytes(long long n, int H) {
     size_t b = 0;
-    b += align_up(sizeof(float) * n) * (5 + RING + 2 * (size_t)H);
+    b += align_up(sizeof(float) * n) * (5 + RING + 2 * (size_t)H + 2);     // + 2: the candidate pair of the current iteration
     b += align_up(sizeof(double) * n);                       // Y64
     b += align_up(sizeof(double) * (1 + 256 + 64));          // loss64, scratch64, work
     b += align_up(sizeof(float) * (8 + 256 + 260 + 4));      // scal, scratch, partial, gtd
@@ -95,7 +95,7 @@ struct Solver {
     };
     x = takef(n), g = takef(n), prev_g = takef(n), d = takef(n), xt = takef(n);
     for (int i = 0; i < RING; ++i) ring[i] = takef(n);
-    for (int i = 0; i < 2 * H; ++i) free_hist.push_back(takef(n));
+    for (int i = 0; i < 2 * H + 2; ++i) free_hist.push_back(takef(n));
     Y64 = reinterpret_cast<double*>(p);
     p += align_up(sizeof(double) * n);
     loss64 = reinterpret_cast<double*>(p);
