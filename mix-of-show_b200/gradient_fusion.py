@@ -258,7 +258,7 @@ def solve_from_gram(G, Cm, vv, n_rows, W0, iters, native=None):
     return Wn
 
 
-FUSION_WORKERS = int(os.environ.get('MOS_FUSION_WORKERS', '4'))
+FUSION_WORKERS = int(os.environ.get('MOS_FUSION_WORKERS', '8'))
 
 
 def solve_all(jobs, iters, workers=None):
