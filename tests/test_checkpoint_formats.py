@@ -96,7 +96,7 @@ def test_clip_container_embedding_surface(monkeypatch):
 
     class FakeEngine:
         def __init__(self, sd, n, **kw):
-            self.n = n
+            self.n, self.T = n, 77
             calls.append(('build', n, sd['text_model.embeddings.token_embedding.weight'].shape[0]))
 
         def set_token_embedding(self, table):
