@@ -9,6 +9,8 @@
 // so features are reduced to [in, in] fp32 on the fly (tcgen05 GEMM with fp32 accumulate output, see gemm.cu) and a
 // closure is one [out, in] x [in, in] fp32 GEMM.  Kernels here: bf16 transpose (Gram operand), small-n Gram, fp32
 // SGEMM, closure epilogue (grad + loss), deterministic vector primitives for the L-BFGS driver, batched LoRA merge.
+#include <stdlib.h>
+
 #include "common.h"
 #include "tc.cuh"
 
@@ -105,27 +107,27 @@ sgemm_nn_kernel(const float* __restrict__ A, const float* __restrict__ B, float*
 // The Gram form squares the condition number of the least-squares problem; the product D G must therefore be carried
 // in fp64 for the solver to reach the residual the reference reaches with its direct fp32 MSE (measured: 2e-5 vs
 // 6e-7 relative residual on an exactly solvable problem with an fp32 product).  <= 4.2 GFLOP per closure.
-template <int TM>   // rows per CTA tile: 64 (4 x 4 per thread) or 32 (2 x 4 per thread, for grids that would not fill the chip)
-__global__ void __launch_bounds__(256, 2)
+template <int TM, int TN>   // CTA tile TM x TN (TM / 16 x TN / 16 outputs per thread): 32 x 64, 64 x 64 or 64 x 128
+__global__ void __launch_bounds__(256, (TN > 64 ? 1 : 2))
 dgemm_mixed_kernel(const float* __restrict__ A, const double* __restrict__ B, double* __restrict__ C, int M, int N,
                    int K) {
-  // every output element accumulates fma(a, b, acc) over k ascending, whatever the tiling: results do not depend on TM / DK.
+  // every output element accumulates fma(a, b, acc) over k ascending, whatever the tiling: results do not depend on the tile.
   // Global loads of k-tile t + 1 are issued before the products of tile t (register prefetch, double-buffered smem); 32-deep
-  // k-tiles and two CTAs per SM keep the DFMA pipe fed across the L2 round trip.
+  // k-tiles keep the DFMA pipe fed across the L2 round trip; thread tx owns columns tx, tx + 16, ... (bank-conflict free).
   constexpr int DK = 32;
-  constexpr int RI = TM / 16;                 // rows per thread
-  constexpr int AL = TM * DK / 256;           // A elements per thread and tile (8 or 4)
-  constexpr int BL = 64 * DK / 256;           // B elements per thread and tile (8)
+  constexpr int RI = TM / 16, RJ = TN / 16;
+  constexpr int AL = TM * DK / 256;           // A elements per thread and k-tile
+  constexpr int BL = TN * DK / 256;           // B elements per thread and k-tile
   extern __shared__ __align__(16) unsigned char dsm[];
   double(*As)[DK][TM + 2] = reinterpret_cast<double(*)[DK][TM + 2]>(dsm);
-  double(*Bs)[DK][64 + 2] = reinterpret_cast<double(*)[DK][64 + 2]>(dsm + sizeof(double) * 2 * DK * (TM + 2));
+  double(*Bs)[DK][TN + 2] = reinterpret_cast<double(*)[DK][TN + 2]>(dsm + sizeof(double) * 2 * DK * (TM + 2));
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * 64;
-  double acc[RI][4];
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  double acc[RI][RJ];
 #pragma unroll
   for (int i = 0; i < RI; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    for (int j = 0; j < RJ; ++j) acc[i][j] = 0.0;
   float ra[AL];
   double rb[BL];
   auto gload = [&](int k0) {
@@ -138,7 +140,7 @@ dgemm_mixed_kernel(const float* __restrict__ A, const double* __restrict__ B, do
 #pragma unroll
     for (int u = 0; u < BL; ++u) {
       const int i = threadIdx.x + u * 256;
-      const int kk = i >> 6, n = i & 63;
+      const int kk = i / TN, n = i % TN;
       rb[u] = (k0 + kk < K && n0 + n < N) ? __ldg(B + (long long)(k0 + kk) * N + n0 + n) : 0.0;
     }
   };
@@ -151,7 +153,7 @@ dgemm_mixed_kernel(const float* __restrict__ A, const double* __restrict__ B, do
 #pragma unroll
     for (int u = 0; u < BL; ++u) {
       const int i = threadIdx.x + u * 256;
-      Bs[buf][i >> 6][i & 63] = rb[u];
+      Bs[buf][i / TN][i % TN] = rb[u];
     }
   };
   gload(0);
@@ -163,15 +165,15 @@ dgemm_mixed_kernel(const float* __restrict__ A, const double* __restrict__ B, do
     if (more) gload(k0 + DK);
 #pragma unroll 8
     for (int k = 0; k < DK; ++k) {
-      double a[RI], b[4];
+      double a[RI], b[RJ];
 #pragma unroll
       for (int i = 0; i < RI; ++i) a[i] = As[buf][k][ty * RI + i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[buf][k][tx + 16 * j];   // consecutive lanes -> consecutive doubles: no bank conflicts
+      for (int j = 0; j < RJ; ++j) b[j] = Bs[buf][k][tx + 16 * j];
 #pragma unroll
       for (int i = 0; i < RI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < RJ; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
     }
     if (more) sstore(buf ^ 1);
     __syncthreads();
@@ -182,7 +184,7 @@ dgemm_mixed_kernel(const float* __restrict__ A, const double* __restrict__ B, do
     const int m = m0 + ty * RI + i;
     if (m >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < RJ; ++j) {
       const int n = n0 + tx + 16 * j;
       if (n < N) C[(long long)m * N + n] = acc[i][j];
     }
@@ -421,19 +423,27 @@ extern "C" int mos_dgemm_mixed(const float* A, const double* B, double* C, int32
                                void* stream) {
   MOS_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0, "mos_dgemm_mixed: bad arguments");
   constexpr int DK = 32;
-  static bool configured = false;
-  const size_t sm32 = sizeof(double) * 2 * DK * ((32 + 2) + (64 + 2)), sm64 = sizeof(double) * 2 * DK * ((64 + 2) + (64 + 2));
-  if (!configured) {
-    MOS_CHECK_CUDA(cudaFuncSetAttribute(dgemm_mixed_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm32));
-    MOS_CHECK_CUDA(cudaFuncSetAttribute(dgemm_mixed_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm64));
-    configured = true;
+  static int tile_env = -1;
+  auto smem = [](int tm, int tn) { return sizeof(double) * 2 * DK * ((tm + 2) + (tn + 2)); };
+  if (tile_env < 0) {
+    const char* e = getenv("MOS_DGEMM_TILE");     // 0 = heuristic, 1 = 32 x 64, 2 = 64 x 64, 3 = 64 x 128 (benchmarking)
+    const int v = e ? atoi(e) : 0;
+    MOS_CHECK_CUDA(cudaFuncSetAttribute(dgemm_mixed_kernel<32, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem(32, 64)));
+    MOS_CHECK_CUDA(cudaFuncSetAttribute(dgemm_mixed_kernel<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem(64, 64)));
+    MOS_CHECK_CUDA(cudaFuncSetAttribute(dgemm_mixed_kernel<64, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem(64, 128)));
+    tile_env = v;
   }
-  if (ceil_div(N, 64) * ceil_div(M, 64) < 2 * 148) {     // too few 64-row tiles for two CTAs per SM: 32-row tiles
+  int tile = tile_env;
+  if (tile == 0) tile = (ceil_div(N, 64) * ceil_div(M, 64) < 2 * 148) ? 1 : 2;   // too few 64-row tiles for two CTAs per SM
+  if (tile == 1) {
     dim3 grid((unsigned)ceil_div(N, 64), (unsigned)ceil_div(M, 32));
-    dgemm_mixed_kernel<32><<<grid, 256, sm32, STREAM(stream)>>>(A, B, C, M, N, K);
-  } else {
+    dgemm_mixed_kernel<32, 64><<<grid, 256, smem(32, 64), STREAM(stream)>>>(A, B, C, M, N, K);
+  } else if (tile == 2) {
     dim3 grid((unsigned)ceil_div(N, 64), (unsigned)ceil_div(M, 64));
-    dgemm_mixed_kernel<64><<<grid, 256, sm64, STREAM(stream)>>>(A, B, C, M, N, K);
+    dgemm_mixed_kernel<64, 64><<<grid, 256, smem(64, 64), STREAM(stream)>>>(A, B, C, M, N, K);
+  } else {
+    dim3 grid((unsigned)ceil_div(N, 128), (unsigned)ceil_div(M, 64));
+    dgemm_mixed_kernel<64, 128><<<grid, 256, smem(64, 128), STREAM(stream)>>>(A, B, C, M, N, K);
   }
   MOS_CHECK_LAUNCH();
   return MOS_OK;

@@ -74,7 +74,20 @@ def fusion():
     spatial = [{k: v for k, v in l.items() if 'attn2.to_k' not in k and 'attn2.to_v' not in k} for l in loras]
     crosskv = [{k: v for k, v in l.items() if 'attn2.to_k' in k or 'attn2.to_v' in k} for l in loras]
     alphas = [1.0] * 5
-    out = {'config': 'gradient_fusion merge of 5 ED-LoRAs into SD1.5-topology UNet weights on 1xB200 (UNet half)'}
+    out = {'config': 'gradient_fusion merge of 5 ED-LoRAs into SD1.5-topology UNet weights on 1xB200 (UNet half)',
+           'workers': gf.FUSION_WORKERS, 'native_driver': gf.FUSION_NATIVE}
+    solve_s = []
+    _solve_all = gf.solve_all
+
+    def timed_solve_all(jobs, iters, workers=None):      # how much of a stage is the L-BFGS solves themselves
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        r = _solve_all(jobs, iters, workers)
+        torch.cuda.synchronize()
+        solve_s.append(round(time.perf_counter() - t, 2))
+        return r
+
+    gf.solve_all = timed_solve_all
     # ---- cross-attention K/V: 32 layers, X = 6 text-feature rows per concept (3 positions x 2 prompts), 500 iterations
     kv_names = sorted({k.replace('.lora_down', '').replace('.lora_up', '') for k in crosskv[0]})
     from mos_b200.engine import cross_attention_names
@@ -88,6 +101,7 @@ def fusion():
     torch.cuda.synchronize()
     out['cross_kv_seconds'] = round(time.perf_counter() - t0, 2)
     out['cross_kv_layers'] = len(w_kv)
+    out['cross_kv_solve_seconds'] = solve_s[-1]
     # ---- spatial attention: 96 layers, 5 x 20 recorded UNet forwards (Gram accumulation on the GPU), 50 iterations
     embeds = [torch.randn(1, 16, 77, 768, generator=torch.Generator().manual_seed(30 + c)) for c in range(5)]
     t0 = time.perf_counter()
@@ -95,6 +109,7 @@ def fusion():
     torch.cuda.synchronize()
     out['spatial_seconds'] = round(time.perf_counter() - t0, 2)
     out['spatial_layers'] = len(w_sp)
+    out['spatial_solve_seconds'] = solve_s[-1]
     name = 'down_blocks.0.attentions.0.transformer_blocks.0.attn1.to_q.weight'
     out['example_delta_rel'] = round(((w_sp[name] - sd[name]).norm() / sd[name].norm()).item(), 5)
     out['data'] = 'synthetic (random-init weights, 5 random ED-LoRAs up~N(0,0.02^2), random text features)'
