@@ -94,7 +94,7 @@ def test_pipeline_decodes_to_pil(cuda):
     g = torch.Generator().manual_seed(3)
     lat = torch.randn(1, 4, 16, 16, generator=g)
     pe, ne = torch.randn(1, 16, 77, 768, generator=g), torch.randn(1, 77, 768, generator=g)
-    kw = dict(prompt_embeds=pe.cuda(), negative_prompt_embeds=ne.cuda(), height=128, width=128, num_inference_steps=3,
+    kw = dict(prompt_embeds=pe.cuda(), negative_prompt_embeds=ne.cuda(), height=32, width=32, num_inference_steps=3,      # vae_scale_factor = 2 for the tiny VAE
               guidance_scale=3.0)
     lat_out = pipe(latents=lat.clone(), output_type='latent', **kw).images
     imgs = pipe(latents=lat.clone(), output_type='pil', **kw).images
