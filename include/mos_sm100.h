@@ -243,6 +243,13 @@ int mos_vec_axpby(float* y, const float* x, float alpha, float beta, int64_t n, 
 int mos_lbfgs_direction(const void* const* S, const void* const* Y, const double* rho, int32_t k, const float* g,
                         float h_diag, int64_t n, float* d, double* work, float* partial, float* gtd, void* stream);
 
+/* The same recursion with the history in two rings of `slots` vectors (logical pair i = physical slot (*head_dev + i) % slots
+ * of S_ring / Y_ring [slots, n]); rho_dev [slots] (physical order) and hdiag_dev [1] live in device memory.  No launch
+ * parameter changes between iterations with the same k: the launches can be captured once in a CUDA graph (csrc/lbfgs.cu). */
+int mos_lbfgs_direction_ring(const float* S_ring, const float* Y_ring, int32_t slots, const int32_t* head_dev,
+                             const double* rho_dev, const float* hdiag_dev, int32_t k, const float* g, int64_t n, float* d,
+                             double* work, float* partial, float* gtd, void* stream);
+
 /* Native driver of one per-layer fusion solve: ONE torch.optim.LBFGS.step(closure) (strong-Wolfe line search, `history` pairs,
  * at most `max_iter` iterations and max_iter * 5 / 4 closure evaluations, tolerances 1e-16 / 1e-16, lr 1: gradient_fusion.py:76-85)
  * on f(D) = s <D, D G - 2 R> + f0 from D = 0; best_D receives the iterate with the lowest loss over all evaluations

@@ -318,18 +318,40 @@ struct LbfgsStep {
   float* partial;         // [RED_BLOCKS]
   unsigned* counter;      // [1], zero between launches
   float* gtd;             // mode 2: <g, d>
+  // ring addressing (mos_lbfgs_direction_ring): the history lives in two rings of `slots` vectors; logical pair i sits in
+  // physical slot (*head + i) % slots, rho / h_diag are read from device memory - the launch parameters of a direction are
+  // then the same on every iteration with a full history, so the 2k + 1 launches can be replayed as one CUDA graph
+  int ring, slots, upd_kind, upd_idx, dot_kind;   // kinds: 0 none, 1 = S ring, 2 = Y ring, 3 = g
+  const float *ring_s, *ring_y;
+  const int* head;
+  const double* rho_dev;  // [slots], physical
+  const float* hdiag_dev;
 };
 __global__ void __launch_bounds__(256) lbfgs_step_kernel(const LbfgsStep p) {
   __shared__ float sh[32];
   __shared__ int last;
-  const float c = (p.upd != nullptr) ? (float)(*p.coef) : 0.f;
+  const float* upd = p.upd;
+  const float* dotv = p.dotv;
+  double rho = p.rho;
+  float h_diag = p.h_diag;
+  if (p.ring) {
+    const int head = *p.head;
+    auto slot = [&](int i) { return (head + i) % p.slots; };
+    upd = p.upd_kind == 1 ? p.ring_s + (long long)slot(p.upd_idx) * p.n
+          : p.upd_kind == 2 ? p.ring_y + (long long)slot(p.upd_idx) * p.n : nullptr;
+    dotv = p.dot_kind == 1 ? p.ring_s + (long long)slot(p.idx) * p.n
+           : p.dot_kind == 2 ? p.ring_y + (long long)slot(p.idx) * p.n : p.g;
+    if (p.mode != 2) rho = p.rho_dev[slot(p.idx)];
+    h_diag = *p.hdiag_dev;
+  }
+  const float c = (upd != nullptr) ? (float)(*p.coef) : 0.f;
   float acc = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
     float v = p.first ? -1.0f * p.g[i] : p.v[i];
-    if (p.upd != nullptr) v = c * p.upd[i] + v;          // contracted to one fma, as vec_axpby_kernel's alpha * x + 1 * y
-    if (p.scale) v = p.h_diag * v;
+    if (upd != nullptr) v = c * upd[i] + v;              // contracted to one fma, as vec_axpby_kernel's alpha * x + 1 * y
+    if (p.scale) v = h_diag * v;
     p.v[i] = v;
-    acc += p.dotv[i] * v;                                // vec_dot_kernel's a[i] * b[i] with a = history vector
+    acc += dotv[i] * v;                                  // vec_dot_kernel's a[i] * b[i] with a = history vector
   }
   const float t = block_sum(acc, sh);
   if (threadIdx.x == 0) {
@@ -346,11 +368,11 @@ __global__ void __launch_bounds__(256) lbfgs_step_kernel(const LbfgsStep p) {
   if (threadIdx.x == 0) {
     const float d1 = 1.f * dot + 0.f;                    // reduce_partials_kernel: scale * t + add
     if (p.mode == 0) {
-      const double al = (double)d1 * p.rho;
+      const double al = (double)d1 * rho;
       p.al[p.idx] = al;
       *p.coef = -al;
     } else if (p.mode == 1) {
-      const double be = (double)d1 * p.rho;
+      const double be = (double)d1 * rho;
       *p.coef = p.al[p.idx] - be;
     } else {
       *p.gtd = d1;
@@ -550,6 +572,70 @@ extern "C" int mos_lbfgs_direction(const void* const* S, const void* const* Y, c
   p.scale = scale ? 1 : 0;
   p.dotv = g;
   p.mode = 2;
+  lbfgs_step_kernel<<<RED_BLOCKS, 256, 0, STREAM(stream)>>>(p);
+  MOS_CHECK_LAUNCH();
+  return MOS_OK;
+}
+
+// Same recursion with the history held in two rings (see LbfgsStep): logical pair i = physical slot (*head_dev + i) % slots of
+// S_ring / Y_ring [slots, n]; rho_dev [slots] (physical) and hdiag_dev [1] in device memory.  The 2k + 1 launches carry no
+// per-iteration host values, so a caller may capture them once in a CUDA graph and replay it while k stays the same.
+extern "C" int mos_lbfgs_direction_ring(const float* S_ring, const float* Y_ring, int32_t slots, const int32_t* head_dev,
+                                        const double* rho_dev, const float* hdiag_dev, int32_t k, const float* g, int64_t n,
+                                        float* d, double* work, float* partial, float* gtd, void* stream) {
+  MOS_CHECK_ARG(S_ring && Y_ring && head_dev && rho_dev && hdiag_dev && g && d && work && partial && gtd && n > 0 && k >= 0 &&
+                    slots >= k && slots > 0, "mos_lbfgs_direction_ring: bad arguments");
+  LbfgsStep p;
+  memset(&p, 0, sizeof(p));
+  p.v = d;
+  p.g = g;
+  p.n = n;
+  p.al = work;
+  p.coef = work + k;
+  p.partial = partial;
+  p.counter = reinterpret_cast<unsigned*>(partial + RED_BLOCKS);
+  p.gtd = gtd;
+  p.ring = 1;
+  p.slots = slots;
+  p.ring_s = S_ring;
+  p.ring_y = Y_ring;
+  p.head = head_dev;
+  p.rho_dev = rho_dev;
+  p.hdiag_dev = hdiag_dev;
+  bool first = true;
+  int pend_kind = 0, pend_idx = 0;
+  for (int i = k - 1; i >= 0; --i) {
+    p.first = first ? 1 : 0;
+    p.upd_kind = pend_kind, p.upd_idx = pend_idx;
+    p.scale = 0;
+    p.dot_kind = 1;
+    p.mode = 0;
+    p.idx = i;
+    lbfgs_step_kernel<<<RED_BLOCKS, 256, 0, STREAM(stream)>>>(p);
+    MOS_CHECK_LAUNCH();
+    first = false;
+    pend_kind = 2, pend_idx = i;
+  }
+  bool scale = true;
+  for (int i = 0; i < k; ++i) {
+    p.first = first ? 1 : 0;
+    p.upd_kind = pend_kind, p.upd_idx = pend_idx;
+    p.scale = scale ? 1 : 0;
+    p.dot_kind = 2;
+    p.mode = 1;
+    p.idx = i;
+    lbfgs_step_kernel<<<RED_BLOCKS, 256, 0, STREAM(stream)>>>(p);
+    MOS_CHECK_LAUNCH();
+    first = false;
+    scale = false;
+    pend_kind = 1, pend_idx = i;
+  }
+  p.first = first ? 1 : 0;
+  p.upd_kind = pend_kind, p.upd_idx = pend_idx;
+  p.scale = scale ? 1 : 0;
+  p.dot_kind = 3;
+  p.mode = 2;
+  p.idx = 0;
   lbfgs_step_kernel<<<RED_BLOCKS, 256, 0, STREAM(stream)>>>(p);
   MOS_CHECK_LAUNCH();
   return MOS_OK;

@@ -60,11 +60,21 @@ struct Solver {
   // device
   float *x, *g, *prev_g, *d, *xt;
   float* ring[RING];
-  std::vector<float*> free_hist;
-  std::vector<float*> S, Y;
-  std::vector<double> rho;
-  double *Y64, *loss64, *scratch64, *work;
-  float *scal, *scratch, *partial, *gtd_dev;
+  // curvature pairs in two rings of H + 1 slots (the extra slot holds the candidate pair of the current iteration): logical
+  // pair i (0 = oldest) lives in physical slot (head + i) % slots
+  float *S_ring, *Y_ring;
+  int slots, head = 0, k = 0;
+  std::vector<double> rho_phys;
+  double *Y64, *loss64, *scratch64, *work, *d_rho;
+  float *scal, *scratch, *partial, *gtd_dev, *d_hdiag;
+  int* d_head;
+  struct Stage {            // pinned: values uploaded before a direction
+    int head;
+    float hdiag;
+    double rho[64];
+  }* stage = nullptr;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
   // pinned host scalars
   double* h_d;
   float* h_f;
@@ -75,14 +85,21 @@ struct Solver {
   Solver(const mos_lbfgs_problem& p, cudaStream_t s) : P(p), st(s), stv(reinterpret_cast<void*>(s)) {
     n = (long long)p.out_f * p.in_f;
     H = p.history > 0 ? p.history : 25;
+    slots = H + 1;
+    rho_phys.assign(slots, 0.0);
+  }
+  ~Solver() {
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    if (graph) cudaGraphDestroy(graph);
   }
 
   static size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
   static size_t workspace_bytes(long long n, int H) {
     size_t b = 0;
-    b += align_up(sizeof(float) * n) * (5 + RING + 2 * (size_t)H + 2);     // + 2: the candidate pair of the current iteration
+    b += align_up(sizeof(float) * n) * (5 + RING);
+    b += 2 * align_up(sizeof(float) * n * ((size_t)H + 1));  // S / Y rings (H pairs + the candidate of the current iteration)
     b += align_up(sizeof(double) * n);                       // Y64
-    b += align_up(sizeof(double) * (1 + 256 + 64));          // loss64, scratch64, work
+    b += align_up(sizeof(double) * (1 + 256 + 64 + 64));     // loss64, scratch64, work, rho
     b += align_up(sizeof(float) * (8 + 256 + 260 + 4));      // scal, scratch, partial, gtd
     return b;
   }
@@ -95,17 +112,21 @@ struct Solver {
     };
     x = takef(n), g = takef(n), prev_g = takef(n), d = takef(n), xt = takef(n);
     for (int i = 0; i < RING; ++i) ring[i] = takef(n);
-    for (int i = 0; i < 2 * H + 2; ++i) free_hist.push_back(takef(n));
+    S_ring = takef(n * (long long)slots);
+    Y_ring = takef(n * (long long)slots);
     Y64 = reinterpret_cast<double*>(p);
     p += align_up(sizeof(double) * n);
     loss64 = reinterpret_cast<double*>(p);
     scratch64 = loss64 + 1;
     work = scratch64 + 256;
-    p += align_up(sizeof(double) * (1 + 256 + 64));
+    d_rho = work + 64;
+    p += align_up(sizeof(double) * (1 + 256 + 64 + 64));
     scal = reinterpret_cast<float*>(p);
     scratch = scal + 8;
     partial = scratch + 256;
     gtd_dev = partial + 260;
+    d_hdiag = scal + 4;
+    d_head = reinterpret_cast<int*>(scal + 5);
   }
 
 #define CK(call)              \
@@ -260,10 +281,9 @@ struct Solver {
         copy(d, g);
         axpby(d, g, -1.0, 0.0);                                          // d = -g
       } else {
-        float *y = free_hist.back();
-        free_hist.pop_back();
-        float* s = free_hist.back();
-        free_hist.pop_back();
+        const int cand = (head + k) % slots;                             // physical slot of the candidate pair
+        float* y = Y_ring + (long long)cand * n;
+        float* s = S_ring + (long long)cand * n;
         copy(y, g);
         axpby(y, prev_g, -1.0, 1.0);                                     // y = g - prev_g
         axpby(s, d, t, 0.0);                                             // s = t d
@@ -272,20 +292,31 @@ struct Solver {
         fetch(2, false);
         const double ys = (double)h_f[0], yy = (double)h_f[1];
         if (ys > 1e-10) {
-          if ((int)S.size() == H) {
-            free_hist.push_back(S.front());
-            free_hist.push_back(Y.front());
-            S.erase(S.begin()), Y.erase(Y.begin()), rho.erase(rho.begin());
-          }
-          S.push_back(s), Y.push_back(y), rho.push_back(1.0 / ys);
+          if (k == H) head = (head + 1) % slots;                          // history full: the oldest pair leaves
+          else ++k;
+          rho_phys[cand] = 1.0 / ys;
           h_diag = ys / yy;
-        } else {
-          free_hist.push_back(s);
-          free_hist.push_back(y);
         }
-        const int k = (int)S.size();
-        CK(mos_lbfgs_direction(reinterpret_cast<const void* const*>(S.data()), reinterpret_cast<const void* const*>(Y.data()),
-                               rho.data(), k, g, (float)h_diag, n, d, work, partial, gtd_dev, stv));
+        stage->head = head;
+        stage->hdiag = (float)h_diag;
+        for (int i = 0; i < slots; ++i) stage->rho[i] = rho_phys[i];
+        CKC(cudaMemcpyAsync(d_hdiag, &stage->hdiag, sizeof(float), cudaMemcpyHostToDevice, st));
+        CKC(cudaMemcpyAsync(d_head, &stage->head, sizeof(int), cudaMemcpyHostToDevice, st));
+        CKC(cudaMemcpyAsync(d_rho, stage->rho, sizeof(double) * slots, cudaMemcpyHostToDevice, st));
+        if (k == H && rc == MOS_OK) {
+          // full history: the 2H + 1 launches of the direction have the same parameters on every iteration -> one graph launch
+          if (graph_exec == nullptr) {
+            CKC(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            CK(mos_lbfgs_direction_ring(S_ring, Y_ring, slots, d_head, d_rho, d_hdiag, k, g, n, d, work, partial, gtd_dev, stv));
+            cudaGraph_t gr = nullptr;
+            if (cudaStreamEndCapture(st, &gr) != cudaSuccess || gr == nullptr) rc = rc == MOS_OK ? MOS_ECUDA : rc;
+            graph = gr;
+            if (rc == MOS_OK) CKC(cudaGraphInstantiate(&graph_exec, graph, 0));
+          }
+          if (rc == MOS_OK) CKC(cudaGraphLaunch(graph_exec, st));
+        } else {
+          CK(mos_lbfgs_direction_ring(S_ring, Y_ring, slots, d_head, d_rho, d_hdiag, k, g, n, d, work, partial, gtd_dev, stv));
+        }
       }
       copy(prev_g, g);
       prev_loss = loss;
@@ -323,9 +354,10 @@ int solve_one(const mos_lbfgs_problem& p, void* workspace, cudaStream_t st) {
   Solver s(p, st);
   s.carve(workspace);
   void* pinned = nullptr;
-  if (cudaHostAlloc(&pinned, 64, cudaHostAllocDefault) != cudaSuccess) return MOS_ECUDA;
+  if (cudaHostAlloc(&pinned, 64 + sizeof(Solver::Stage), cudaHostAllocDefault) != cudaSuccess) return MOS_ECUDA;
   s.h_d = reinterpret_cast<double*>(pinned);
   s.h_f = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(pinned) + 16);
+  s.stage = reinterpret_cast<Solver::Stage*>(reinterpret_cast<uint8_t*>(pinned) + 64);
   s.run();
   cudaStreamSynchronize(st);
   cudaFreeHost(pinned);
