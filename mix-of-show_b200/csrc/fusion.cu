@@ -456,7 +456,7 @@ extern "C" int mos_dgemm_mixed(const float* A, const double* B, double* C, int32
     tile_env = v;
   }
   int tile = tile_env;
-  if (tile == 0) tile = (ceil_div(N, 64) * ceil_div(M, 64) < 2 * 148) ? 1 : 2;   // too few 64-row tiles for two CTAs per SM
+  if (tile == 0) tile = 2;   // 64 x 64: best under concurrent solves (config 3 A/B: 2.16 s vs 2.76 s (32 x 64) and 2.26 s (64 x 128))
   if (tile == 1) {
     dim3 grid((unsigned)ceil_div(N, 64), (unsigned)ceil_div(M, 32));
     dgemm_mixed_kernel<32, 64><<<grid, 256, smem(32, 64), STREAM(stream)>>>(A, B, C, M, N, K);

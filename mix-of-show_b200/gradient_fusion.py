@@ -522,9 +522,13 @@ def merge_spatial_attention(unet_state_dict, unet_spatial_attn_list, alphas, con
     if block_out is not None:
         kw = dict(block_out=block_out, layers=layers)
     grams, merged_w = [], []
+    eng = None
     for c, tuned in enumerate(unet_spatial_attn_list):
-        eng = UNetEngine(unet_state_dict, 1, H, Wd, lora=tuned, lora_alpha=alphas[c], merge_lora=True, device=device,
-                         use_graph=False, **kw)
+        if eng is None:
+            eng = UNetEngine(unet_state_dict, 1, H, Wd, lora=tuned, lora_alpha=alphas[c], merge_lora=True, device=device,
+                             use_graph=False, **kw)
+        else:
+            eng.set_merged_lora(tuned, alphas[c])       # only the LoRA'd projections are re-packed
         rec = GramRecorder(device)
         eng.gram_rec = rec
         nx = len(eng.xattn_names)

@@ -76,6 +76,7 @@ class UNetEngine:
         self._merge = lora if merge_lora else None
         self.sd = state_dict
         self.w = {}
+        self._pack_args = {}
         self.bufs = {}
         self.launches = 0
         self.xattn_names = cross_attention_names(block_out, layers)
@@ -108,6 +109,7 @@ class UNetEngine:
 
     def _pack_linear(self, key, modules, geglu=False, conv3=False):
         """modules: list of module names whose weights are concatenated along N (q|k|v fusion)."""
+        self._pack_args[key] = (list(modules), geglu, conv3)
         Ws, bs, downs, ups = [], [], [], []
         any_lora = False
         for m in modules:
@@ -345,6 +347,21 @@ class UNetEngine:
             return
         ops.layernorm(x, g, b, y, M=M, C=C, ldx=x.stride(0), ldy=y.stride(0))
         self.launches += 1
+
+    def set_merged_lora(self, lora, lora_alpha=1.0):
+        """Gradient fusion runs the same UNet once per concept with that concept's LoRA folded into the weights
+        (gradient_fusion.py:700-712): re-pack only the entries that contain a LoRA'd module instead of building a new
+        engine (packing all 860 M parameters costs ~0.5 s)."""
+        assert self.lora is None, 'set_merged_lora: the engine was built with an un-merged LoRA'
+        old = self._merge or {}
+        self._merge, self.lora_alpha = lora, float(lora_alpha)
+        suffix = '.lora_down.weight'
+        targets = {k[:-len(suffix)] for src in (old, lora or {}) for k in src if k.endswith(suffix)}
+        for key, (modules, geglu, conv3) in list(self._pack_args.items()):
+            if any(m in targets for m in modules):
+                self._pack_linear(key, modules, geglu, conv3)
+        self.graph = None
+        self._text_version = None       # cached text K/V projections depend on the packed cross-attention weights
 
     # ------------------------------------------------------------------------------------------ blocks
     def resnet(self, name, x, out, h, w, cin, cout):
