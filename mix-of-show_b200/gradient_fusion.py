@@ -528,7 +528,7 @@ def merge_spatial_attention(unet_state_dict, unet_spatial_attn_list, alphas, con
             eng = UNetEngine(unet_state_dict, 1, H, Wd, lora=tuned, lora_alpha=alphas[c], merge_lora=True, device=device,
                              use_graph=False, **kw)
         else:
-            eng.set_merged_lora(tuned, alphas[c])       # only the LoRA'd projections are re-packed
+            eng.set_merged_lora(tuned, alphas[c], state_dict=unet_state_dict)   # only the LoRA'd projections are re-packed
         rec = GramRecorder(device)
         eng.gram_rec = rec
         nx = len(eng.xattn_names)

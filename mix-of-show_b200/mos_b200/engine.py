@@ -348,11 +348,14 @@ class UNetEngine:
         ops.layernorm(x, g, b, y, M=M, C=C, ldx=x.stride(0), ldy=y.stride(0))
         self.launches += 1
 
-    def set_merged_lora(self, lora, lora_alpha=1.0):
+    def set_merged_lora(self, lora, lora_alpha=1.0, state_dict=None):
         """Gradient fusion runs the same UNet once per concept with that concept's LoRA folded into the weights
         (gradient_fusion.py:700-712): re-pack only the entries that contain a LoRA'd module instead of building a new
         engine (packing all 860 M parameters costs ~0.5 s)."""
         assert self.lora is None, 'set_merged_lora: the engine was built with an un-merged LoRA'
+        if state_dict is None:
+            raise ValueError('set_merged_lora needs the fp32 state_dict again (the engine keeps no master copy)')
+        self.sd = state_dict
         old = self._merge or {}
         self._merge, self.lora_alpha = lora, float(lora_alpha)
         suffix = '.lora_down.weight'
@@ -360,6 +363,7 @@ class UNetEngine:
         for key, (modules, geglu, conv3) in list(self._pack_args.items()):
             if any(m in targets for m in modules):
                 self._pack_linear(key, modules, geglu, conv3)
+        self.sd = None
         self.graph = None
         self._text_version = None       # cached text K/V projections depend on the packed cross-attention weights
 
