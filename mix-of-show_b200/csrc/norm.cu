@@ -706,7 +706,13 @@ extern "C" int mos_groupnorm_fwd(const void* x, int64_t ldx, int32_t B, int32_t 
     const int vec = (cpg % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0) ? 4 : 2;
     const long long slab = (long long)HW * cpg * 2;
     int k = 1;
-    while (k < 8 && HW / (2 * k) >= 16 && (slab / k > 48 * 1024 || (long long)B * GN_GROUPS * k < 148)) k *= 2;
+    static int min_ctas = 0;
+    if (min_ctas == 0) {
+      const char* e = getenv("MOS_GN_MIN_CTAS");      // clusters are widened until the grid has at least this many CTAs
+      min_ctas = e ? atoi(e) : 148;
+      if (min_ctas < 1) min_ctas = 148;
+    }
+    while (k < 8 && HW / (2 * k) >= 16 && (slab / k > 48 * 1024 || (long long)B * GN_GROUPS * k < min_ctas)) k *= 2;
     const int rows_per_cta = (int)ceil_div(HW, k);
     const size_t smem = (size_t)rows_per_cta * cpg * 2;
     if (smem <= 200 * 1024 && cpg % 2 == 0 && ldx % 2 == 0 && ldy % 2 == 0) {
