@@ -709,8 +709,8 @@ extern "C" int mos_groupnorm_fwd(const void* x, int64_t ldx, int32_t B, int32_t 
     static int min_ctas = 0;
     if (min_ctas == 0) {
       const char* e = getenv("MOS_GN_MIN_CTAS");      // clusters are widened until the grid has at least this many CTAs
-      min_ctas = e ? atoi(e) : 148;
-      if (min_ctas < 1) min_ctas = 148;
+      min_ctas = e ? atoi(e) : 296;                  // two CTAs per SM: 6.10 vs 6.23 ms per step with 148 (profiles/README.md)
+      if (min_ctas < 1) min_ctas = 296;
     }
     while (k < 8 && HW / (2 * k) >= 16 && (slab / k > 48 * 1024 || (long long)B * GN_GROUPS * k < min_ctas)) k *= 2;
     const int rows_per_cta = (int)ceil_div(HW, k);
