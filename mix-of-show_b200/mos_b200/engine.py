@@ -30,6 +30,7 @@ FUSED_SPLITK = os.environ.get('MOS_SPLITK_FUSED', '0') == '1'
 # streams 1.7 GB of weights through a mostly idle HBM, the 126 MB L2 holds any single layer.  MOS_L2_PREFETCH=0/1.
 L2_PREFETCH = os.environ.get('MOS_L2_PREFETCH', '0') == '1'
 L2_PREFETCH_MAX_BYTES = 48 << 20
+SPLITK_MIN_KB = int(os.environ.get('MOS_SPLITK_MIN_KB', '8'))      # fewest 64-deep k-blocks a split-K slice may get
 SKIP_CH = [320, 320, 320, 320, 640, 640, 640, 1280, 1280, 1280, 1280, 1280]
 
 
@@ -275,9 +276,9 @@ class UNetEngine:
     # ------------------------------------------------------------------------------------------ op helpers
     def _splits(self, M, N, kb_total):
         tiles = _r(M, 128) // 128 * (N // 160)
-        if tiles >= 96 or kb_total < 16:
+        if tiles >= 96 or kb_total < 2 * SPLITK_MIN_KB:
             return 1
-        s = max(1, min(max(1, 148 // tiles), kb_total // 8, 16))
+        s = max(1, min(max(1, 148 // tiles), kb_total // SPLITK_MIN_KB, 16))
         per = -(-kb_total // s)          # k blocks per split
         return -(-kb_total // per)       # normalised so that no split is empty
 
