@@ -150,17 +150,11 @@ struct Solver {
   }
   void copy(float* dst, const float* src) { CKC(cudaMemcpyAsync(dst, src, sizeof(float) * n, cudaMemcpyDeviceToDevice, st)); }
   void axpby(float* y, const float* xx, double a, double b) { CK(mos_vec_axpby(y, xx, (float)a, (float)b, n, stv)); }
-  double dot(const float* a, const float* b) {
-    CK(mos_vec_dot(a, b, n, scal, scratch, stv));
-    fetch(1, false);
-    return (double)h_f[0];
-  }
   double absmax(const float* a, double scale) {
     CK(mos_vec_absmax(a, n, (float)scale, scal, scratch, stv));
     fetch(1, false);
     return (double)h_f[0];
   }
-  const float* gptr(int slot) const { return slot < 0 ? g : ring[slot]; }
 
   // closure at `pt` (gradient into `grad`) + <grad, dvec> (dvec may be NULL): loss, gtd with ONE synchronisation
   void closure(const float* pt, float* grad, const float* dvec, double& loss, double& gtd) {

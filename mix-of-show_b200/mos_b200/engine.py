@@ -20,9 +20,6 @@ from ._lib import MOS_SEG_ROWS, MOS_SEG_TRANSPOSED
 
 BF16 = torch.bfloat16       # weights (and the training engine's activations)
 F16 = torch.float16
-# Experiment (opt-in, MOS_GEMM_PREFETCH_W=1): request the first weight tiles of every GEMM before griddepcontrol.wait.
-# Measured on B200 in round 1: no gain for the batch-2 denoise step (6.41 -> 6.55 ms together with a cheaper erf), so off.
-PREFETCH_W = os.environ.get('MOS_GEMM_PREFETCH_W') == '1'      # (kept for the bench history; the library ignores w_static)
 # split-K GEMMs finalize in-kernel (mos_gemm_args.tile_counters); MOS_SPLITK_FUSED=0 restores the separate
 # mos_splitk_finalize launch (A/B timing, profiles/README.md)
 FUSED_SPLITK = os.environ.get('MOS_SPLITK_FUSED', '0') == '1'
