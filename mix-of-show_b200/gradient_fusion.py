@@ -523,7 +523,18 @@ def merge_spatial_attention(unet_state_dict, unet_spatial_attn_list, alphas, con
         kw = dict(block_out=block_out, layers=layers)
     grams, merged_w = [], []
     eng = None
+    prof = os.environ.get('MOS_FUSION_PROFILE') == '1'       # stage timing printout (tools/config_bench.py)
+    import time
+    marks = []
+
+    def mark(label):
+        if prof:
+            torch.cuda.synchronize()
+            marks.append((label, time.perf_counter()))
+
+    mark('start')
     for c, tuned in enumerate(unet_spatial_attn_list):
+        mark(f'concept {c}: pack')
         if eng is None:
             eng = UNetEngine(unet_state_dict, 1, H, Wd, lora=tuned, lora_alpha=alphas[c], merge_lora=True, device=device,
                              use_graph=False, **kw)
@@ -539,6 +550,7 @@ def merge_spatial_attention(unet_state_dict, unet_spatial_attn_list, alphas, con
         x0_prev = torch.zeros_like(latents)
         eng.in_ehs.copy_(ehs_to_layer_major(concept_embeds[c].to(device), nx))
         eng.in_latents.copy_(latents)
+        mark(f'concept {c}: forwards')
         for i, t in enumerate(sched.timesteps):
             eng.in_t.fill_(float(t))
             eng.run()
@@ -547,6 +559,7 @@ def merge_spatial_attention(unet_state_dict, unet_spatial_attn_list, alphas, con
         grams.append(rec)
         merged_w.append(tuned)
         eng.gram_rec = None
+    mark('job assembly')
     names = sorted({k.replace('.lora_down', '').replace('.lora_up', '') for t in unet_spatial_attn_list for k in t})
     jobs = []
     for name in names:                                          # e.g. '...attn1.to_q.weight'
@@ -570,7 +583,16 @@ def merge_spatial_attention(unet_state_dict, unet_spatial_attn_list, alphas, con
             vv += float((Wc.double() * WG.double()).sum())
             n += grams[c].rows[rec_key]
         jobs.append((name, G, Cm, vv, n, W0, tuple(unet_state_dict[name].shape)))
-    return solve_all(jobs, optimize_iters)
+    mark('solve')
+    out = solve_all(jobs, optimize_iters)
+    mark('end')
+    if prof:
+        agg = {}
+        for (label, t0), (_, t1) in zip(marks[:-1], marks[1:]):
+            key = label.split(': ')[-1]
+            agg[key] = agg.get(key, 0.0) + (t1 - t0)
+        print('merge_spatial_attention seconds: ' + ', '.join(f'{k} {v:.2f}' for k, v in agg.items()), flush=True)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ orchestration (host)
