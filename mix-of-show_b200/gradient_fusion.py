@@ -488,30 +488,20 @@ class GramRecorder:
     cores (transpose -> tcgen05 GEMM with fp32 accumulate output)."""
 
     def __init__(self, device):
-        self.dev, self.G, self.rows_per_forward, self._xt = device, {}, {}, {}
-        self.forwards = 0          # counted by the caller (one per recorded UNet forward): under a CUDA graph this callable
-        #                            only runs at capture time, the accumulation itself is replayed on the device
-
-    @property
-    def rows(self):
-        return {k: v * self.forwards for k, v in self.rows_per_forward.items()}
-
-    def reset(self):
-        """zero the accumulated Gram matrices (after the warm-up / capture pass of a graphed engine)"""
-        for G in self.G.values():
-            G.zero_()
-        self.forwards = 0
+        self.dev, self.G, self.rows, self._xt = device, {}, {}, {}
 
     def __call__(self, key, A, M, C):
         G = self.G.get(key)
-        if G is None:
+        first = G is None
+        if first:
             G = self.G[key] = torch.zeros(C, C, device=self.dev, dtype=F32)
-        self.rows_per_forward[key] = M
-        xt = self._xt.get((C, M, A.dtype))           # shared scratch: the recorded GEMMs of a forward run in stream order
+            self.rows[key] = 0
+        xt = self._xt.get((C, M, A.dtype))
         if xt is None:
             xt = self._xt[(C, M, A.dtype)] = torch.empty(C, M, device=self.dev, dtype=A.dtype)
         ops.transpose_bf16(A, xt, rows=M, C=C, ldx=A.stride(0))
         ops.gemm(xt, xt, G, out_f32=True, accumulate=True)
+        self.rows[key] += M
 
 
 SPATIAL_KEYS = (('attn1.to_q', 'attn1.in'), ('attn1.to_k', 'attn1.in'), ('attn1.to_v', 'attn1.in'),
@@ -547,7 +537,7 @@ def merge_spatial_attention(unet_state_dict, unet_spatial_attn_list, alphas, con
         mark(f'concept {c}: pack')
         if eng is None:
             eng = UNetEngine(unet_state_dict, 1, H, Wd, lora=tuned, lora_alpha=alphas[c], merge_lora=True, device=device,
-                             use_graph=True, **kw)
+                             use_graph=False, **kw)
         else:
             eng.set_merged_lora(tuned, alphas[c], state_dict=unet_state_dict)   # only the LoRA'd projections are re-packed
         rec = GramRecorder(device)
@@ -561,15 +551,9 @@ def merge_spatial_attention(unet_state_dict, unet_spatial_attn_list, alphas, con
         eng.in_ehs.copy_(ehs_to_layer_major(concept_embeds[c].to(device), nx))
         eng.in_latents.copy_(latents)
         mark(f'concept {c}: forwards')
-        # the recorded forward (UNet + 96 transpose / Gram-accumulate pairs) is captured once per concept: the first run() is
-        # the warm-up + capture + one replay, its two accumulations are discarded
-        eng.in_t.fill_(float(sched.timesteps[0]))
-        eng.run()
-        rec.reset()
         for i, t in enumerate(sched.timesteps):
             eng.in_t.fill_(float(t))
             eng.run()
-            rec.forwards += 1
             ops.cfg_dpmpp_step(eng.out_eps, latents, x0_prev, eng.in_latents.view(-1), cfg=False, guidance=1.0,
                                coef=sched.coefficients(i))
         grams.append(rec)
@@ -587,7 +571,7 @@ def merge_spatial_attention(unet_state_dict, unet_spatial_attn_list, alphas, con
         d_in = W0.shape[1]
         G = torch.zeros(d_in, d_in, device=device)
         Cm = torch.zeros(W0.shape[0], d_in, device=device)
-        vv, n = torch.zeros((), device=device, dtype=torch.float64), 0
+        vv, n = 0.0, 0
         for c, tuned in enumerate(unet_spatial_attn_list):
             Gc = grams[c].G[rec_key]
             Wc = _merged(W0, tuned[mod + '.lora_down.weight'], tuned[mod + '.lora_up.weight'], alphas[c], device) \
@@ -596,9 +580,9 @@ def merge_spatial_attention(unet_state_dict, unet_spatial_attn_list, alphas, con
             ops.sgemm_nn(Wc.contiguous(), Gc, WG)
             ops.vec_axpby(G.view(-1), Gc.view(-1), 1.0, 1.0)
             ops.vec_axpby(Cm.view(-1), WG.view(-1), 1.0, 1.0)
-            vv = vv + (Wc.double() * WG.double()).sum()        # fp64 on the device, same order: one host read per layer
+            vv += float((Wc.double() * WG.double()).sum())
             n += grams[c].rows[rec_key]
-        jobs.append((name, G, Cm, float(vv), n, W0, tuple(unet_state_dict[name].shape)))
+        jobs.append((name, G, Cm, vv, n, W0, tuple(unet_state_dict[name].shape)))
     mark('solve')
     out = solve_all(jobs, optimize_iters)
     mark('end')

@@ -118,45 +118,6 @@ def test_native_lbfgs_driver_bit_identical_to_python_driver(cuda, out_f, in_f, n
         assert torch.equal(v.view(torch.int32), a.cpu().view(torch.int32))
 
 
-def test_gram_recording_under_cuda_graph_equals_eager(cuda):
-    """merge_spatial_attention replays the recorded forward (UNet + transpose / Gram-accumulate pairs) as a CUDA graph: the
-    accumulated Gram matrices and row counts must equal the eager recording bit for bit (warm-up / capture passes discarded
-    by GramRecorder.reset)."""
-    import gradient_fusion as gf
-    from mos_b200.engine import UNetEngine, ehs_to_layer_major
-    from oracle import unet as ou
-    ref = ou.build_unet(0, ou.TINY)
-    sd = {k: v.detach() for k, v in ref.state_dict().items()}
-    kw = dict(block_out=ou.TINY['block_out_channels'], layers=ou.TINY['layers_per_block'])
-    g = torch.Generator().manual_seed(5)
-    ehs = torch.randn(1, 16, 77, 768, generator=g)
-    lats = [torch.randn(1, 4, 32, 32, generator=g) for _ in range(3)]
-    out = {}
-    for mode in ('eager', 'graph'):
-        eng = UNetEngine(sd, 1, 32, 32, use_graph=(mode == 'graph'), **kw)
-        rec = gf.GramRecorder(torch.device('cuda'))
-        eng.gram_rec = rec
-        nx = len(eng.xattn_names)
-        eng.in_ehs.copy_(ehs_to_layer_major(ehs[:, :nx].cuda(), nx))
-        eng.in_t.fill_(500.0)
-        if mode == 'graph':
-            eng.in_latents.copy_(lats[0].cuda())
-            eng.run()                 # warm-up + capture + first replay
-            rec.reset()
-        for i, l in enumerate(lats):
-            eng.in_latents.copy_(l.cuda())
-            eng.in_t.fill_(900.0 - 300.0 * i)
-            eng.run()
-            rec.forwards += 1
-        torch.cuda.synchronize()
-        out[mode] = ({k: v.clone() for k, v in rec.G.items()}, dict(rec.rows))
-    (Ge, re_), (Gg, rg) = out['eager'], out['graph']
-    assert re_ == rg and Ge.keys() == Gg.keys() and len(Ge) > 0
-    for k in Ge:
-        assert torch.equal(Ge[k], Gg[k]), k
-        assert Ge[k].abs().sum().item() > 0
-
-
 def test_dgemm_mixed_tilings(cuda):
     """the fp64 closure product in both tilings (32- and 64-row CTA tiles) vs torch fp64"""
     from mos_b200 import ops
