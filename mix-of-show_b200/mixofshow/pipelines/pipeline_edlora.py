@@ -14,7 +14,6 @@ import torch
 from mixofshow.models.edlora import (revise_edlora_unet_attention_controller_forward,
                                      revise_edlora_unet_attention_forward)
 from mos_b200 import ops
-from mos_b200.engine import ehs_to_layer_major
 from mos_b200.scheduler import DPMSolverPP2M
 
 

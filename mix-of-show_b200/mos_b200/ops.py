@@ -7,8 +7,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import (MOS_OUT_BF16, MOS_OUT_F32, MOS_OUT_HEADS, MOS_SEG_ROWS, MOS_SEG_TRANSPOSED, GemmArgs, act_dtype, check,
-                   current_stream, ptr)
+from ._lib import MOS_OUT_BF16, MOS_OUT_F32, MOS_OUT_HEADS, GemmArgs, act_dtype, check, current_stream, ptr
 
 BN = 160
 BK = 64
